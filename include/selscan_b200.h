@@ -1,0 +1,115 @@
+/*
+ * selscan_b200.h -- C ABI of the B200-native selective scan (libselscan_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path of Grozta/Mamba-UNet:
+ *   SS2D.forward_core            code/networks/mamba_sys.py:396-436
+ *   -> selective_scan_fn         mamba/mamba_ssm/ops/selective_scan_interface.py:77-83
+ *   -> selective_scan_cuda.fwd   mamba/csrc/selective_scan/selective_scan.cpp:226-336
+ *   -> selective_scan_cuda.bwd   mamba/csrc/selective_scan/selective_scan.cpp:338-492
+ * The entry points below are what the reference's pybind module (selective_scan.cpp:494-497) binds, with
+ * ATen tensors replaced by raw device pointers + sizes + element strides (the reference's own
+ * SSMParamsBase / SSMParamsBwd, selective_scan.h:26-101, minus the torch types).
+ *
+ * Contract
+ *  - Every pointer is a DEVICE pointer on the current CUDA device.  The caller allocates every output
+ *    and scratch buffer and owns it; the library never allocates, frees or caches device memory.
+ *  - Launches go to `stream` (a cudaStream_t passed as void*); nothing synchronises, nothing changes the
+ *    current device.  Re-entrant: safe from the main thread and autograd worker threads at once.
+ *  - Return value: 0 ok; < 0 invalid argument (message via selscan_b200_last_error(), thread local);
+ *    > 0 the cudaError_t of a failed launch.
+ *  - dtype: fp32 real (u, delta, A, B, C, D, z, delta_bias).  B and C are "variable" (input dependent):
+ *    (batch, ngroups, dstate, seqlen), any element strides; channel d uses group d / (dim / ngroups)
+ *    (selective_scan_fwd_kernel.cuh:99).  dstate <= 16 (Mamba-UNet uses 16).  fp16/bf16 I/O, complex A and
+ *    constant (dim, dstate) B/C -- which Mamba-UNet never passes -- are rejected with a message.
+ *  - u, delta, z, out, dout, du, ddelta, dz have unit stride along seqlen (the reference requires the
+ *    same, selective_scan.cpp:252-253); batch/channel strides are free.
+ */
+#ifndef SELSCAN_B200_H_
+#define SELSCAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SELSCAN_B200_ABI_VERSION 1
+/* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
+#define SELSCAN_B200_CKPT_INTERVAL 8
+/* states are padded to this count inside the kernels and in the checkpoint buffer */
+#define SELSCAN_B200_STATE_PAD 16
+
+/* replaces selective_scan_cuda.fwd(u, delta, A, B, C, D_, z_, delta_bias_, delta_softplus)
+ * (selective_scan.cpp:226-232) */
+typedef struct selscan_fwd_args {
+  int32_t batch, dim, seqlen, dstate, ngroups;
+  int32_t delta_softplus;            /* 1: delta = softplus(delta + delta_bias), threshold 20 */
+  const float* u;                    /* (batch, dim, seqlen) */
+  const float* delta;                /* (batch, dim, seqlen) */
+  const float* A;                    /* (dim, dstate) */
+  const float* B;                    /* (batch, ngroups, dstate, seqlen) */
+  const float* C;                    /* (batch, ngroups, dstate, seqlen) */
+  const float* D;                    /* (dim) or NULL */
+  const float* z;                    /* (batch, dim, seqlen) or NULL */
+  const float* delta_bias;           /* (dim) or NULL */
+  int64_t u_batch_stride, u_d_stride;
+  int64_t delta_batch_stride, delta_d_stride;
+  int64_t A_d_stride, A_n_stride;
+  int64_t B_batch_stride, B_group_stride, B_n_stride, B_l_stride;
+  int64_t C_batch_stride, C_group_stride, C_n_stride, C_l_stride;
+  int64_t z_batch_stride, z_d_stride;
+  float* out;                        /* (batch, dim, seqlen): y + D*u, NOT gated */
+  int64_t out_batch_stride, out_d_stride;
+  float* out_z;                      /* (batch, dim, seqlen): out * silu(z); required iff z != NULL */
+  int64_t out_z_batch_stride, out_z_d_stride;
+  float* last_state;                 /* (batch, dim, dstate) contiguous, or NULL */
+  float* ckpt;                       /* selscan_b200_ckpt_elems() floats, or NULL (inference) */
+} selscan_fwd_args;
+
+/* replaces selective_scan_cuda.bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_,
+ * delta_softplus, recompute_out_z) (selective_scan.cpp:338-349) */
+typedef struct selscan_bwd_args {
+  int32_t batch, dim, seqlen, dstate, ngroups;
+  int32_t delta_softplus;
+  const float* u;
+  const float* delta;
+  const float* A;
+  const float* B;
+  const float* C;
+  const float* D;                    /* or NULL */
+  const float* z;                    /* or NULL */
+  const float* delta_bias;           /* or NULL */
+  const float* dout;                 /* (batch, dim, seqlen) */
+  const float* out;                  /* ungated forward output; required iff z != NULL */
+  const float* ckpt;                 /* written by selscan_b200_fwd on the same inputs */
+  int64_t u_batch_stride, u_d_stride;
+  int64_t delta_batch_stride, delta_d_stride;
+  int64_t A_d_stride, A_n_stride;
+  int64_t B_batch_stride, B_group_stride, B_n_stride, B_l_stride;
+  int64_t C_batch_stride, C_group_stride, C_n_stride, C_l_stride;
+  int64_t z_batch_stride, z_d_stride;
+  int64_t dout_batch_stride, dout_d_stride;
+  int64_t out_batch_stride, out_d_stride;
+  float* du;                         /* (batch, dim, seqlen) contiguous, fully written */
+  float* ddelta;                     /* (batch, dim, seqlen) contiguous, fully written */
+  float* dz;                         /* (batch, dim, seqlen) contiguous; required iff z != NULL */
+  float* dA;                         /* (dim, dstate)                  contiguous, ZERO-INITIALISED by caller */
+  float* dB;                         /* (batch, ngroups, dstate, seqlen) contiguous, ZERO-INITIALISED */
+  float* dC;                         /* (batch, ngroups, dstate, seqlen) contiguous, ZERO-INITIALISED */
+  float* dD;                         /* (dim) ZERO-INITIALISED; required iff D != NULL */
+  float* ddelta_bias;                /* (dim) ZERO-INITIALISED; required iff delta_bias != NULL */
+} selscan_bwd_args;
+
+int selscan_b200_abi_version(void);
+const char* selscan_b200_last_error(void);
+
+/* number of floats the `ckpt` scratch of one (batch, dim, seqlen, dstate) problem needs (may be 0) */
+int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+
+int selscan_b200_fwd(const selscan_fwd_args* args, void* stream);
+int selscan_b200_bwd(const selscan_bwd_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELSCAN_B200_H_ */

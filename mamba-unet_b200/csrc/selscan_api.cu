@@ -1,0 +1,113 @@
+// C ABI of libselscan_b200.so (declared in include/selscan_b200.h): argument validation + dispatch.
+// Mirrors the host side of the reference extension,
+// /root/reference/mamba/csrc/selective_scan/selective_scan.cpp:226-336 (fwd) and :338-492 (bwd):
+// same shape / stride / presence rules, reported through return codes instead of TORCH_CHECK.
+#include <cstdarg>
+#include <cstdio>
+
+#include "selscan_common.cuh"
+#include "selscan_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool m4(int64_t s) { return (s & 3) == 0; }
+
+// shape rules shared by fwd and bwd (selective_scan.cpp:233-305, 351-447)
+template <typename Args>
+int check_common(const Args& a, const char* who) {
+  if (a.batch < 0 || a.dim <= 0 || a.seqlen < 0) return fail("%s: bad sizes batch=%d dim=%d seqlen=%d", who, a.batch, a.dim, a.seqlen);
+  if (a.dstate < 1) return fail("%s: dstate must be >= 1 (got %d)", who, a.dstate);
+  if (a.dstate > SELSCAN_B200_STATE_PAD)
+    return fail("%s: selective_scan only supports state dimension <= %d in this build (got %d); the reference allows 256",
+                who, SELSCAN_B200_STATE_PAD, a.dstate);
+  if (a.ngroups < 1 || a.dim % a.ngroups != 0) return fail("%s: dim (%d) must be divisible by ngroups (%d)", who, a.dim, a.ngroups);
+  if (!a.u || !a.delta || !a.A || !a.B || !a.C) return fail("%s: u, delta, A, B, C must not be NULL", who);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) int selscan_b200_abi_version(void) { return SELSCAN_B200_ABI_VERSION; }
+
+__attribute__((visibility("default"))) const char* selscan_b200_last_error(void) { return g_err; }
+
+__attribute__((visibility("default"))) int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
+  (void)dstate;
+  if (batch <= 0 || dim <= 0 || seqlen <= 0) return 0;
+  const int64_t n_ckpt = (seqlen + SELSCAN_B200_CKPT_INTERVAL - 1) / SELSCAN_B200_CKPT_INTERVAL - 1;
+  return (int64_t)batch * dim * n_ckpt * SELSCAN_B200_STATE_PAD;
+}
+
+__attribute__((visibility("default"))) int selscan_b200_fwd(const selscan_fwd_args* args, void* stream) {
+  if (!args) return fail("selscan_b200_fwd: args is NULL");
+  const selscan_fwd_args& a = *args;
+  if (int rc = check_common(a, "selscan_b200_fwd")) return rc;
+  if (!a.out) return fail("selscan_b200_fwd: out must not be NULL");
+  if (a.z && !a.out_z) return fail("selscan_b200_fwd: out_z is required when z is given");
+  selscan::FwdLaunch p;
+  p.a = a;
+  p.dim_per_group = a.dim / a.ngroups;
+  p.n_ckpt = (a.seqlen + selscan::kCkptInterval - 1) / selscan::kCkptInterval - 1;
+  if (p.n_ckpt < 0) p.n_ckpt = 0;
+  if (a.ckpt && !al16(a.ckpt)) return fail("selscan_b200_fwd: ckpt must be 16-byte aligned");
+  p.vec_rows = al16(a.u) && al16(a.delta) && al16(a.out) && m4(a.u_batch_stride) && m4(a.u_d_stride) &&
+               m4(a.delta_batch_stride) && m4(a.delta_d_stride) && m4(a.out_batch_stride) && m4(a.out_d_stride) &&
+               (!a.z || (al16(a.z) && al16(a.out_z) && m4(a.z_batch_stride) && m4(a.z_d_stride) &&
+                         m4(a.out_z_batch_stride) && m4(a.out_z_d_stride)));
+  p.vec_bc = al16(a.B) && al16(a.C) && a.B_l_stride == 1 && a.C_l_stride == 1 && m4(a.B_batch_stride) &&
+             m4(a.B_group_stride) && m4(a.B_n_stride) && m4(a.C_batch_stride) && m4(a.C_group_stride) &&
+             m4(a.C_n_stride);
+  const cudaError_t e = selscan::launch_fwd(p, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    fail("selscan_b200_fwd: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+__attribute__((visibility("default"))) int selscan_b200_bwd(const selscan_bwd_args* args, void* stream) {
+  if (!args) return fail("selscan_b200_bwd: args is NULL");
+  const selscan_bwd_args& a = *args;
+  if (int rc = check_common(a, "selscan_b200_bwd")) return rc;
+  if (!a.dout || !a.du || !a.ddelta || !a.dA || !a.dB || !a.dC)
+    return fail("selscan_b200_bwd: dout, du, ddelta, dA, dB, dC must not be NULL");
+  if (a.z && (!a.out || !a.dz)) return fail("selscan_b200_bwd: out and dz are required when z is given");
+  if (a.D && !a.dD) return fail("selscan_b200_bwd: dD is required when D is given");
+  if (a.delta_bias && !a.ddelta_bias) return fail("selscan_b200_bwd: ddelta_bias is required when delta_bias is given");
+  selscan::BwdLaunch p;
+  p.a = a;
+  if (!a.D) p.a.dD = nullptr;
+  if (!a.delta_bias) p.a.ddelta_bias = nullptr;
+  p.dim_per_group = a.dim / a.ngroups;
+  p.n_ckpt = (a.seqlen + selscan::kCkptInterval - 1) / selscan::kCkptInterval - 1;
+  if (p.n_ckpt < 0) p.n_ckpt = 0;
+  if (p.n_ckpt > 0 && !a.ckpt) return fail("selscan_b200_bwd: ckpt (saved scan states from selscan_b200_fwd) is required when seqlen > %d", SELSCAN_B200_CKPT_INTERVAL);
+  if (a.ckpt && !al16(a.ckpt)) return fail("selscan_b200_bwd: ckpt must be 16-byte aligned");
+  p.tiles_per_group = (p.dim_per_group + 63) / 64;
+  p.vec_rows = m4(a.seqlen) && al16(a.u) && al16(a.delta) && al16(a.dout) && al16(a.du) && al16(a.ddelta) &&
+               m4(a.u_batch_stride) && m4(a.u_d_stride) && m4(a.delta_batch_stride) && m4(a.delta_d_stride) &&
+               m4(a.dout_batch_stride) && m4(a.dout_d_stride) &&
+               (!a.z || (al16(a.z) && al16(a.out) && al16(a.dz) && m4(a.z_batch_stride) && m4(a.z_d_stride) &&
+                         m4(a.out_batch_stride) && m4(a.out_d_stride)));
+  const cudaError_t e = selscan::launch_bwd(p, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    fail("selscan_b200_bwd: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+}  // extern "C"

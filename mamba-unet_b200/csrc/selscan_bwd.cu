@@ -1,0 +1,278 @@
+// Backward selective scan for sm_100a -- replaces selective_scan_bwd_kernel
+// (/root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489) behind the C ABI.
+//
+// Mapping (v1): a CTA owns 64 channels of ONE (batch, group) and walks the sequence backwards in chunks
+// of kCkptInterval (8) positions.  Two lanes (lane, lane^16) share a channel, 8 states each.  Per chunk a
+// thread restarts the recurrence from the state the forward kernel saved (one MUFU.EX2 per (position,
+// state), kept in registers together with the states), then runs the reverse recurrence
+//     dx_l = C_l * dy_l + a_{l+1} * dx_{l+1}
+// entirely in registers -- no block-wide scan, no running products (cf. the reference's forward scan +
+// BlockReverseScan, bwd_kernel.cuh:243-274).  du / ddelta reduce over the 16 states with one shuffle.
+// dB / dC need a sum over the channels of the group; the reference issues one global atomic per
+// (batch, channel, state, position) (bwd_kernel.cuh:298-316).  Here the chunk's x and dx go to a swizzled
+// shared-memory tile and the CTA contracts them over its 64 channels (thread = (position, 4 states)),
+// then adds one value per (state, position) per CTA to global memory.
+#include "selscan_common.cuh"
+#include "selscan_kernels.h"
+
+namespace selscan {
+
+constexpr int kBwdRows = 64;                  // channels per CTA
+constexpr int kBwdThreads = 2 * kBwdRows;     // two lanes per channel
+constexpr int kHalf = kStatePad / 2;          // states per thread
+constexpr int kCk = kCkptInterval;            // chunk length
+constexpr int kTileFloats = kBwdRows * kCk * kStatePad;  // one [row][pos][state] tile
+
+struct BwdSmem {
+  float X[kTileFloats];            // states x_{l,n}        (for dC)
+  float DX[kTileFloats];           // adjoints dx_{l,n}     (for dB)
+  float BC[kCk * 2 * kStatePad];   // [pos][0..15] = B, [pos][16..31] = C
+  float SDY[kBwdRows * kCk];       // (gated) dout
+  float SDU[kBwdRows * kCk];       // delta * u
+};
+
+// float index of the 4-state chunk `nq` (0..3) of position j of row r; the XOR spreads the 16 rows a
+// quarter-warp touches over all 32 banks (each row is exactly 32 x 16 B).
+__device__ __forceinline__ int tile_idx(int r, int j, int nq) { return r * (kCk * kStatePad) + (((j * 4 + nq) ^ (r & 7)) << 2); }
+
+template <bool kHasZ>
+__global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const BwdLaunch p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const selscan_bwd_args& a = p.a;
+  const int L = a.seqlen, N = a.dstate;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int h = lane >> 4;                      // which half of the states
+  const int r = warp * 16 + (lane & 15);        // row inside the CTA tile
+  int bid = blockIdx.x;
+  const int tile = bid % p.tiles_per_group; bid /= p.tiles_per_group;
+  const int g = bid % a.ngroups;
+  const int b = bid / a.ngroups;
+  const int dg = tile * kBwdRows + r;           // channel inside the group
+  const bool active = dg < p.dim_per_group;
+  const int d = g * p.dim_per_group + (active ? dg : 0);
+  const int64_t row = (int64_t)b * a.dim + d;
+
+  const float* __restrict__ u = a.u + (int64_t)b * a.u_batch_stride + (int64_t)d * a.u_d_stride;
+  const float* __restrict__ dt = a.delta + (int64_t)b * a.delta_batch_stride + (int64_t)d * a.delta_d_stride;
+  const float* __restrict__ dout = a.dout + (int64_t)b * a.dout_batch_stride + (int64_t)d * a.dout_d_stride;
+  const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
+  const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
+  float* __restrict__ du = a.du + row * L;
+  float* __restrict__ ddt = a.ddelta + row * L;
+  const float* __restrict__ z = nullptr;
+  const float* __restrict__ fout = nullptr;
+  float* __restrict__ dz = nullptr;
+  if (kHasZ) {
+    z = a.z + (int64_t)b * a.z_batch_stride + (int64_t)d * a.z_d_stride;
+    fout = a.out + (int64_t)b * a.out_batch_stride + (int64_t)d * a.out_d_stride;
+    dz = a.dz + row * L;
+  }
+  const float* __restrict__ ck = a.ckpt + row * p.n_ckpt * kStatePad + h * kHalf;
+
+  float A2[kHalf], dA[kHalf], w[kHalf];
+#pragma unroll
+  for (int n = 0; n < kHalf; ++n) {
+    const int ng = h * kHalf + n;
+    A2[n] = (active && ng < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)ng * a.A_n_stride) * kLog2e : 0.f;
+    dA[n] = 0.f;
+    w[n] = 0.f;  // a_{l+1} * dx_{l+1}, zero beyond the last position
+  }
+  const float Dv = (active && a.D) ? __ldg(a.D + d) : 0.f;
+  const float bias = (active && a.delta_bias) ? __ldg(a.delta_bias + d) : 0.f;
+  const bool softplus = a.delta_softplus != 0;
+  const bool vr = p.vec_rows != 0;
+  float dD_acc = 0.f, dbias_acc = 0.f;
+
+  const int n_chunks = (L + kCk - 1) / kCk;
+  for (int c = n_chunks - 1; c >= 0; --c) {
+    const int l0 = c * kCk;
+    // ---- stage B/C of this chunk: [pos][32] -------------------------------------------------------
+#pragma unroll
+    for (int i = tid; i < kCk * 2 * kStatePad; i += kBwdThreads) {
+      const int j = i & (kCk - 1), col = i >> 3;  // consecutive threads -> consecutive positions
+      const int n = col & (kStatePad - 1);
+      float v = 0.f;
+      if (n < N && l0 + j < L) {
+        v = (col < kStatePad) ? __ldg(Bg + (int64_t)n * a.B_n_stride + (int64_t)(l0 + j) * a.B_l_stride)
+                              : __ldg(Cg + (int64_t)n * a.C_n_stride + (int64_t)(l0 + j) * a.C_l_stride);
+      }
+      sm.BC[j * 2 * kStatePad + col] = v;
+    }
+    // ---- per-row scalars of the chunk --------------------------------------------------------------
+    float dl[kCk], sg[kCk], uv[kCk], dy[kCk];
+#pragma unroll
+    for (int q = 0; q < kCk / 4; ++q) {
+      float t0[4], t1[4], t2[4];
+      if (active) {
+        load_row4(u, l0 + 4 * q, L, vr, t0);
+        load_row4(dt, l0 + 4 * q, L, vr, t1);
+        load_row4(dout, l0 + 4 * q, L, vr, t2);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t0[j] = t1[j] = t2[j] = 0.f;
+      }
+      if (kHasZ) {
+        float zv[4], ov[4], dzv[4];
+        if (active) {
+          load_row4(z, l0 + 4 * q, L, vr, zv);
+          load_row4(fout, l0 + 4 * q, L, vr, ov);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zv[j] = ov[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // bwd_kernel.cuh:186-191
+          const float s = sigmoidf_fast(zv[j]);
+          dzv[j] = t2[j] * ov[j] * s * (1.f + zv[j] * (1.f - s));
+          t2[j] = t2[j] * zv[j] * s;
+        }
+        if (active && h == 0) store_row4(dz, l0 + 4 * q, L, vr, dzv);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool valid = active && (l0 + 4 * q + j < L);
+        const float xb = t1[j] + bias;
+        const float v = softplus ? softplus20(xb) : xb;
+        dl[4 * q + j] = valid ? v : 0.f;   // invalid: a = 1, b = 0 -> identity step
+        sg[4 * q + j] = softplus ? (xb <= 20.f ? sigmoidf_fast(xb) : 1.f) : 1.f;
+        uv[4 * q + j] = valid ? t0[j] : 0.f;
+        dy[4 * q + j] = valid ? t2[j] : 0.f;
+      }
+    }
+    {  // scalars the channel contraction needs
+      float* dst = (h == 0) ? &sm.SDY[r * kCk] : &sm.SDU[r * kCk];
+#pragma unroll
+      for (int j = 0; j < kCk; ++j) dst[j] = (h == 0) ? dy[j] : dl[j] * uv[j];
+    }
+    __syncthreads();  // BC ready
+
+    // ---- forward recompute from the saved state ------------------------------------------------------
+    float x0[kHalf], ea[kCk][kHalf], xs[kCk][kHalf];
+    if (c > 0 && active) {
+      const float4 c0 = ldg4(ck + (int64_t)(c - 1) * kStatePad);
+      const float4 c1 = ldg4(ck + (int64_t)(c - 1) * kStatePad + 4);
+      x0[0] = c0.x; x0[1] = c0.y; x0[2] = c0.z; x0[3] = c0.w;
+      x0[4] = c1.x; x0[5] = c1.y; x0[6] = c1.z; x0[7] = c1.w;
+    } else {
+#pragma unroll
+      for (int n = 0; n < kHalf; ++n) x0[n] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kCk; ++j) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&sm.BC[j * 32 + h * kHalf]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sm.BC[j * 32 + h * kHalf + 4]);
+      const float Bv[kHalf] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float dlu = dl[j] * uv[j];
+#pragma unroll
+      for (int n = 0; n < kHalf; ++n) {
+        ea[j][n] = ex2(dl[j] * A2[n]);
+        const float xp = (j == 0) ? x0[n] : xs[j - 1][n];
+        xs[j][n] = fmaf(ea[j][n], xp, dlu * Bv[n]);
+      }
+      *reinterpret_cast<float4*>(&sm.X[tile_idx(r, j, 2 * h)]) = make_float4(xs[j][0], xs[j][1], xs[j][2], xs[j][3]);
+      *reinterpret_cast<float4*>(&sm.X[tile_idx(r, j, 2 * h + 1)]) = make_float4(xs[j][4], xs[j][5], xs[j][6], xs[j][7]);
+    }
+
+    // ---- reverse recurrence ---------------------------------------------------------------------------
+    float ov[kCk];  // du for the h == 0 lane, ddelta for its partner
+#pragma unroll
+    for (int j = kCk - 1; j >= 0; --j) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&sm.BC[j * 32 + h * kHalf]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sm.BC[j * 32 + h * kHalf + 4]);
+      const float4 c0 = *reinterpret_cast<const float4*>(&sm.BC[j * 32 + kStatePad + h * kHalf]);
+      const float4 c1 = *reinterpret_cast<const float4*>(&sm.BC[j * 32 + kStatePad + h * kHalf + 4]);
+      const float Bv[kHalf] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float Cv[kHalf] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      float dxv[kHalf];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int n = 0; n < kHalf; ++n) {
+        const float dx = fmaf(Cv[n], dy[j], w[n]);        // dx_{l,n}
+        dxv[n] = dx;
+        s1 = fmaf(dx, Bv[n], s1);                          // sum_n dx * B            (bwd_kernel.cuh:280-281)
+        const float xp = (j == 0) ? x0[n] : xs[j - 1][n];
+        const float wg = dx * (ea[j][n] * xp);             // dx * a_l * x_{l-1}      (:283, x - b form)
+        s2 = fmaf(wg, A2[n], s2);                          // in units of log2(e)
+        dA[n] = fmaf(wg, dl[j], dA[n]);                    // :286
+        w[n] = ea[j][n] * dx;                              // carried to position l-1
+      }
+      *reinterpret_cast<float4*>(&sm.DX[tile_idx(r, j, 2 * h)]) = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
+      *reinterpret_cast<float4*>(&sm.DX[tile_idx(r, j, 2 * h + 1)]) = make_float4(dxv[4], dxv[5], dxv[6], dxv[7]);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+      const float duj = fmaf(dl[j], s1, Dv * dy[j]);       // :211, :280
+      const float dd = fmaf(uv[j], s1, s2 * kLn2) * sg[j]; // :281-284, :446-450
+      ov[j] = (h == 0) ? duj : dd;
+      dbias_acc += (l0 + j < L) ? dd : 0.f;
+      dD_acc = fmaf(dy[j], uv[j], dD_acc);                 // :213
+    }
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < kCk / 4; ++q) {
+        const float o[4] = {ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]};
+        store_row4(h == 0 ? du : ddt, l0 + 4 * q, L, vr, o);
+      }
+    }
+    __syncthreads();  // X, DX, SDY, SDU complete
+
+    // ---- contract the chunk over the CTA's channels: dB = sum_r (delta*u) * dx, dC = sum_r dy * x ----
+    {
+      const int which = tid >> 6;          // 0: dB, 1: dC
+      const int rh = (tid >> 5) & 1;       // which half of the rows
+      const int j = (tid >> 2) & 7;
+      const int nq = tid & 3;
+      const float* __restrict__ src = which ? sm.X : sm.DX;
+      const float* __restrict__ scal = which ? sm.SDY : sm.SDU;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int rr = 0; rr < kBwdRows / 2; ++rr) {
+        const int r2 = rh * (kBwdRows / 2) + rr;
+        const float4 v = *reinterpret_cast<const float4*>(&src[tile_idx(r2, j, nq)]);
+        const float s = scal[r2 * kCk + j];
+        acc.x = fmaf(s, v.x, acc.x);
+        acc.y = fmaf(s, v.y, acc.y);
+        acc.z = fmaf(s, v.z, acc.z);
+        acc.w = fmaf(s, v.w, acc.w);
+      }
+      if (l0 + j < L) {
+        float* __restrict__ dst = (which ? a.dC : a.dB) + ((int64_t)b * a.ngroups + g) * N * (int64_t)L + (l0 + j);
+        const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (nq * 4 + i < N) atomicAdd(dst + (int64_t)(nq * 4 + i) * L, vals[i]);
+      }
+    }
+    __syncthreads();  // tiles free for the next chunk
+  }
+
+  if (active) {
+#pragma unroll
+    for (int n = 0; n < kHalf; ++n)
+      if (h * kHalf + n < N) atomicAdd(a.dA + (int64_t)d * N + h * kHalf + n, dA[n]);  // sum over batch
+    if (h == 0 && a.dD != nullptr) atomicAdd(a.dD + d, dD_acc);
+    if (h == 1 && a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbias_acc);
+  }
+}
+
+cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream) {
+  if (p.a.batch == 0 || p.a.seqlen == 0) return cudaSuccess;
+  static_assert(sizeof(BwdSmem) <= 110 * 1024, "two CTAs per SM");
+  const int smem = (int)sizeof(BwdSmem);
+  const unsigned grid = (unsigned)((int64_t)p.a.batch * p.a.ngroups * p.tiles_per_group);
+  cudaError_t e;
+  if (p.a.z != nullptr) {
+    e = cudaFuncSetAttribute(selscan_bwd_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    selscan_bwd_chunk_kernel<true><<<grid, kBwdThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(selscan_bwd_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    selscan_bwd_chunk_kernel<false><<<grid, kBwdThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace selscan

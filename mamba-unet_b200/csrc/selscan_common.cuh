@@ -1,0 +1,64 @@
+// Device-side helpers shared by the forward and backward selective-scan kernels (sm_100a).
+//
+// Numerics follow the reference kernels so that parity holds to fp32 round-off:
+//   softplus     x <= 20 ? log1pf(expf(x)) : x         selective_scan_fwd_kernel.cuh:153-156
+//   decay        a = exp2f(delta * (A * log2(e)))      selective_scan_fwd_kernel.cuh:168-175,216
+//   silu gate    z / (1 + expf(-z))                    selective_scan_fwd_kernel.cuh:293
+//   softplus'    g / (1 + expf(-x))  for x <= 20       selective_scan_bwd_kernel.cuh:446-450
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace selscan {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kStatePad = 16;     // SELSCAN_B200_STATE_PAD
+constexpr int kCkptInterval = 8;  // SELSCAN_B200_CKPT_INTERVAL
+
+// MUFU.EX2 (one SFU op, flush-to-zero): the only transcendental on the per-(position, state) path.
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// 4 consecutive sequence positions starting at l0 from a unit-stride row; positions >= L read as 0.
+__device__ __forceinline__ void load_row4(const float* __restrict__ row, int l0, int L, bool vec, float (&v)[4]) {
+  if (vec && l0 + 4 <= L) {
+    const float4 t = ldg4(row + l0);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (l0 + j < L) ? __ldg(row + l0 + j) : 0.f;
+  }
+}
+
+__device__ __forceinline__ void store_row4(float* __restrict__ row, int l0, int L, bool vec, const float (&v)[4]) {
+  if (vec && l0 + 4 <= L) {
+    *reinterpret_cast<float4*>(row + l0) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (l0 + j < L) row[l0 + j] = v[j];
+  }
+}
+
+// 4 consecutive positions of one (group, state) row of B or C with arbitrary position stride.
+__device__ __forceinline__ void load_bc4(const float* __restrict__ base, int64_t l_stride, int l0, int L, bool vec,
+                                         float (&v)[4]) {
+  if (vec && l0 + 4 <= L) {
+    const float4 t = ldg4(base + l0);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (l0 + j < L) ? __ldg(base + (int64_t)(l0 + j) * l_stride) : 0.f;
+  }
+}
+
+}  // namespace selscan

@@ -1,0 +1,28 @@
+// Host-visible launch interface between the C ABI (selscan_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/selscan_b200.h"
+
+namespace selscan {
+
+struct FwdLaunch {
+  selscan_fwd_args a;
+  int dim_per_group;  // dim / ngroups
+  int n_ckpt;         // saved states per row = ceil(seqlen / interval) - 1
+  int vec_rows;       // u/delta/z/out rows are 16-byte aligned at every multiple-of-4 position
+  int vec_bc;         // B and C rows likewise (and unit position stride)
+};
+
+struct BwdLaunch {
+  selscan_bwd_args a;
+  int dim_per_group;
+  int n_ckpt;
+  int tiles_per_group;  // ceil(dim_per_group / rows per CTA)
+  int vec_rows;         // u/delta/dout/z/out/du/ddelta/dz rows 16-byte aligned at multiples of 4
+};
+
+cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream);
+cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);
+
+}  // namespace selscan

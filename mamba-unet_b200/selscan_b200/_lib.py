@@ -1,0 +1,87 @@
+"""ctypes binding of libselscan_b200.so (C ABI declared in include/selscan_b200.h).
+
+There is no fallback: if the library is missing or fails to load, every op raises RuntimeError.
+"""
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "lib", "libselscan_b200.so")
+
+ABI_VERSION = 1
+CKPT_INTERVAL = 8
+STATE_PAD = 16
+
+_i32, _i64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+
+class FwdArgs(ctypes.Structure):
+    """struct selscan_fwd_args -- field order must match include/selscan_b200.h (tests/test_abi.py checks)."""
+    _fields_ = (
+        [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups", "delta_softplus")]
+        + [(n, _ptr) for n in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")]
+        + [(n, _i64) for n in (
+            "u_batch_stride", "u_d_stride", "delta_batch_stride", "delta_d_stride", "A_d_stride", "A_n_stride",
+            "B_batch_stride", "B_group_stride", "B_n_stride", "B_l_stride",
+            "C_batch_stride", "C_group_stride", "C_n_stride", "C_l_stride",
+            "z_batch_stride", "z_d_stride")]
+        + [("out", _ptr), ("out_batch_stride", _i64), ("out_d_stride", _i64),
+           ("out_z", _ptr), ("out_z_batch_stride", _i64), ("out_z_d_stride", _i64),
+           ("last_state", _ptr), ("ckpt", _ptr)]
+    )
+
+
+class BwdArgs(ctypes.Structure):
+    """struct selscan_bwd_args."""
+    _fields_ = (
+        [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "ngroups", "delta_softplus")]
+        + [(n, _ptr) for n in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias", "dout", "out", "ckpt")]
+        + [(n, _i64) for n in (
+            "u_batch_stride", "u_d_stride", "delta_batch_stride", "delta_d_stride", "A_d_stride", "A_n_stride",
+            "B_batch_stride", "B_group_stride", "B_n_stride", "B_l_stride",
+            "C_batch_stride", "C_group_stride", "C_n_stride", "C_l_stride",
+            "z_batch_stride", "z_d_stride", "dout_batch_stride", "dout_d_stride",
+            "out_batch_stride", "out_d_stride")]
+        + [(n, _ptr) for n in ("du", "ddelta", "dz", "dA", "dB", "dC", "dD", "ddelta_bias")]
+    )
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared library once; raise RuntimeError (never fall back) if it is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libselscan_b200.so not found at {LIB_PATH}: build it with `python mamba-unet_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for selective_scan_fn)")
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise RuntimeError(f"cannot load {LIB_PATH}: {e}") from e
+        lib.selscan_b200_abi_version.restype = ctypes.c_int
+        lib.selscan_b200_last_error.restype = ctypes.c_char_p
+        lib.selscan_b200_ckpt_elems.restype = ctypes.c_int64
+        lib.selscan_b200_ckpt_elems.argtypes = [_i32] * 4
+        lib.selscan_b200_fwd.restype = ctypes.c_int
+        lib.selscan_b200_fwd.argtypes = [ctypes.POINTER(FwdArgs), _ptr]
+        lib.selscan_b200_bwd.restype = ctypes.c_int
+        lib.selscan_b200_bwd.argtypes = [ctypes.POINTER(BwdArgs), _ptr]
+        if lib.selscan_b200_abi_version() != ABI_VERSION:
+            raise RuntimeError("libselscan_b200.so ABI version mismatch: rebuild with mamba-unet_b200/build.py")
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().selscan_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

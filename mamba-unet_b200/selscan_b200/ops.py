@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference op interface for the selective scan.
+
+Mirrors /root/reference/mamba/mamba_ssm/ops/selective_scan_interface.py:
+  SelectiveScanFn   :14-74   (autograd forward/backward around the native kernels)
+  selective_scan_fn :77-83
+  selective_scan_ref:86-152  (the semantic spec, plain PyTorch; exported because callers import it)
+Same names, argument meaning, return values and error class (RuntimeError); the native calls go to
+libselscan_b200.so through its C ABI (include/selscan_b200.h) instead of the pybind `selective_scan_cuda`.
+selective_scan_fn has no fallback: without a CUDA tensor or without the library it raises.
+"""
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
+    """Shape / dtype / device rules of selective_scan.cpp:233-305 (TORCH_CHECK -> RuntimeError)."""
+    if not u.is_cuda:
+        raise RuntimeError("selective_scan_fn: u must be a CUDA tensor (this build has no CPU fallback; "
+                           "use selective_scan_ref for a CPU reference)")
+    for name, t in (("delta", delta), ("A", A), ("B", B), ("C", C), ("D", D), ("z", z), ("delta_bias", delta_bias)):
+        if t is not None and t.device != u.device:
+            raise RuntimeError(f"selective_scan_fn: {name} must be on the same device as u")
+    if u.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise RuntimeError(f"selective_scan_fn: unsupported input type {u.dtype}")
+    if delta.dtype != u.dtype:
+        raise RuntimeError("selective_scan_fn: delta must have the same dtype as u")
+    if A.is_complex():
+        raise RuntimeError("selective_scan_fn: complex A is not supported by the B200 build (Mamba-UNet uses real A)")
+    if A.dtype != torch.float32:
+        raise RuntimeError("selective_scan_fn: A must be float32")
+    if u.dim() != 3 or delta.shape != u.shape:
+        raise RuntimeError(f"selective_scan_fn: u and delta must both be (batch, dim, seqlen); got {tuple(u.shape)} "
+                           f"and {tuple(delta.shape)}")
+    batch, dim, seqlen = u.shape
+    if A.dim() != 2 or A.shape[0] != dim:
+        raise RuntimeError(f"selective_scan_fn: A must be (dim, dstate) = ({dim}, N); got {tuple(A.shape)}")
+    dstate = A.shape[1]
+    if dstate > 256:
+        raise RuntimeError("selective_scan only supports state dimension <= 256")
+    for name, t in (("B", B), ("C", C)):
+        if t.dim() < 3:
+            raise RuntimeError(f"selective_scan_fn: constant (dim, dstate) {name} is not supported by the B200 build; "
+                               f"pass the input-dependent (batch, [groups,] dstate, seqlen) form Mamba-UNet uses")
+        if t.dtype != u.dtype:
+            raise RuntimeError(f"selective_scan_fn: {name} must have the same dtype as u")
+        want = (batch, dstate, seqlen) if t.dim() == 3 else (batch, t.shape[1], dstate, seqlen)
+        if tuple(t.shape) != want:
+            raise RuntimeError(f"selective_scan_fn: {name} has shape {tuple(t.shape)}, expected {want}")
+    for name, t in (("D", D), ("delta_bias", delta_bias)):
+        if t is not None:
+            if t.dtype != torch.float32:
+                raise RuntimeError(f"selective_scan_fn: {name} must be float32")
+            if tuple(t.shape) != (dim,):
+                raise RuntimeError(f"selective_scan_fn: {name} must have shape ({dim},); got {tuple(t.shape)}")
+    if z is not None and (z.dtype != u.dtype or z.shape != u.shape):
+        raise RuntimeError("selective_scan_fn: z must have the shape and dtype of u")
+    return batch, dim, seqlen, dstate
+
+
+def _rowmajor(t):
+    """Unit stride along seqlen (selective_scan_interface.py:19-22,29-30)."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _strides2(t):
+    return (0, 0) if t is None else (t.stride(0), t.stride(1))
+
+
+def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=None, last_state=None, ckpt=None):
+    """One selscan_b200_fwd call on the current stream.  All tensors fp32 CUDA; B, C 4-D (batch, G, N, L);
+    u/delta/z/out unit-stride along seqlen; outputs preallocated by the caller (the library never allocates)."""
+    lib = _lib.load()
+    batch, dim, seqlen = u.shape
+    a = _lib.FwdArgs(
+        batch=batch, dim=dim, seqlen=seqlen, dstate=A.shape[1], ngroups=B.shape[1],
+        delta_softplus=int(bool(delta_softplus)),
+        u=_p(u), delta=_p(delta), A=_p(A), B=_p(B), C=_p(C), D=_p(D), z=_p(z), delta_bias=_p(delta_bias),
+        u_batch_stride=u.stride(0), u_d_stride=u.stride(1),
+        delta_batch_stride=delta.stride(0), delta_d_stride=delta.stride(1),
+        A_d_stride=A.stride(0), A_n_stride=A.stride(1),
+        B_batch_stride=B.stride(0), B_group_stride=B.stride(1), B_n_stride=B.stride(2), B_l_stride=B.stride(3),
+        C_batch_stride=C.stride(0), C_group_stride=C.stride(1), C_n_stride=C.stride(2), C_l_stride=C.stride(3),
+        z_batch_stride=_strides2(z)[0], z_d_stride=_strides2(z)[1],
+        out=_p(out), out_batch_stride=out.stride(0), out_d_stride=out.stride(1),
+        out_z=_p(out_z), out_z_batch_stride=_strides2(out_z)[0], out_z_d_stride=_strides2(out_z)[1],
+        last_state=_p(last_state), ckpt=_p(ckpt))
+    with torch.cuda.device(u.device):
+        _lib.check(lib.selscan_b200_fwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_fwd")
+
+
+def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softplus,
+               du, ddelta, dA, dB, dC, dD=None, dz=None, ddelta_bias=None):
+    """One selscan_b200_bwd call on the current stream.  dA, dB, dC, dD, ddelta_bias must be zero-initialised."""
+    lib = _lib.load()
+    batch, dim, seqlen = u.shape
+    a = _lib.BwdArgs(
+        batch=batch, dim=dim, seqlen=seqlen, dstate=A.shape[1], ngroups=B.shape[1],
+        delta_softplus=int(bool(delta_softplus)),
+        u=_p(u), delta=_p(delta), A=_p(A), B=_p(B), C=_p(C), D=_p(D), z=_p(z), delta_bias=_p(delta_bias),
+        dout=_p(dout), out=_p(out), ckpt=_p(ckpt),
+        u_batch_stride=u.stride(0), u_d_stride=u.stride(1),
+        delta_batch_stride=delta.stride(0), delta_d_stride=delta.stride(1),
+        A_d_stride=A.stride(0), A_n_stride=A.stride(1),
+        B_batch_stride=B.stride(0), B_group_stride=B.stride(1), B_n_stride=B.stride(2), B_l_stride=B.stride(3),
+        C_batch_stride=C.stride(0), C_group_stride=C.stride(1), C_n_stride=C.stride(2), C_l_stride=C.stride(3),
+        z_batch_stride=_strides2(z)[0], z_d_stride=_strides2(z)[1],
+        dout_batch_stride=dout.stride(0), dout_d_stride=dout.stride(1),
+        out_batch_stride=_strides2(out)[0], out_d_stride=_strides2(out)[1],
+        du=_p(du), ddelta=_p(ddelta), dz=_p(dz), dA=_p(dA), dB=_p(dB), dC=_p(dC), dD=_p(dD),
+        ddelta_bias=_p(ddelta_bias))
+    with torch.cuda.device(u.device):
+        _lib.check(lib.selscan_b200_bwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_bwd")
+
+
+def ckpt_elems(batch, dim, seqlen, dstate):
+    return int(_lib.load().selscan_b200_ckpt_elems(batch, dim, seqlen, dstate))
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    """selective_scan_interface.py:14-74, on the sm_100a kernels."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                return_last_state=False):
+        batch, dim, seqlen, dstate = _check_inputs(u, delta, A, B, C, D, z, delta_bias)
+        _lib.load()
+        in_dtype = u.dtype
+        if in_dtype != torch.float32:
+            # fp16 / bf16 I/O: the kernels compute in fp32 exactly as the reference's do
+            # (input_t -> float on load, selective_scan_common.h:148-176); widen here, round once on return.
+            u, delta, B, C = u.float(), delta.float(), B.float(), C.float()
+            z = z.float() if z is not None else None
+        u, delta = _rowmajor(u), _rowmajor(delta)
+        z = _rowmajor(z) if z is not None else None
+        if D is not None:
+            D = D.contiguous()
+        if delta_bias is not None:
+            delta_bias = delta_bias.contiguous()
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)  # selective_scan_interface.py:31-36
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        ngroups = B.shape[1]
+        if C.shape[1] != ngroups or dim % ngroups != 0:
+            raise RuntimeError(f"selective_scan_fn: B and C must share a group count dividing dim={dim}; "
+                               f"got {B.shape[1]} and {C.shape[1]}")
+        needs_grad = any(ctx.needs_input_grad)
+        with torch.cuda.device(u.device):
+            out = torch.empty((batch, dim, seqlen), device=u.device, dtype=torch.float32)
+            out_z = torch.empty_like(out) if z is not None else None
+            last_state = (torch.empty((batch, dim, dstate), device=u.device, dtype=torch.float32)
+                          if return_last_state else None)
+            ckpt = None
+            if needs_grad:  # saved scan states, the role of the reference's `x` (selective_scan.cpp:313)
+                ckpt = torch.empty((max(ckpt_elems(batch, dim, seqlen, dstate), 4),), device=u.device,
+                                   dtype=torch.float32)
+            launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z, last_state, ckpt)
+        ctx.delta_softplus = bool(delta_softplus)
+        ctx.has_z = z is not None
+        ctx.in_dtype = in_dtype
+        if needs_grad:
+            if not ctx.has_z:
+                ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, ckpt)
+            else:
+                ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, ckpt, out)
+        ret = out_z if ctx.has_z else out
+        if in_dtype != torch.float32:
+            ret = ret.to(in_dtype)
+        if not return_last_state:
+            return ret
+        ctx.mark_non_differentiable(last_state)
+        return ret, last_state
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        if not ctx.has_z:
+            u, delta, A, B, C, D, delta_bias, ckpt = ctx.saved_tensors
+            z = out = None
+        else:
+            u, delta, A, B, C, D, z, delta_bias, ckpt, out = ctx.saved_tensors
+        dout = _rowmajor(dout.float())
+        batch, dim, seqlen = u.shape
+        dstate, ngroups = A.shape[1], B.shape[1]
+        with torch.cuda.device(u.device):
+            du = torch.empty((batch, dim, seqlen), device=u.device, dtype=torch.float32)
+            ddelta = torch.empty_like(du)
+            dz = torch.empty_like(du) if z is not None else None
+            # reductions are accumulated in fp32 with atomics: zero-initialised, as selective_scan.cpp:458-466
+            dA = torch.zeros((dim, dstate), device=u.device, dtype=torch.float32)
+            dB = torch.zeros((batch, ngroups, dstate, seqlen), device=u.device, dtype=torch.float32)
+            dC = torch.zeros_like(dB)
+            dD = torch.zeros((dim,), device=u.device, dtype=torch.float32) if D is not None else None
+            dbias = torch.zeros((dim,), device=u.device, dtype=torch.float32) if delta_bias is not None else None
+            launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, ctx.delta_softplus,
+                       du, ddelta, dA, dB, dC, dD, dz, dbias)
+        dB = dB.squeeze(1) if ctx.squeeze_B else dB  # selective_scan_interface.py:67-68
+        dC = dC.squeeze(1) if ctx.squeeze_C else dC
+        if ctx.in_dtype != torch.float32:
+            du, ddelta = du.to(ctx.in_dtype), ddelta.to(ctx.in_dtype)
+            dB, dC = dB.to(ctx.in_dtype), dC.to(ctx.in_dtype)
+            dz = dz.to(ctx.in_dtype) if dz is not None else None
+        return (du, ddelta, dA, dB, dC, dD, dz, dbias, None, None)
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """if return_last_state is True, returns (out, last_state); last_state is (batch, dim, dstate) and
+    carries no gradient (selective_scan_interface.py:77-83)."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+
+
+def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                       return_last_state=False):
+    """Plain-PyTorch statement of the op (any device), the role of selective_scan_interface.py:86-152.
+
+    u, delta: (B, D, L); A: (D, N) real; B, C: (B, N, L) or (B, G, N, L); D, delta_bias: (D,); z: (B, D, L).
+    Exported because callers import it next to selective_scan_fn (code/networks/mamba_sys.py:17-20);
+    selective_scan_fn never calls it."""
+    dtype_in = u.dtype
+    u, delta = u.float(), delta.float()
+    if delta_bias is not None:
+        delta = delta + delta_bias[..., None].float()
+    if delta_softplus:
+        delta = F.softplus(delta)
+    if A.is_complex() or B.dim() < 3 or C.dim() < 3:
+        raise RuntimeError("selective_scan_ref (B200 build): only real A with input-dependent B and C is provided")
+    batch, dim, seqlen = u.shape
+    dstate = A.shape[1]
+    B, C = B.float(), C.float()
+    if B.dim() == 3:
+        B = B.unsqueeze(1)
+    if C.dim() == 3:
+        C = C.unsqueeze(1)
+    B = B.repeat_interleave(dim // B.shape[1], dim=1)  # channel d -> group d // (dim / G)
+    C = C.repeat_interleave(dim // C.shape[1], dim=1)
+    decay = torch.exp(delta.unsqueeze(-1) * A.view(1, dim, 1, dstate))           # (B, D, L, N)
+    drive = (delta * u).unsqueeze(-1) * B.permute(0, 1, 3, 2)                    # (B, D, L, N)
+    x = u.new_zeros((batch, dim, dstate))
+    ys = []
+    for l in range(seqlen):
+        x = decay[:, :, l] * x + drive[:, :, l]
+        ys.append((x * C[:, :, :, l]).sum(-1))
+    y = torch.stack(ys, dim=2) if ys else u.new_zeros((batch, dim, 0))
+    out = y if D is None else y + u * D.view(1, dim, 1).float()
+    if z is not None:
+        out = out * F.silu(z.float())
+    out = out.to(dtype_in)
+    return out if not return_last_state else (out, x)

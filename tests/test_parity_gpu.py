@@ -1,0 +1,279 @@
+"""GPU parity: the sm_100a kernels, called through the public op (selective_scan_fn -> C ABI), against
+ (a) the golden fixtures produced by the reference's own selective_scan_ref, and
+ (b) the fp64 C oracle on seeded inputs (reference test grid + the four Mamba-UNet stage shapes),
+plus size-independent properties at the BASELINE.json batch (24).
+
+Tolerances (north-star): forward rtol 1e-4, atol 1e-5 x max(1, max|ref|); gradients rtol 1e-3,
+atol 1e-4 x max(1, max|ref|).  The reference's own test accepts far more (rtol 6e-4 / atol 2e-3 forward,
+mamba/tests/ops/test_selective_scan.py:45-51,116-149).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FWD_RTOL, FWD_ATOL = 1e-4, 1e-5
+BWD_RTOL, BWD_ATOL = 1e-3, 1e-4
+
+
+def _t(a, grad=True):
+    if a is None:
+        return None
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.requires_grad_(grad)
+
+
+def run_ours(inp, softplus, return_last_state=True, squeeze=False):
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    t = {k: _t(v, grad=(k != "dout")) for k, v in inp.items()}
+    res = selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], z=t["z"],
+                            delta_bias=t["delta_bias"], delta_softplus=softplus,
+                            return_last_state=return_last_state)
+    out, last = res if return_last_state else (res, None)
+    out.backward(t["dout"])
+    torch.cuda.synchronize()
+    g = {"du": t["u"].grad, "ddelta": t["delta"].grad, "dA": t["A"].grad, "dB": t["B"].grad, "dC": t["C"].grad,
+         "dD": t["D"].grad if t["D"] is not None else None, "dz": t["z"].grad if t["z"] is not None else None,
+         "ddelta_bias": t["delta_bias"].grad if t["delta_bias"] is not None else None}
+    return (out.detach().cpu().numpy(), None if last is None else last.cpu().numpy(),
+            {k: (None if v is None else v.cpu().numpy()) for k, v in g.items()})
+
+
+def close(got, ref, rtol, atol, name):
+    scale = max(1.0, float(np.abs(ref).max())) if ref.size else 1.0
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    bound = atol * scale + rtol * np.abs(ref)
+    worst = float((err / bound).max()) if ref.size else 0.0
+    assert worst <= 1.0, f"{name}: max err/bound = {worst:.3f}, max abs err = {err.max():.3e}, scale = {scale:.3e}"
+
+
+def check_all(out, last, grads, ref_out, ref_last, ref_grads):
+    close(out, ref_out, FWD_RTOL, FWD_ATOL, "out")
+    if last is not None and ref_last is not None:
+        close(last, ref_last, FWD_RTOL, FWD_ATOL, "last_state")
+    for k, ref in ref_grads.items():
+        if ref is None:
+            continue
+        got = grads[k]
+        assert got is not None, k
+        if got.shape != ref.shape:  # oracle returns 4-D dB/dC
+            got = got.reshape(ref.shape)
+        close(got, ref, BWD_RTOL, BWD_ATOL, k)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_against_reference_golden(name):
+    g = load_golden(name)
+    sp = bool(int(g["delta_softplus"]))
+    inp = {k: g.get(k) for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias", "dout")}
+    out, last, grads = run_ours(inp, sp)
+    ref_grads = {k: g.get(k) for k in ("du", "ddelta", "dA", "dB", "dC", "dD", "dz", "ddelta_bias")}
+    check_all(out, last, grads, g["out"], g["last_state"], ref_grads)
+
+
+def _oracle_case(oracle, batch, dim, L, N, G, dist, seed, has_z, has_D, has_bias, softplus):
+    inp = oracle.make_inputs(batch, dim, L, N, G, dist=dist, seed=seed, has_z=has_z, has_D=has_D, has_bias=has_bias)
+    ref_out, ref_last = oracle.oracle_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"],
+                                          inp["delta_bias"], softplus, return_last_state=True, precision=64)
+    ref_g = oracle.oracle_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"],
+                              inp["delta_bias"], inp["dout"], softplus, precision=64)
+    out, last, grads = run_ours(inp, softplus)
+    check_all(out, last, grads, ref_out, ref_last, ref_g)
+
+
+# the reference's own grid (test_selective_scan.py:18-56): dim 4, dstate 8, groups 1/2, everything on
+@pytest.mark.parametrize("G", [1, 2])
+@pytest.mark.parametrize("L", [128, 256, 512, 1024, 2048, 4096])
+def test_reference_test_grid(oracle, L, G):
+    _oracle_case(oracle, 2, 4, L, 8, G, "T", 0, True, True, True, True)
+
+
+# what the reference grid does not cover
+@pytest.mark.parametrize("L", [1, 7, 8, 9, 49, 196, 784, 2049, 3136])
+@pytest.mark.parametrize("dist", ["T", "M"])
+def test_uneven_lengths_n16_g4(oracle, L, dist):
+    _oracle_case(oracle, 2, 8, L, 16, 4, dist, 10 + L, False, True, True, True)
+
+
+@pytest.mark.parametrize("has_z,has_D,has_bias,softplus", [
+    (False, False, False, False), (True, False, True, True), (False, True, False, True), (True, True, True, False)])
+@pytest.mark.parametrize("N,G,dpg", [(16, 1, 1), (16, 2, 4), (8, 4, 3), (5, 1, 70), (16, 1, 130)])
+def test_optional_args_groups_states(oracle, has_z, has_D, has_bias, softplus, N, G, dpg):
+    _oracle_case(oracle, 2, G * dpg, 100, N, G, "T", 77, has_z, has_D, has_bias, softplus)
+
+
+# the four SS2D stages of MambaUnet, full channel counts, batch 2
+@pytest.mark.parametrize("D,L", [(192, 3136), (384, 784), (768, 196), (1536, 49)])
+@pytest.mark.parametrize("dist", ["T", "M"])
+def test_unet_stage_shapes(oracle, D, L, dist):
+    _oracle_case(oracle, 2, 4 * D, L, 16, 4, dist, 5, False, True, True, True)
+
+
+def test_strided_bc_native_xdbl_layout(oracle):
+    """B/C as views of x_dbl = (batch, K, L, R+2N) permuted, i.e. stride(-1) = R+2N."""
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    batch, K, D, L, N, R = 2, 4, 8, 50, 16, 6
+    inp = oracle.make_inputs(batch, K * D, L, N, K, dist="M", seed=21)
+    xdbl = torch.randn(batch, K, L, R + 2 * N, device="cuda")
+    xdbl[..., R:R + N] = torch.from_numpy(inp["B"]).cuda().permute(0, 1, 3, 2)
+    xdbl[..., R + N:] = torch.from_numpy(inp["C"]).cuda().permute(0, 1, 3, 2)
+    xdbl.requires_grad_()
+    Bv = xdbl[..., R:R + N].permute(0, 1, 3, 2)
+    Cv = xdbl[..., R + N:].permute(0, 1, 3, 2)
+    assert Bv.stride(-1) == R + 2 * N
+    u, dt, A = _t(inp["u"]), _t(inp["delta"]), _t(inp["A"])
+    Dp, bias = _t(inp["D"]), _t(inp["delta_bias"])
+    out = selective_scan_fn(u, dt, A, Bv, Cv, Dp, z=None, delta_bias=bias, delta_softplus=True)
+    out.backward(torch.from_numpy(inp["dout"]).cuda())
+    ref_out = oracle.oracle_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None,
+                                inp["delta_bias"], True, precision=64)
+    ref_g = oracle.oracle_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None,
+                              inp["delta_bias"], inp["dout"], True, precision=64)
+    close(out.detach().cpu().numpy(), ref_out, FWD_RTOL, FWD_ATOL, "out")
+    gx = xdbl.grad.cpu().numpy()
+    close(np.transpose(gx[..., R:R + N], (0, 1, 3, 2)), ref_g["dB"], BWD_RTOL, BWD_ATOL, "dB")
+    close(np.transpose(gx[..., R + N:], (0, 1, 3, 2)), ref_g["dC"], BWD_RTOL, BWD_ATOL, "dC")
+    assert np.all(gx[..., :R] == 0)
+    close(u.grad.cpu().numpy(), ref_g["du"], BWD_RTOL, BWD_ATOL, "du")
+
+
+def test_noncontiguous_u_and_dout(oracle):
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    inp = oracle.make_inputs(2, 8, 40, 16, 4, dist="T", seed=31)
+    u_t = torch.from_numpy(inp["u"]).cuda().transpose(1, 2).contiguous().transpose(1, 2).requires_grad_()  # stride(-1) != 1
+    assert u_t.stride(-1) != 1
+    rest = {k: _t(inp[k]) for k in ("delta", "A", "B", "C", "D", "delta_bias")}
+    out = selective_scan_fn(u_t, rest["delta"], rest["A"], rest["B"], rest["C"], rest["D"], None, rest["delta_bias"], True)
+    dout = torch.from_numpy(inp["dout"]).cuda().transpose(1, 2).contiguous().transpose(1, 2)
+    out.backward(dout)
+    ref_out = oracle.oracle_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None,
+                                inp["delta_bias"], True, precision=64)
+    ref_g = oracle.oracle_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], None,
+                              inp["delta_bias"], inp["dout"], True, precision=64)
+    close(out.detach().cpu().numpy(), ref_out, FWD_RTOL, FWD_ATOL, "out")
+    close(u_t.grad.cpu().numpy(), ref_g["du"], BWD_RTOL, BWD_ATOL, "du")
+    close(rest["delta"].grad.cpu().numpy(), ref_g["ddelta"], BWD_RTOL, BWD_ATOL, "ddelta")
+
+
+def test_half_precision_io(oracle):
+    """fp16 / bf16 inputs: fp32 math, one rounding on output (reference tolerances, test_selective_scan.py:45-47)."""
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    inp = oracle.make_inputs(2, 8, 64, 16, 2, dist="T", seed=41)
+    for dtype, rtol, atol in ((torch.float16, 3e-3, 5e-3), (torch.bfloat16, 3e-2, 5e-2)):
+        t = {k: torch.from_numpy(inp[k]).cuda() for k in ("u", "delta", "B", "C")}
+        t = {k: v.to(dtype) for k, v in t.items()}
+        A, Dp, bias = (torch.from_numpy(inp[k]).cuda() for k in ("A", "D", "delta_bias"))
+        out = selective_scan_fn(t["u"], t["delta"], A, t["B"], t["C"], Dp, None, bias, True)
+        assert out.dtype == dtype
+        ref = oracle.oracle_fwd(t["u"].float().cpu().numpy(), t["delta"].float().cpu().numpy(), inp["A"],
+                                t["B"].float().cpu().numpy(), t["C"].float().cpu().numpy(), inp["D"], None,
+                                inp["delta_bias"], True, precision=64)
+        close(out.float().cpu().numpy(), ref, rtol, atol, f"out[{dtype}]")
+
+
+def test_no_grad_and_errors():
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    u = torch.randn(1, 4, 16, device="cuda")
+    A = -torch.rand(4, 16, device="cuda")
+    B = torch.randn(1, 1, 16, 16, device="cuda")
+    with torch.no_grad():
+        out = selective_scan_fn(u, u.abs(), A, B, B)
+    assert out.shape == u.shape and not out.requires_grad
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u.abs(), A[:, :3].to(torch.complex64), B, B)
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u.abs(), A, B[:, :, :8], B)
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u.cpu(), u.abs().cpu(), A.cpu(), B.cpu(), B.cpu())
+    with pytest.raises(RuntimeError):
+        selective_scan_fn(u, u.abs(), torch.zeros(4, 32, device="cuda"), torch.zeros(1, 1, 32, 16, device="cuda"),
+                          torch.zeros(1, 1, 32, 16, device="cuda"))
+
+
+def test_checkpoint_recompute_and_double_backward_call():
+    """Works under torch.utils.checkpoint (mamba_sys.py:618-619) and from the autograd worker thread."""
+    from torch.utils.checkpoint import checkpoint
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    torch.manual_seed(0)
+    u = torch.randn(2, 8, 70, device="cuda", requires_grad=True)
+    dt = torch.rand(2, 8, 70, device="cuda", requires_grad=True)
+    A = (-torch.rand(8, 16, device="cuda")).requires_grad_()
+    B = torch.randn(2, 2, 16, 70, device="cuda", requires_grad=True)
+    C = torch.randn(2, 2, 16, 70, device="cuda", requires_grad=True)
+
+    def f(u, dt, A, B, C):
+        return selective_scan_fn(u, dt, A, B, C, None, None, None, True)
+
+    o1 = f(u, dt, A, B, C)
+    g1 = torch.autograd.grad(o1.sum(), (u, dt, A, B, C))
+    o2 = checkpoint(f, u, dt, A, B, C, use_reentrant=False)
+    g2 = torch.autograd.grad(o2.sum(), (u, dt, A, B, C))
+    assert torch.equal(o1, o2)
+    for a, b in zip(g1, g2):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+
+
+# ---- BASELINE.json batch (24): size-independent properties + oracle on a row subset -------------------------
+@pytest.mark.parametrize("D,L", [(192, 3136), (1536, 49)])
+def test_full_batch_properties(oracle, D, L):
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    batch, K, N = 24, 4, 16
+    dim = K * D
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    u = torch.randn(batch, dim, L, device="cuda", generator=g)
+    dt = 0.5 * torch.randn(batch, dim, L, device="cuda", generator=g)
+    A = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(dim, 1) * (0.5 + torch.rand(dim, 1, device="cuda", generator=g))
+    Bm = torch.randn(batch, K, N, L, device="cuda", generator=g)
+    Cm = torch.randn(batch, K, N, L, device="cuda", generator=g)
+    Dp = torch.ones(dim, device="cuda")
+    bias = torch.full((dim,), -4.0, device="cuda")
+    leaves = [t.requires_grad_() for t in (u, dt, A, Bm, Cm, Dp, bias)]
+    out, last = selective_scan_fn(u, dt, A, Bm, Cm, Dp, None, bias, True, True)
+    dout = torch.randn(batch, dim, L, device="cuda", generator=g)
+    grads = torch.autograd.grad(out, leaves, dout)
+    assert all(torch.isfinite(t).all() for t in (out, last) + tuple(grads))
+
+    # (1) causality: changing u after position k leaves out[..., :k] bit-identical
+    k = L // 2
+    u2 = u.detach().clone()
+    u2[:, :, k:] += 1.0
+    with torch.no_grad():
+        out2 = selective_scan_fn(u2, dt, A, Bm, Cm, Dp, None, bias, True)
+    assert torch.equal(out2[:, :, :k], out.detach()[:, :, :k])
+
+    # (2) linearity in u (fixed delta, B, C): out(2u) == 2 out(u) up to rounding
+    with torch.no_grad():
+        out3 = selective_scan_fn(2 * u.detach(), dt, A, Bm, Cm, Dp, None, bias, True)
+    torch.testing.assert_close(out3, 2 * out.detach(), rtol=1e-5, atol=1e-5)
+
+    # (3) batch independence: running a single batch element alone gives the same rows bit-for-bit
+    with torch.no_grad():
+        solo = selective_scan_fn(u.detach()[5:6], dt.detach()[5:6], A, Bm.detach()[5:6], Cm.detach()[5:6], Dp, None, bias, True)
+    assert torch.equal(solo[0], out.detach()[5])
+
+    # (4) oracle on one whole (batch element, group): all D channels of group 2 of batch element 7
+    b0, g0 = 7, 2
+    sl = slice(g0 * D, (g0 + 1) * D)
+    sub = dict(u=u[b0:b0 + 1, sl], delta=dt[b0:b0 + 1, sl], A=A[sl], B=Bm[b0:b0 + 1, g0:g0 + 1], C=Cm[b0:b0 + 1, g0:g0 + 1],
+               D=Dp[sl], delta_bias=bias[sl], dout=dout[b0:b0 + 1, sl])
+    sub = {k_: v.detach().cpu().numpy() for k_, v in sub.items()}
+    ref_out, ref_last = oracle.oracle_fwd(sub["u"], sub["delta"], sub["A"], sub["B"], sub["C"], sub["D"], None,
+                                          sub["delta_bias"], True, return_last_state=True, precision=64)
+    ref_g = oracle.oracle_bwd(sub["u"], sub["delta"], sub["A"], sub["B"], sub["C"], sub["D"], None,
+                              sub["delta_bias"], sub["dout"], True, precision=64)
+    close(out.detach()[b0:b0 + 1, sl].cpu().numpy(), ref_out, FWD_RTOL, FWD_ATOL, "out[subset]")
+    close(last[b0:b0 + 1, sl].cpu().numpy(), ref_last, FWD_RTOL, FWD_ATOL, "last_state[subset]")
+    close(grads[0][b0:b0 + 1, sl].cpu().numpy(), ref_g["du"], BWD_RTOL, BWD_ATOL, "du[subset]")
+    close(grads[1][b0:b0 + 1, sl].cpu().numpy(), ref_g["ddelta"], BWD_RTOL, BWD_ATOL, "ddelta[subset]")
+    close(grads[3][b0:b0 + 1, g0:g0 + 1].cpu().numpy(), ref_g["dB"], BWD_RTOL, BWD_ATOL, "dB[subset]")
+    close(grads[4][b0:b0 + 1, g0:g0 + 1].cpu().numpy(), ref_g["dC"], BWD_RTOL, BWD_ATOL, "dC[subset]")

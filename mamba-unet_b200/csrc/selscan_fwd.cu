@@ -8,6 +8,8 @@
 // carries the running product.  The 32 lanes of a warp are 32 consecutive channels of one group, so the
 // B/C loads are warp-uniform (one sector, broadcast).  Every kCkptInterval positions the state is saved
 // for the backward kernel (the role of the reference's per-chunk `x` scratch, selective_scan.cpp:313).
+#include <cstdlib>
+
 #include "selscan_common.cuh"
 #include "selscan_kernels.h"
 
@@ -103,9 +105,15 @@ __global__ void __launch_bounds__(kFwdThreads) selscan_fwd_rowserial_kernel(cons
   }
 }
 
+bool force_generic() {
+  const char* e = getenv("SELSCAN_B200_GENERIC");
+  return e != nullptr && e[0] == '1';
+}
+
 cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream) {
   const int64_t rows = (int64_t)p.a.batch * p.a.dim;
   if (rows == 0 || p.a.seqlen == 0) return cudaSuccess;
+  if (!force_generic() && fwd_tma_eligible(p)) return launch_fwd_tma(p, stream);
   const unsigned grid = (unsigned)((rows + kFwdThreads - 1) / kFwdThreads);
   if (p.a.z != nullptr)
     selscan_fwd_rowserial_kernel<true><<<grid, kFwdThreads, 0, stream>>>(p);

@@ -1,0 +1,246 @@
+// Forward selective scan, tiled path for sm_100a: TMA-staged shared-memory tiles + mbarrier pipeline +
+// packed f32x2 arithmetic.  Replaces selective_scan_fwd_kernel
+// (/root/reference/mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303) for the aligned shapes Mamba-UNet
+// produces (channels per group a multiple of 64, 16-byte aligned rows); everything else takes selscan_fwd.cu.
+//
+// CTA = 64 channels of one (batch, group) x the whole sequence, walked in tiles of 32 positions.
+//   warp 4 (producer): per tile, one elected lane issues two TMA loads (u and delta, box 64 rows x 32 positions,
+//       128-byte swizzle) into a 3-stage ring; all 32 lanes gather the tile's B and C values (any strides: the
+//       (N, L) layout and the l-major x_dbl layout both coalesce) into a [position][B0..15 C0..15] tile.
+//   warps 0-3 (consumers): 16 channels each, two lanes per channel (8 states per lane, lane ^ 16 is the partner).
+//       Row data comes from the swizzled tile with conflict-free 128-bit loads; B/C are warp-uniform broadcast
+//       loads.  The recurrence is thread-serial: per position and state pair one FMUL2, two MUFU.EX2, one FMUL2 and
+//       two FFMA2 -- no cross-thread scan.  y is reduced over the two lanes with one shuffle, staged in a swizzled
+//       16x32 tile and written back by a per-warp TMA store, so HBM only ever sees full 128-byte rows.
+// Full/empty mbarriers per stage are the only synchronisation: warps drift freely, there is no __syncthreads in
+// the loop.  All waits are bounded (trap instead of hang).
+#include "selscan_common.cuh"
+#include "selscan_kernels.h"
+#include "selscan_ptx.cuh"
+#include "selscan_tma_host.h"
+
+namespace selscan {
+
+namespace {
+
+constexpr int kTL = 32;          // positions per tile (128-byte rows)
+constexpr int kRows = 64;        // channels per CTA
+constexpr int kConsWarps = 4;    // 16 channels each
+constexpr int kStages = 3;
+constexpr int kBCPitch = 36;     // floats per position in the B/C tile (32 + pad, keeps 16-byte alignment)
+constexpr int kThreads = (kConsWarps + 1) * 32;
+constexpr int kHalfStates = kStatePad / 2;
+
+struct FwdTmaSmem {
+  float U[kStages][kRows * kTL];        // 8 KB per stage, [row][32] with the 128B TMA swizzle
+  float DT[kStages][kRows * kTL];
+  float OUT[kConsWarps][2][16 * kTL];   // 2 KB per buffer
+  float BC[kStages][kTL * kBCPitch];
+  u64 full[kStages];
+  u64 empty[kStages];
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
+                       const __grid_constant__ CUtensorMap map_out, const FwdLaunch p) {
+  extern __shared__ unsigned char smem_raw[];
+  FwdTmaSmem& sm = *reinterpret_cast<FwdTmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const selscan_fwd_args& a = p.a;
+  const int L = a.seqlen, N = a.dstate;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_group = p.dim_per_group / kRows;
+  int bid = blockIdx.x;
+  const int tile_g = bid % tiles_per_group; bid /= tiles_per_group;
+  const int g = bid % a.ngroups;
+  const int b = bid / a.ngroups;
+  const int d0 = g * p.dim_per_group + tile_g * kRows;
+  const int n_tiles = (L + kTL - 1) / kTL;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&sm.full[s]), 32);           // the 32 producer lanes (+ the TMA transaction bytes)
+      mbar_init(smem_u32(&sm.empty[s]), kConsWarps);  // one arrival per consumer warp
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&map_u);
+    tma_prefetch_desc(&map_dt);
+    tma_prefetch_desc(&map_out);
+  }
+  __syncthreads();
+
+  if (warp == kConsWarps) {
+    // ================================ producer ================================
+    const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
+    const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
+    const bool lanes_along_l = (a.B_l_stride == 1 && a.C_l_stride == 1);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % kStages, k = t / kStages;
+      if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
+      const int l0 = t * kTL;
+      const uint32_t full = smem_u32(&sm.full[s]);
+      if (lane == 0) {
+        mbar_expect_tx(full, 2u * kRows * kTL * 4u);
+        tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
+        tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
+      }
+      float* bc = sm.BC[s];
+      float v[32];
+      if (lanes_along_l) {  // (.., N, L) layout: a warp reads 128 contiguous bytes of one state row
+        const int l = l0 + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = i & 15;
+          const float* src = (i < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
+          v[i] = (n < N && l < L) ? __ldg(src + l) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bc[lane * kBCPitch + i] = v[i];
+      } else {              // l-major layout (x_dbl): a warp reads the 16 B and 16 C values of one position
+        const int n = lane & 15;
+        const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
+        const int64_t ls = (lane < 16) ? a.B_l_stride : a.C_l_stride;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bc[j * kBCPitch + lane] = v[j];
+      }
+      mbar_arrive(full);
+    }
+    return;
+  }
+
+  // ================================ consumers ================================
+  const int h = lane >> 4;             // which 8 states
+  const int r = lane & 15;             // channel inside the warp
+  const int rr = warp * 16 + r;        // channel inside the CTA
+  const int d = d0 + rr;
+  const int64_t row = (int64_t)b * a.dim + d;
+  u64 A2p[4], x2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n0 = h * kHalfStates + 2 * q;
+    const float a0 = (n0 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n0 * a.A_n_stride) * kLog2e : 0.f;
+    const float a1 = (n0 + 1 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + 1) * a.A_n_stride) * kLog2e : 0.f;
+    A2p[q] = pk2(a0, a1);
+    x2[q] = pk2(0.f, 0.f);
+  }
+  const float Dv = a.D ? __ldg(a.D + d) : 0.f;
+  const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
+  const bool softplus = a.delta_softplus != 0;
+  float* __restrict__ ck = a.ckpt ? a.ckpt + row * p.n_ckpt * kStatePad + h * kHalfStates : nullptr;
+  const uint32_t swz = (uint32_t)(rr & 7) << 4;   // 128B swizzle: 16-byte chunk index ^= row & 7
+  const uint32_t swz_o = (uint32_t)(r & 7) << 4;
+
+  for (int t = 0; t < n_tiles; ++t) {
+    const int s = t % kStages, k = t / kStages;
+    const int l0 = t * kTL;
+    mbar_wait(smem_u32(&sm.full[s]), k & 1);
+    const uint32_t u_row = smem_u32(sm.U[s]) + rr * (kTL * 4);
+    const uint32_t dt_row = smem_u32(sm.DT[s]) + rr * (kTL * 4);
+    const uint32_t bc_base = smem_u32(sm.BC[s]) + h * (kHalfStates * 4);
+    const uint32_t out_tile = smem_u32(sm.OUT[warp][t & 1]);
+    const uint32_t out_row = out_tile + r * (kTL * 4);
+#pragma unroll 2
+    for (int q = 0; q < kTL / 4; ++q) {
+      const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
+      const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
+      const float uv[4] = {u4.x, u4.y, u4.z, u4.w};
+      float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+      float y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = dl[j] + bias;
+        if (softplus) v = softplus20(v);
+        dl[j] = (l0 + 4 * q + j < L) ? v : 0.f;   // past the end: a = 1, b = 0
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t bc = bc_base + (uint32_t)(4 * q + j) * (kBCPitch * 4);
+        u64 Bp[4], Cp[4];
+        lds_2x64(bc, Bp[0], Bp[1]);
+        lds_2x64(bc + 16, Bp[2], Bp[3]);
+        lds_2x64(bc + 64, Cp[0], Cp[1]);
+        lds_2x64(bc + 80, Cp[2], Cp[3]);
+        const u64 dd = pk2(dl[j], dl[j]);
+        const float du = dl[j] * uv[j];
+        const u64 duu = pk2(du, du);
+        u64 ya = pk2(0.f, 0.f), yb = pk2(0.f, 0.f);
+#pragma unroll
+        for (int pr = 0; pr < 4; ++pr) {
+          float t0, t1;
+          upk2(mul2(dd, A2p[pr]), t0, t1);
+          const u64 e = pk2(ex2(t0), ex2(t1));
+          x2[pr] = fma2(e, x2[pr], mul2(duu, Bp[pr]));
+          if (pr & 1) yb = fma2(Cp[pr], x2[pr], yb);
+          else ya = fma2(Cp[pr], x2[pr], ya);
+        }
+        y[j] = hsum2(add2(ya, yb));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        y[j] += __shfl_xor_sync(0xffffffffu, y[j], 16);
+        y[j] = fmaf(Dv, uv[j], y[j]);
+      }
+      if (h == 0) sts_f4(out_row + (((uint32_t)q << 4) ^ swz_o), make_float4(y[0], y[1], y[2], y[3]));
+      if ((q & 1) && ck != nullptr) {   // positions l0 + 4q + 3 closes an interval of 8
+        const int done = l0 + 4 * q + 4;
+        if (done < L) {
+          float xs[8];
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) upk2(x2[pr], xs[2 * pr], xs[2 * pr + 1]);
+          float4* dst = reinterpret_cast<float4*>(ck + (int64_t)(done / kCkptInterval - 1) * kStatePad);
+          dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+          dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+        }
+      }
+    }
+    fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(smem_u32(&sm.empty[s]));   // the warp is done reading stage s
+      tma_store_3d(&map_out, out_tile, l0, d0 + warp * 16, b);
+      tma_store_commit();
+      tma_store_wait_read<1>();              // the other OUT buffer (tile t-1) has been read: free for tile t+1
+    }
+    __syncwarp();
+  }
+  if (lane == 0) tma_store_wait_all<0>();
+  if (a.last_state != nullptr) {
+    float xs[8];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr) upk2(x2[pr], xs[2 * pr], xs[2 * pr + 1]);
+#pragma unroll
+    for (int n = 0; n < kHalfStates; ++n)
+      if (h * kHalfStates + n < N) a.last_state[row * N + h * kHalfStates + n] = xs[n];
+  }
+}
+
+}  // namespace
+
+bool fwd_tma_eligible(const FwdLaunch& p) {
+  const selscan_fwd_args& a = p.a;
+  if (a.z != nullptr) return false;                       // the gated variant stays on the generic kernel
+  if (p.dim_per_group % kRows != 0) return false;
+  if (a.seqlen < 1) return false;
+  if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : 0)) return false;
+  if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : 0)) return false;
+  if (!tma_row_ok(a.out, a.out_d_stride, a.batch > 1 ? a.out_batch_stride : 0)) return false;
+  return tensor_map_encoder() != nullptr;
+}
+
+cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
+  const selscan_fwd_args& a = p.a;
+  CUtensorMap mu, mdt, mout;
+  if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kTL, kRows) ||
+      !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kTL, kRows) ||
+      !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, 16))
+    return cudaErrorInvalidValue;
+  const int smem = (int)sizeof(FwdTmaSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(selscan_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kRows));
+  selscan_fwd_tma_kernel<<<grid, kThreads, smem, stream>>>(mu, mdt, mout, p);
+  return cudaGetLastError();
+}
+
+}  // namespace selscan

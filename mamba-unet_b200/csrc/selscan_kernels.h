@@ -23,6 +23,11 @@ struct BwdLaunch {
 };
 
 cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream);
+// tiled TMA path (selscan_fwd_tma.cu): aligned shapes with channels-per-group % 64 == 0 and no z
+bool fwd_tma_eligible(const FwdLaunch& p);
+cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream);
+// SELSCAN_B200_GENERIC=1 in the environment forces the generic kernels (debugging / A-B timing only)
+bool force_generic();
 cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);
 
 }  // namespace selscan

@@ -7,11 +7,14 @@
 //   warp 4 (producer): per tile, one elected lane issues two TMA loads (u and delta, box 64 rows x 32 positions,
 //       128-byte swizzle) into a 3-stage ring; all 32 lanes gather the tile's B and C values (any strides: the
 //       (N, L) layout and the l-major x_dbl layout both coalesce) into a [position][B0..15 C0..15] tile.
-//   warps 0-3 (consumers): 16 channels each, two lanes per channel (8 states per lane, lane ^ 16 is the partner).
-//       Row data comes from the swizzled tile with conflict-free 128-bit loads; B/C are warp-uniform broadcast
-//       loads.  The recurrence is thread-serial: per position and state pair one FMUL2, two MUFU.EX2, one FMUL2 and
-//       two FFMA2 -- no cross-thread scan.  y is reduced over the two lanes with one shuffle, staged in a swizzled
-//       16x32 tile and written back by a per-warp TMA store, so HBM only ever sees full 128-byte rows.
+//   warps 0-7 (consumers): 8 channels each, FOUR lanes per channel (4 states per lane), so that a batch-24 stage-1
+//       call already gives 16 resident consumer warps per SM.  Row data comes from the swizzled tile with
+//       conflict-free 128-bit loads (the 4 lanes of a channel broadcast); each lane loads only its own 4 B and 4 C
+//       values per position.  softplus(delta + bias) is evaluated once per element (lane j of a channel takes
+//       position 4q+j of a quad) and shared with 4 shuffles.  The recurrence is thread-serial: per position and
+//       state pair one FMUL2, two MUFU.EX2, one FMUL2 and two FFMA2 -- no cross-thread scan.  The 4 partial y of a
+//       quad are reduce-scattered over the 4 lanes (3 shuffles), staged in a swizzled 8x32 tile and written back by
+//       a per-warp TMA store, so HBM only ever sees full 128-byte rows.
 // Full/empty mbarriers per stage are the only synchronisation: warps drift freely, there is no __syncthreads in
 // the loop.  All waits are bounded (trap instead of hang).
 #include "selscan_common.cuh"
@@ -25,16 +28,17 @@ namespace {
 
 constexpr int kTL = 32;          // positions per tile (128-byte rows)
 constexpr int kRows = 64;        // channels per CTA
-constexpr int kConsWarps = 4;    // 16 channels each
+constexpr int kConsWarps = 8;    // 8 channels each, 4 lanes per channel
 constexpr int kStages = 3;
 constexpr int kBCPitch = 36;     // floats per position in the B/C tile (32 + pad, keeps 16-byte alignment)
 constexpr int kThreads = (kConsWarps + 1) * 32;
-constexpr int kHalfStates = kStatePad / 2;
+constexpr int kLaneStates = kStatePad / 4;  // states per lane
+constexpr int kWarpRows = kRows / kConsWarps;
 
 struct FwdTmaSmem {
   float U[kStages][kRows * kTL];        // 8 KB per stage, [row][32] with the 128B TMA swizzle
   float DT[kStages][kRows * kTL];
-  float OUT[kConsWarps][2][16 * kTL];   // 2 KB per buffer
+  float OUT[kConsWarps][2][kWarpRows * kTL];   // 1 KB per buffer
   float BC[kStages][kTL * kBCPitch];
   u64 full[kStages];
   u64 empty[kStages];
@@ -110,15 +114,15 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   }
 
   // ================================ consumers ================================
-  const int h = lane >> 4;             // which 8 states
-  const int r = lane & 15;             // channel inside the warp
-  const int rr = warp * 16 + r;        // channel inside the CTA
+  const int sq = lane & 3;             // which 4 states
+  const int r = lane >> 2;             // channel inside the warp
+  const int rr = warp * kWarpRows + r; // channel inside the CTA
   const int d = d0 + rr;
   const int64_t row = (int64_t)b * a.dim + d;
-  u64 A2p[4], x2[4];
+  u64 A2p[2], x2[2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int n0 = h * kHalfStates + 2 * q;
+  for (int q = 0; q < 2; ++q) {
+    const int n0 = sq * kLaneStates + 2 * q;
     const float a0 = (n0 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n0 * a.A_n_stride) * kLog2e : 0.f;
     const float a1 = (n0 + 1 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + 1) * a.A_n_stride) * kLog2e : 0.f;
     A2p[q] = pk2(a0, a1);
@@ -127,9 +131,10 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   const float Dv = a.D ? __ldg(a.D + d) : 0.f;
   const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
   const bool softplus = a.delta_softplus != 0;
-  float* __restrict__ ck = a.ckpt ? a.ckpt + row * p.n_ckpt * kStatePad + h * kHalfStates : nullptr;
+  float* __restrict__ ck = a.ckpt ? a.ckpt + row * p.n_ckpt * kStatePad + sq * kLaneStates : nullptr;
   const uint32_t swz = (uint32_t)(rr & 7) << 4;   // 128B swizzle: 16-byte chunk index ^= row & 7
-  const uint32_t swz_o = (uint32_t)(r & 7) << 4;
+  const int src0 = lane & ~3;                     // first lane of my channel
+  const bool hi1 = (sq & 2) != 0, hi0 = (sq & 1) != 0;
 
   for (int t = 0; t < n_tiles; ++t) {
     const int s = t % kStages, k = t / kStages;
@@ -137,60 +142,63 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     mbar_wait(smem_u32(&sm.full[s]), k & 1);
     const uint32_t u_row = smem_u32(sm.U[s]) + rr * (kTL * 4);
     const uint32_t dt_row = smem_u32(sm.DT[s]) + rr * (kTL * 4);
-    const uint32_t bc_base = smem_u32(sm.BC[s]) + h * (kHalfStates * 4);
+    const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLaneStates * 4);
     const uint32_t out_tile = smem_u32(sm.OUT[warp][t & 1]);
-    const uint32_t out_row = out_tile + r * (kTL * 4);
+    const uint32_t out_row = out_tile + r * (kTL * 4) + sq * 4;   // r == rr & 7: same swizzle key
 #pragma unroll 2
     for (int q = 0; q < kTL / 4; ++q) {
       const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
       const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
       const float uv[4] = {u4.x, u4.y, u4.z, u4.w};
-      float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-      float y[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = dl[j] + bias;
-        if (softplus) v = softplus20(v);
-        dl[j] = (l0 + 4 * q + j < L) ? v : 0.f;   // past the end: a = 1, b = 0
+      // my position of the quad: discretise delta once per element, then share within the channel
+      float mine = hi1 ? (hi0 ? d4.w : d4.z) : (hi0 ? d4.y : d4.x);
+      mine += bias;
+      if (softplus) {
+        float w_unused;
+        mine = softplus_fast(mine, w_unused);
       }
+      mine = (l0 + 4 * q + sq < L) ? mine : 0.f;   // past the end: a = 1, b = 0
+      float dl[4], y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dl[j] = __shfl_sync(0xffffffffu, mine, src0 + j);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t bc = bc_base + (uint32_t)(4 * q + j) * (kBCPitch * 4);
-        u64 Bp[4], Cp[4];
+        u64 Bp[2], Cp[2];
         lds_2x64(bc, Bp[0], Bp[1]);
-        lds_2x64(bc + 16, Bp[2], Bp[3]);
         lds_2x64(bc + 64, Cp[0], Cp[1]);
-        lds_2x64(bc + 80, Cp[2], Cp[3]);
         const u64 dd = pk2(dl[j], dl[j]);
         const float du = dl[j] * uv[j];
         const u64 duu = pk2(du, du);
-        u64 ya = pk2(0.f, 0.f), yb = pk2(0.f, 0.f);
-#pragma unroll
-        for (int pr = 0; pr < 4; ++pr) {
-          float t0, t1;
-          upk2(mul2(dd, A2p[pr]), t0, t1);
-          const u64 e = pk2(ex2(t0), ex2(t1));
-          x2[pr] = fma2(e, x2[pr], mul2(duu, Bp[pr]));
-          if (pr & 1) yb = fma2(Cp[pr], x2[pr], yb);
-          else ya = fma2(Cp[pr], x2[pr], ya);
-        }
-        y[j] = hsum2(add2(ya, yb));
+        float t0, t1, t2, t3;
+        upk2(mul2(dd, A2p[0]), t0, t1);
+        upk2(mul2(dd, A2p[1]), t2, t3);
+        const u64 e0 = pk2(ex2(t0), ex2(t1));
+        const u64 e1 = pk2(ex2(t2), ex2(t3));
+        x2[0] = fma2(e0, x2[0], mul2(duu, Bp[0]));
+        x2[1] = fma2(e1, x2[1], mul2(duu, Bp[1]));
+        y[j] = hsum2(fma2(Cp[1], x2[1], mul2(Cp[0], x2[0])));
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        y[j] += __shfl_xor_sync(0xffffffffu, y[j], 16);
-        y[j] = fmaf(Dv, uv[j], y[j]);
+      // reduce-scatter the 4 partial sums over the 4 lanes of the channel: lane sq ends with position 4q + sq
+      {
+        const float s0 = hi1 ? y[0] : y[2], s1 = hi1 ? y[1] : y[3];
+        float k0 = hi1 ? y[2] : y[0], k1 = hi1 ? y[3] : y[1];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float s2 = hi0 ? k0 : k1;
+        float kk = hi0 ? k1 : k0;
+        kk += __shfl_xor_sync(0xffffffffu, s2, 1);
+        const float umine = hi1 ? (hi0 ? uv[3] : uv[2]) : (hi0 ? uv[1] : uv[0]);
+        const float yo = fmaf(Dv, umine, kk);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(out_row + (((uint32_t)q << 4) ^ swz)), "f"(yo) : "memory");
       }
-      if (h == 0) sts_f4(out_row + (((uint32_t)q << 4) ^ swz_o), make_float4(y[0], y[1], y[2], y[3]));
-      if ((q & 1) && ck != nullptr) {   // positions l0 + 4q + 3 closes an interval of 8
+      if ((q & 1) && ck != nullptr) {   // position l0 + 4q + 3 closes an interval of 8
         const int done = l0 + 4 * q + 4;
         if (done < L) {
-          float xs[8];
-#pragma unroll
-          for (int pr = 0; pr < 4; ++pr) upk2(x2[pr], xs[2 * pr], xs[2 * pr + 1]);
-          float4* dst = reinterpret_cast<float4*>(ck + (int64_t)(done / kCkptInterval - 1) * kStatePad);
-          dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
-          dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+          float xs[4];
+          upk2(x2[0], xs[0], xs[1]);
+          upk2(x2[1], xs[2], xs[3]);
+          *reinterpret_cast<float4*>(ck + (int64_t)(done / kCkptInterval - 1) * kStatePad) = make_float4(xs[0], xs[1], xs[2], xs[3]);
         }
       }
     }
@@ -198,7 +206,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(smem_u32(&sm.empty[s]));   // the warp is done reading stage s
-      tma_store_3d(&map_out, out_tile, l0, d0 + warp * 16, b);
+      tma_store_3d(&map_out, out_tile, l0, d0 + warp * kWarpRows, b);
       tma_store_commit();
       tma_store_wait_read<1>();              // the other OUT buffer (tile t-1) has been read: free for tile t+1
     }
@@ -206,12 +214,12 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   }
   if (lane == 0) tma_store_wait_all<0>();
   if (a.last_state != nullptr) {
-    float xs[8];
+    float xs[4];
+    upk2(x2[0], xs[0], xs[1]);
+    upk2(x2[1], xs[2], xs[3]);
 #pragma unroll
-    for (int pr = 0; pr < 4; ++pr) upk2(x2[pr], xs[2 * pr], xs[2 * pr + 1]);
-#pragma unroll
-    for (int n = 0; n < kHalfStates; ++n)
-      if (h * kHalfStates + n < N) a.last_state[row * N + h * kHalfStates + n] = xs[n];
+    for (int n = 0; n < kLaneStates; ++n)
+      if (sq * kLaneStates + n < N) a.last_state[row * N + sq * kLaneStates + n] = xs[n];
   }
 }
 
@@ -233,7 +241,7 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   CUtensorMap mu, mdt, mout;
   if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kTL, kRows) ||
       !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kTL, kRows) ||
-      !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, 16))
+      !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, kWarpRows))
     return cudaErrorInvalidValue;
   const int smem = (int)sizeof(FwdTmaSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(selscan_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

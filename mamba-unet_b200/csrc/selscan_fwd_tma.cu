@@ -145,11 +145,14 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLaneStates * 4);
     const uint32_t out_tile = smem_u32(sm.OUT[warp][t & 1]);
     const uint32_t out_row = out_tile + r * (kTL * 4) + sq * 4;   // r == rr & 7: same swizzle key
-#pragma unroll 2
-    for (int q = 0; q < kTL / 4; ++q) {
+    // Software pipeline over the 8 quads of the tile: while quad q's recurrence runs, quad q+1's row data is
+    // loaded, discretised and shared, and quad q-1's partial sums are reduce-scattered and stored.
+    float uv_n[4], dl_n[4];        // quad q+1 (prefetched)
+    float yp[4], up = 0.f;         // quad q-1 partial sums and my u of that quad
+    auto prefetch = [&](int q, float (&uv)[4], float (&dl)[4]) {
       const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
       const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
-      const float uv[4] = {u4.x, u4.y, u4.z, u4.w};
+      uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w;
       // my position of the quad: discretise delta once per element, then share within the channel
       float mine = hi1 ? (hi0 ? d4.w : d4.z) : (hi0 ? d4.y : d4.x);
       mine += bias;
@@ -158,9 +161,28 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         mine = softplus_fast(mine, w_unused);
       }
       mine = (l0 + 4 * q + sq < L) ? mine : 0.f;   // past the end: a = 1, b = 0
-      float dl[4], y[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) dl[j] = __shfl_sync(0xffffffffu, mine, src0 + j);
+    };
+    auto finish = [&](int q, const float (&y)[4], float umine) {
+      // reduce-scatter the 4 partial sums over the 4 lanes of the channel: lane sq ends with position 4q + sq
+      const float s0 = hi1 ? y[0] : y[2], s1 = hi1 ? y[1] : y[3];
+      float k0 = hi1 ? y[2] : y[0], k1 = hi1 ? y[3] : y[1];
+      k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float s2 = hi0 ? k0 : k1;
+      float kk = hi0 ? k1 : k0;
+      kk += __shfl_xor_sync(0xffffffffu, s2, 1);
+      const float yo = fmaf(Dv, umine, kk);
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(out_row + (((uint32_t)q << 4) ^ swz)), "f"(yo) : "memory");
+    };
+    prefetch(0, uv_n, dl_n);
+#pragma unroll
+    for (int q = 0; q < kTL / 4; ++q) {
+      float uv[4], dl[4], y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { uv[j] = uv_n[j]; dl[j] = dl_n[j]; }
+      if (q + 1 < kTL / 4) prefetch(q + 1, uv_n, dl_n);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t bc = bc_base + (uint32_t)(4 * q + j) * (kBCPitch * 4);
@@ -179,19 +201,10 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         x2[1] = fma2(e1, x2[1], mul2(duu, Bp[1]));
         y[j] = hsum2(fma2(Cp[1], x2[1], mul2(Cp[0], x2[0])));
       }
-      // reduce-scatter the 4 partial sums over the 4 lanes of the channel: lane sq ends with position 4q + sq
-      {
-        const float s0 = hi1 ? y[0] : y[2], s1 = hi1 ? y[1] : y[3];
-        float k0 = hi1 ? y[2] : y[0], k1 = hi1 ? y[3] : y[1];
-        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        const float s2 = hi0 ? k0 : k1;
-        float kk = hi0 ? k1 : k0;
-        kk += __shfl_xor_sync(0xffffffffu, s2, 1);
-        const float umine = hi1 ? (hi0 ? uv[3] : uv[2]) : (hi0 ? uv[1] : uv[0]);
-        const float yo = fmaf(Dv, umine, kk);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(out_row + (((uint32_t)q << 4) ^ swz)), "f"(yo) : "memory");
-      }
+      if (q > 0) finish(q - 1, yp, up);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) yp[j] = y[j];
+      up = hi1 ? (hi0 ? uv[3] : uv[2]) : (hi0 ? uv[1] : uv[0]);
       if ((q & 1) && ck != nullptr) {   // position l0 + 4q + 3 closes an interval of 8
         const int done = l0 + 4 * q + 4;
         if (done < L) {
@@ -202,6 +215,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         }
       }
     }
+    finish(kTL / 4 - 1, yp, up);
     fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {

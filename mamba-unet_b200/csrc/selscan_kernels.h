@@ -29,5 +29,8 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream);
 // SELSCAN_B200_GENERIC=1 in the environment forces the generic kernels (debugging / A-B timing only)
 bool force_generic();
 cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);
+// tiled TMA path (selscan_bwd_tma.cu): aligned shapes with channels-per-group % 32 == 0, seqlen > 16, no z
+bool bwd_tma_eligible(const BwdLaunch& p);
+cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream);
 
 }  // namespace selscan

@@ -3,16 +3,18 @@
 // (/root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489) for the aligned shapes Mamba-UNet
 // produces (channels per group a multiple of 32, 16-byte aligned rows, no z); everything else takes selscan_bwd.cu.
 //
-// CTA = 32 channels of one (batch, group); the sequence is walked backwards in tiles of 16 positions = 2 chunks of 8
-// (the checkpoint interval).
-//   warp 4 (producer): per tile one elected lane issues TMA loads of u, delta, dout (box 32 rows x 16 positions) and of
-//       the two saved scan states the tile's chunks restart from (box 32 rows x 2 states; the state "before position
-//       0" is the tensor map's out-of-bounds zero fill); all lanes gather the tile's B/C into a [position][32] tile.
+// CTA = 32 channels of one (batch, group); the sequence is walked backwards in chunks of 8 positions (the checkpoint
+// interval).  52 KB of shared memory and 96 registers per thread: four CTAs = 16 compute warps per SM, which makes a
+// batch-24 stage-1 call exactly one wave.
+//   warp 4 (producer): per chunk one elected lane issues TMA loads of u, delta, dout (box 32 rows x 8 positions) and of
+//       the saved scan state the chunk restarts from (box 32 rows x 16 states; the state "before position 0" is the
+//       tensor map's out-of-bounds zero fill); all lanes gather the chunk's B/C into a [position][32] tile.
 //   warps 0-3 (compute): 8 channels each, four lanes per channel, 4 states per lane.  Per chunk:
 //       prep     lane j of a channel discretises positions 2j, 2j+1 (softplus, sigmoid) and publishes delta and
 //                delta*u for its channel; nothing is computed twice;
-//       forward  restart from the saved state: per position and state pair FMUL2, 2 MUFU.EX2, FMUL2, FFMA2; decays and
-//                states stay in registers (packed), states also go to the swizzled X tile;
+//       forward  restart from the saved state: per position and state pair FMUL2, 2 MUFU.EX2, FMUL2, FFMA2; the
+//                states go to the swizzled X tile (decays are recomputed in the reverse pass: MUFU has slack,
+//                registers do not);
 //       reverse  dx = C*dy + a*dx', in registers; dx goes to the DX tile; partial sums of du / ddelta over the lane's 4
 //                states, dA accumulated in registers;
 //       reduce   the partial sums are reduce-scattered over the 4 lanes (lane j finalises positions 2j, 2j+1: du, ddelta
@@ -32,7 +34,7 @@ namespace {
 
 constexpr int kR = 32;            // channels per CTA
 constexpr int kW = 4;             // compute warps
-constexpr int kT = 16;            // positions per staged tile
+constexpr int kT = 8;             // positions per staged tile = one chunk
 constexpr int kC = kCkptInterval; // positions per chunk (8)
 constexpr int kStg = 2;
 constexpr int kPitch = 36;        // B/C tile pitch (floats)
@@ -40,16 +42,18 @@ constexpr int kThr = (kW + 1) * 32;
 constexpr int kLS = kStatePad / 4;  // states per lane
 
 struct BwdTmaSmem {
-  float CK[kStg][kR * 32];          // 4 KB: [row][2 states x 16], 128B swizzle
-  float U[kStg][kR * kT];           // 2 KB: [row][16]
+  float CK[kStg][kR * kStatePad];   // 2 KB: [row][16 states]
+  float U[kStg][kR * kT];           // 1 KB: [row][8]
   float DT[kStg][kR * kT];
   float DY[kStg][kR * kT];
   float BC[kStg][kT * kPitch];
   float X[kR * kC * kStatePad];     // 16 KB, swizzled [row][pos][state]
   float DX[kR * kC * kStatePad];
-  float SD[kR * kC];                // delta   per (row, position of the chunk)
-  float SDU[kR * kC];               // delta*u
-  float DU[kW][2][8 * kT];          // per-warp output tiles, double-buffered (512 B each)
+  float SD[kR * kC];                // delta   per (row, position of the chunk): [row][pos]
+  float SDU[kR * kC];               // delta*u                                    [row][pos]
+  float TDU[kC * kR];               // delta*u, transposed for the contraction    [pos][row]
+  float TDY[kC * kR];               // dout                                       [pos][row]
+  float DU[kW][2][8 * kT];          // per-warp output tiles, double-buffered (256 B each)
   float DDT[kW][2][8 * kT];
   u64 full[kStg];
   u64 empty[kStg];
@@ -67,7 +71,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
                : "memory");
 }
 
-__global__ void __launch_bounds__(kThr, 3)
+__global__ void __launch_bounds__(kThr, 4)
 selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                        const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
                        const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt, const BwdLaunch p) {
@@ -112,33 +116,34 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       const int l0 = t * kT;
       const uint32_t full = smem_u32(&sm.full[s]);
       if (lane == 0) {
-        mbar_expect_tx(full, (uint32_t)(3 * kR * kT * 4 + kR * 32 * 4));
+        mbar_expect_tx(full, (uint32_t)(3 * kR * kT * 4 + kR * kStatePad * 4));
         tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
         tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
         tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
-        // saved states 2t-1 (start of chunk 2t) and 2t (start of chunk 2t+1); state "-1" is out of bounds -> zeros
-        tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (2 * t - 1) * kStatePad, row0, full);
+        // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
+        tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, row0, full);
       }
       float* bc = sm.BC[s];
-      float v[16];
-      if (lanes_along_l) {   // lane = (B|C, position): 64 contiguous bytes per half warp
-        const int l = l0 + (lane & 15);
-        const int which = lane >> 4;
+      float v[8];
+      if (lanes_along_l) {   // lane = (state half, B|C, position): 32 contiguous bytes per 8 lanes
+        const int pos = lane & 7, which = (lane >> 3) & 1, nh = lane >> 4;
+        const int l = l0 + pos;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
+        for (int q = 0; q < 8; ++q) {
+          const int n = nh * 8 + q;
           const float* src = which ? (Cg + (int64_t)n * a.C_n_stride) : (Bg + (int64_t)n * a.B_n_stride);
-          v[n] = (n < N && l < L) ? __ldg(src + l) : 0.f;
+          v[q] = (n < N && l < L) ? __ldg(src + l) : 0.f;
         }
 #pragma unroll
-        for (int n = 0; n < 16; ++n) bc[(lane & 15) * kPitch + which * 16 + n] = v[n];
+        for (int q = 0; q < 8; ++q) bc[pos * kPitch + which * 16 + nh * 8 + q] = v[q];
       } else {               // lane = (B|C, state): the 16 B and 16 C values of one position are contiguous
         const int n = lane & 15;
         const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
         const int64_t ls = (lane < 16) ? a.B_l_stride : a.C_l_stride;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) bc[j * kPitch + lane] = v[j];
+        for (int j = 0; j < 8; ++j) bc[j * kPitch + lane] = v[j];
       }
       mbar_arrive(full);
     }
@@ -166,12 +171,20 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
   const bool softplus = a.delta_softplus != 0;
   float dD_acc = 0.f, dbias_acc = 0.f;
-  // contraction role of this thread
+  // shared-space addresses of this thread's slots
+  const uint32_t x_row = smem_u32(sm.X) + (uint32_t)r * (kC * kStatePad * 4);
+  const uint32_t dx_row = smem_u32(sm.DX) + (uint32_t)r * (kC * kStatePad * 4);
+  const uint32_t xsw = (uint32_t)swz_row(r);
+  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)r * (kC * 4);
+  const uint32_t sdu_row = smem_u32(sm.SDU) + (uint32_t)r * (kC * 4);
+  // contraction role of this thread: (tensor, position, 4 states, half of the rows)
   const int c_which = tid >> 6;                       // 0: dB from DX and delta*u, 1: dC from X and dy
   const int c_j = ((tid >> 5) & 1) * 4 + ((lane >> 2) & 3);
   const int c_nq = lane & 3;
-  const int c_par = lane >> 4;                        // row parity handled by this lane
-  float* __restrict__ dBC = (c_which ? a.dC : a.dB) + ((int64_t)b * a.ngroups + g) * N * (int64_t)L;
+  const int c_half = lane >> 4;                       // rows 16*c_half .. 16*c_half+15
+  const uint32_t c_src = smem_u32(c_which ? sm.X : sm.DX);
+  const uint32_t c_scal = smem_u32(c_which ? sm.TDY : sm.TDU) + (uint32_t)(c_j * kR + c_half * 16) * 4;
+  float* __restrict__ dBC = (c_which ? a.dC : a.dB) + ((int64_t)b * a.ngroups + g) * N * (int64_t)L + (int64_t)(c_nq * 4) * L + c_j;
 
   for (int i = 0; i < n_tiles; ++i) {
     const int t = n_tiles - 1 - i;
@@ -181,103 +194,101 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     const uint32_t u_row = smem_u32(sm.U[s]) + r * (kT * 4);
     const uint32_t dt_row = smem_u32(sm.DT[s]) + r * (kT * 4);
     const uint32_t dy_row = smem_u32(sm.DY[s]) + r * (kT * 4);
-    const uint32_t ck_row = smem_u32(sm.CK[s]) + r * 128;
+    const uint32_t ck_row = smem_u32(sm.CK[s]) + r * (kStatePad * 4);
     const uint32_t du_tile = smem_u32(sm.DU[warp][i & 1]);
     const uint32_t ddt_tile = smem_u32(sm.DDT[warp][i & 1]);
 
-#pragma unroll 1
-    for (int cc = 1; cc >= 0; --cc) {       // chunk 2t+1 first, then 2t
-      const int c0 = l0 + cc * kC;          // first position of the chunk
-      if (c0 >= L) continue;                // (only the second chunk of the last tile can be empty; uniform)
-      // ---------------- prep: my two positions of the chunk ----------------
-      const int pj = 2 * sq;                // chunk-local positions pj, pj+1
+    {
+      const int c0 = l0;                    // first position of the chunk
+      // ---------------- prep: my two positions (2sq, 2sq+1) of the chunk ----------------
+      const int pj = 2 * sq;
       float my_dl[2], my_sg[2], my_u[2], my_dy[2];
       {
-        float2 uu, dd, yy;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(uu.x), "=f"(uu.y) : "r"(u_row + (cc * kC + pj) * 4));
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(dd.x), "=f"(dd.y) : "r"(dt_row + (cc * kC + pj) * 4));
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(yy.x), "=f"(yy.y) : "r"(dy_row + (cc * kC + pj) * 4));
-        const float uin[2] = {uu.x, uu.y}, din[2] = {dd.x, dd.y}, yin[2] = {yy.x, yy.y};
+        const uint32_t off = (uint32_t)pj * 4;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(my_u[0]), "=f"(my_u[1]) : "r"(u_row + off));
+        float din[2];
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(din[0]), "=f"(din[1]) : "r"(dt_row + off));
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(my_dy[0]), "=f"(my_dy[1]) : "r"(dy_row + off));
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const float xb = din[e] + bias;
-          float wexp = 0.f;
-          float v = xb;
-          float sgm = 1.f;
+          float v = xb, sgm = 1.f;
           if (softplus) {
+            float wexp;
             v = softplus_fast(xb, wexp);
             sgm = sigmoid_from_w(xb, wexp);   // softplus' (bwd_kernel.cuh:446-450; == 1 to rounding for x > 20)
           }
-          const bool valid = (c0 + pj + e) < L;
-          my_dl[e] = valid ? v : 0.f;          // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
+          my_dl[e] = ((c0 + pj + e) < L) ? v : 0.f;   // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
           my_sg[e] = sgm;
-          my_u[e] = uin[e];
-          my_dy[e] = yin[e];
         }
-        float* sd = &sm.SD[r * kC + pj];
-        float* sdu = &sm.SDU[r * kC + pj];
-        *reinterpret_cast<float2*>(sd) = make_float2(my_dl[0], my_dl[1]);
-        *reinterpret_cast<float2*>(sdu) = make_float2(my_dl[0] * my_u[0], my_dl[1] * my_u[1]);
+        const float du0 = my_dl[0] * my_u[0], du1 = my_dl[1] * my_u[1];
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sd_row + pj * 4), "f"(my_dl[0]), "f"(my_dl[1]) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sdu_row + pj * 4), "f"(du0), "f"(du1) : "memory");
+        // transposed copies for the contraction: [position][row]
+        const uint32_t tdu = smem_u32(sm.TDU) + (uint32_t)(pj * kR + r) * 4, tdy = smem_u32(sm.TDY) + (uint32_t)(pj * kR + r) * 4;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu), "f"(du0) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu + kR * 4), "f"(du1) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy), "f"(my_dy[0]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy + kR * 4), "f"(my_dy[1]) : "memory");
       }
       __syncwarp();
-      float dl[kC], du_[kC], dy[kC];
+      // ---------------- forward recompute from the saved state (states kept, decays recomputed later) ----------------
+      u64 x0[2];
+      lds_2x64(ck_row + (uint32_t)sq * 16, x0[0], x0[1]);
+      const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLS * 4);
       {
-        const float4 t0 = *reinterpret_cast<const float4*>(&sm.SD[r * kC]);
-        const float4 t1 = *reinterpret_cast<const float4*>(&sm.SD[r * kC + 4]);
-        const float4 v0 = *reinterpret_cast<const float4*>(&sm.SDU[r * kC]);
-        const float4 v1 = *reinterpret_cast<const float4*>(&sm.SDU[r * kC + 4]);
-        const float4 y0 = lds_f4(dy_row + (cc * kC) * 4);
-        const float4 y1 = lds_f4(dy_row + (cc * kC + 4) * 4);
-        dl[0] = t0.x; dl[1] = t0.y; dl[2] = t0.z; dl[3] = t0.w; dl[4] = t1.x; dl[5] = t1.y; dl[6] = t1.z; dl[7] = t1.w;
-        du_[0] = v0.x; du_[1] = v0.y; du_[2] = v0.z; du_[3] = v0.w; du_[4] = v1.x; du_[5] = v1.y; du_[6] = v1.z; du_[7] = v1.w;
-        dy[0] = y0.x; dy[1] = y0.y; dy[2] = y0.z; dy[3] = y0.w; dy[4] = y1.x; dy[5] = y1.y; dy[6] = y1.z; dy[7] = y1.w;
-      }
-      // ---------------- forward recompute from the saved state ----------------
-      u64 x0[2], ea[kC][2], xs[kC][2];
-      lds_2x64(ck_row + ((uint32_t)((cc * 4 + sq) ^ (r & 7)) << 4), x0[0], x0[1]);
-      const uint32_t bc_base = smem_u32(sm.BC[s]) + (uint32_t)(cc * kC) * (kPitch * 4) + sq * (kLS * 4);
+        const float4 dA_ = lds_f4(sd_row), dB_ = lds_f4(sd_row + 16);
+        const float4 uA_ = lds_f4(sdu_row), uB_ = lds_f4(sdu_row + 16);
+        const float dl[kC] = {dA_.x, dA_.y, dA_.z, dA_.w, dB_.x, dB_.y, dB_.z, dB_.w};
+        const float du_[kC] = {uA_.x, uA_.y, uA_.z, uA_.w, uB_.x, uB_.y, uB_.z, uB_.w};
+        u64 xr0 = x0[0], xr1 = x0[1];   // running state; every x_j goes to the X tile (also read back by the reverse pass)
 #pragma unroll
-      for (int j = 0; j < kC; ++j) {
-        u64 Bp[2];
-        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
-        const u64 dd = pk2(dl[j], dl[j]);
-        const u64 duu = pk2(du_[j], du_[j]);
-        float t0, t1, t2, t3;
-        upk2(mul2(dd, A2p[0]), t0, t1);
-        upk2(mul2(dd, A2p[1]), t2, t3);
-        ea[j][0] = pk2(ex2(t0), ex2(t1));
-        ea[j][1] = pk2(ex2(t2), ex2(t3));
-        xs[j][0] = fma2(ea[j][0], j == 0 ? x0[0] : xs[j - 1][0], mul2(duu, Bp[0]));
-        xs[j][1] = fma2(ea[j][1], j == 0 ? x0[1] : xs[j - 1][1], mul2(duu, Bp[1]));
-        float4 xv;
-        upk2(xs[j][0], xv.x, xv.y);
-        upk2(xs[j][1], xv.z, xv.w);
-        *reinterpret_cast<float4*>(&sm.X[xt_idx(r, j, sq)]) = xv;
+        for (int j = 0; j < kC; ++j) {
+          u64 Bp[2];
+          lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
+          const u64 dd = pk2(dl[j], dl[j]);
+          const u64 duu = pk2(du_[j], du_[j]);
+          float t0, t1, t2, t3;
+          upk2(mul2(dd, A2p[0]), t0, t1);
+          upk2(mul2(dd, A2p[1]), t2, t3);
+          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
+          xr0 = fma2(e0, xr0, mul2(duu, Bp[0]));
+          xr1 = fma2(e1, xr1, mul2(duu, Bp[1]));
+          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(x_row + ((((uint32_t)(j * 4 + sq)) ^ xsw) << 4)), "l"(xr0), "l"(xr1) : "memory");
+        }
       }
       // ---------------- reverse recurrence ----------------
       float s1p[kC], s2p[kC];
+      {
+        const float4 dA_ = lds_f4(sd_row), dB_ = lds_f4(sd_row + 16);
+        const float4 yA_ = lds_f4(dy_row), yB_ = lds_f4(dy_row + 16);
+        const float dl[kC] = {dA_.x, dA_.y, dA_.z, dA_.w, dB_.x, dB_.y, dB_.z, dB_.w};
+        const float dy[kC] = {yA_.x, yA_.y, yA_.z, yA_.w, yB_.x, yB_.y, yB_.z, yB_.w};
 #pragma unroll
-      for (int j = kC - 1; j >= 0; --j) {
-        u64 Bp[2], Cp[2];
-        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
-        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4) + 64, Cp[0], Cp[1]);
-        const u64 dyy = pk2(dy[j], dy[j]);
-        const u64 dd = pk2(dl[j], dl[j]);
-        const u64 dx0 = fma2(Cp[0], dyy, w2[0]);                      // dx_{l,n}
-        const u64 dx1 = fma2(Cp[1], dyy, w2[1]);
-        float4 dv;
-        upk2(dx0, dv.x, dv.y);
-        upk2(dx1, dv.z, dv.w);
-        *reinterpret_cast<float4*>(&sm.DX[xt_idx(r, j, sq)]) = dv;
-        s1p[j] = hsum2(fma2(dx1, Bp[1], mul2(dx0, Bp[0])));           // sum_n dx * B          (bwd_kernel.cuh:280-281)
-        const u64 g0 = mul2(ea[j][0], j == 0 ? x0[0] : xs[j - 1][0]);  // a_l * x_{l-1}         (:283, x - b form)
-        const u64 g1 = mul2(ea[j][1], j == 0 ? x0[1] : xs[j - 1][1]);
-        const u64 wg0 = mul2(dx0, g0), wg1 = mul2(dx1, g1);
-        s2p[j] = hsum2(fma2(wg1, A2p[1], mul2(wg0, A2p[0])));          // in units of log2(e)
-        dA2[0] = fma2(wg0, dd, dA2[0]);                                 // :286
-        dA2[1] = fma2(wg1, dd, dA2[1]);
-        w2[0] = mul2(ea[j][0], dx0);                                    // carried to position l-1
-        w2[1] = mul2(ea[j][1], dx1);
+        for (int j = kC - 1; j >= 0; --j) {
+          u64 Bp[2], Cp[2];
+          lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
+          lds_2x64(bc_base + (uint32_t)j * (kPitch * 4) + 64, Cp[0], Cp[1]);
+          const u64 dyy = pk2(dy[j], dy[j]);
+          const u64 dd = pk2(dl[j], dl[j]);
+          float t0, t1, t2, t3;                                          // decays again: MUFU has slack, registers do not
+          upk2(mul2(dd, A2p[0]), t0, t1);
+          upk2(mul2(dd, A2p[1]), t2, t3);
+          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
+          const u64 dx0 = fma2(Cp[0], dyy, w2[0]);                      // dx_{l,n}
+          const u64 dx1 = fma2(Cp[1], dyy, w2[1]);
+          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(dx_row + ((((uint32_t)(j * 4 + sq)) ^ xsw) << 4)), "l"(dx0), "l"(dx1) : "memory");
+          s1p[j] = hsum2(fma2(dx1, Bp[1], mul2(dx0, Bp[0])));           // sum_n dx * B          (bwd_kernel.cuh:280-281)
+          u64 xp0 = x0[0], xp1 = x0[1];                                   // x_{l-1}: my own slot of the X tile
+          if (j > 0) lds_2x64(x_row + ((((uint32_t)((j - 1) * 4 + sq)) ^ xsw) << 4), xp0, xp1);
+          const u64 wg0 = mul2(dx0, mul2(e0, xp0));                       // dx * a_l * x_{l-1}  (:283, x - b form)
+          const u64 wg1 = mul2(dx1, mul2(e1, xp1));
+          s2p[j] = hsum2(fma2(wg1, A2p[1], mul2(wg0, A2p[0])));          // in units of log2(e)
+          dA2[0] = fma2(wg0, dd, dA2[0]);                                 // :286
+          dA2[1] = fma2(wg1, dd, dA2[1]);
+          w2[0] = mul2(e0, dx0);                                          // carried to position l-1
+          w2[1] = mul2(e1, dx1);
+        }
       }
       // ---------------- reduce-scatter s1 / s2 over the 4 lanes: lane sq finalises positions 2sq, 2sq+1 ----------------
       float f1[2], f2[2];
@@ -305,34 +316,37 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
           dbias_acc += ((c0 + pj + e) < L) ? o_dd[e] : 0.f;
           dD_acc = fmaf(my_dy[e], my_u[e], dD_acc);                                // :213
         }
-        const uint32_t off = (uint32_t)(rw * kT + cc * kC + pj) * 4;
+        const uint32_t off = (uint32_t)(rw * kT + pj) * 4;
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(du_tile + off), "f"(o_du[0]), "f"(o_du[1]) : "memory");
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ddt_tile + off), "f"(o_dd[0]), "f"(o_dd[1]) : "memory");
       }
-      named_bar_sync(1, kW * 32);   // X, DX, SDU complete for the CTA's 32 channels
+      named_bar_sync(1, kW * 32);   // X, DX, TDU, TDY complete for the CTA's 32 channels
       // ---------------- contraction over the channels ----------------
       {
-        const float* __restrict__ src = c_which ? sm.X : sm.DX;
         u64 acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
-#pragma unroll 8
-        for (int rr = 0; rr < kR / 2; ++rr) {
-          const int r2 = rr * 2 + c_par;
-          u64 v0, v1;
-          lds_2x64(smem_u32(&src[xt_idx(r2, c_j, c_nq)]), v0, v1);
-          const float sc = c_which ? sm.DY[s][r2 * kT + cc * kC + c_j] : sm.SDU[r2 * kC + c_j];
-          const u64 ss = pk2(sc, sc);
-          acc0 = fma2(ss, v0, acc0);
-          acc1 = fma2(ss, v1, acc1);
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const float4 sc4 = lds_f4(c_scal + r4 * 16);
+          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int r2 = c_half * 16 + r4 * 4 + e;
+            u64 v0, v1;
+            lds_2x64(c_src + (uint32_t)r2 * (kC * kStatePad * 4) + ((((uint32_t)(c_j * 4 + c_nq)) ^ (uint32_t)swz_row(r2)) << 4), v0, v1);
+            const u64 ss = pk2(sc[e], sc[e]);
+            acc0 = fma2(ss, v0, acc0);
+            acc1 = fma2(ss, v1, acc1);
+          }
         }
         float o[4];
         upk2(acc0, o[0], o[1]);
         upk2(acc1, o[2], o[3]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
-        if (c_par == 0 && c0 + c_j < L) {
+        if (c_half == 0 && c0 + c_j < L) {
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (c_nq * 4 + e < N) atomicAdd(dBC + (int64_t)(c_nq * 4 + e) * L + (c0 + c_j), o[e]);
+            if (c_nq * 4 + e < N) atomicAdd(dBC + (int64_t)e * L + c0, o[e]);
         }
       }
       named_bar_sync(1, kW * 32);   // tiles free for the next chunk
@@ -375,10 +389,10 @@ inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int
   if (!enc) return false;
   const cuuint64_t gdim[2] = {(cuuint64_t)n_ckpt * kStatePad, (cuuint64_t)rows};
   const cuuint64_t gstr[1] = {(cuuint64_t)n_ckpt * kStatePad * 4};
-  const cuuint32_t box[2] = {32, (cuuint32_t)kR};
+  const cuuint32_t box[2] = {(cuuint32_t)kStatePad, (cuuint32_t)kR};
   const cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -387,7 +401,7 @@ bool bwd_tma_eligible(const BwdLaunch& p) {
   const selscan_bwd_args& a = p.a;
   if (a.z != nullptr) return false;
   if (p.dim_per_group % kR != 0) return false;
-  if (p.n_ckpt < 2 || (a.seqlen & 3) != 0) return false;   // the checkpoint box spans two saved states
+  if (p.n_ckpt < 1 || (a.seqlen & 3) != 0) return false;
   const int64_t zero = 0;
   if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : zero)) return false;
   if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : zero)) return false;

@@ -20,7 +20,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 }
 
 // dims (fastest first): {seqlen, dim, batch}; box {box_l, box_rows, 1}; rows of box_l*4 = 128 B use the 128-byte swizzle
-// (unless swizzle = false); narrower boxes are dense.
+// and rows of 64 B the 64-byte swizzle (unless swizzle = false); other boxes are dense.
 inline bool make_row_map(CUtensorMap* map, const float* base, int seqlen, int dim, int batch, int64_t d_stride,
                          int64_t batch_stride, int box_l, int box_rows, bool swizzle = true) {
   auto enc = tensor_map_encoder();
@@ -29,7 +29,8 @@ inline bool make_row_map(CUtensorMap* map, const float* base, int seqlen, int di
   const cuuint64_t gstr[2] = {(cuuint64_t)d_stride * 4, (cuuint64_t)(batch > 1 ? batch_stride : (int64_t)dim * d_stride) * 4};
   const cuuint32_t box[3] = {(cuuint32_t)box_l, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUtensorMapSwizzle sw = (swizzle && box_l * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : (box_l * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_l * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE));
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;

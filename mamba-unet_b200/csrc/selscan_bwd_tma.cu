@@ -40,6 +40,8 @@ constexpr int kStg = 2;
 constexpr int kPitch = 36;        // B/C tile pitch (floats)
 constexpr int kThr = (kW + 1) * 32;
 constexpr int kLS = kStatePad / 4;  // states per lane
+constexpr int kSP = 12;           // row pitch of the per-row scalar scratch (floats)
+constexpr int kTP = 36;           // position pitch of the transposed scalar scratch (floats)
 
 struct BwdTmaSmem {
   float CK[kStg][kR * kStatePad];   // 2 KB: [row][16 states]
@@ -49,10 +51,10 @@ struct BwdTmaSmem {
   float BC[kStg][kT * kPitch];
   float X[kR * kC * kStatePad];     // 16 KB, swizzled [row][pos][state]
   float DX[kR * kC * kStatePad];
-  float SD[kR * kC];                // delta   per (row, position of the chunk): [row][pos]
-  float SDU[kR * kC];               // delta*u                                    [row][pos]
-  float TDU[kC * kR];               // delta*u, transposed for the contraction    [pos][row]
-  float TDY[kC * kR];               // dout                                       [pos][row]
+  float SD[kR * kSP];               // delta   per (row, position of the chunk): [row][pos], pitch 12 (conflict-free LDS.128)
+  float SDU[kR * kSP];              // delta*u                                    [row][pos]
+  float TDU[kC * kTP];              // delta*u, transposed for the contraction    [pos][row], pitch 36
+  float TDY[kC * kTP];              // dout                                       [pos][row]
   float DU[kW][2][8 * kT];          // per-warp output tiles, double-buffered (256 B each)
   float DDT[kW][2][8 * kT];
   u64 full[kStg];
@@ -125,17 +127,18 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       }
       float* bc = sm.BC[s];
       float v[8];
-      if (lanes_along_l) {   // lane = (state half, B|C, position): 32 contiguous bytes per 8 lanes
-        const int pos = lane & 7, which = (lane >> 3) & 1, nh = lane >> 4;
+      if (lanes_along_l) {   // lane = (group of 8 values, position): 32 contiguous bytes per 8 lanes
+        const int pos = lane & 7, grp = lane >> 3;       // values 8*grp .. 8*grp+7 of [B0..15 C0..15]
         const int l = l0 + pos;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int n = nh * 8 + q;
-          const float* src = which ? (Cg + (int64_t)n * a.C_n_stride) : (Bg + (int64_t)n * a.B_n_stride);
+          const int vi = grp * 8 + q, n = vi & 15;
+          const float* src = (vi >= 16) ? (Cg + (int64_t)n * a.C_n_stride) : (Bg + (int64_t)n * a.B_n_stride);
           v[q] = (n < N && l < L) ? __ldg(src + l) : 0.f;
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bc[pos * kPitch + which * 16 + nh * 8 + q] = v[q];
+        const uint32_t dst = smem_u32(bc) + (uint32_t)(pos * kPitch + grp * 8) * 4;
+        sts_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
+        sts_f4(dst + 16, make_float4(v[4], v[5], v[6], v[7]));
       } else {               // lane = (B|C, state): the 16 B and 16 C values of one position are contiguous
         const int n = lane & 15;
         const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
@@ -175,15 +178,15 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   const uint32_t x_row = smem_u32(sm.X) + (uint32_t)r * (kC * kStatePad * 4);
   const uint32_t dx_row = smem_u32(sm.DX) + (uint32_t)r * (kC * kStatePad * 4);
   const uint32_t xsw = (uint32_t)swz_row(r);
-  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)r * (kC * 4);
-  const uint32_t sdu_row = smem_u32(sm.SDU) + (uint32_t)r * (kC * 4);
+  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)r * (kSP * 4);
+  const uint32_t sdu_row = smem_u32(sm.SDU) + (uint32_t)r * (kSP * 4);
   // contraction role of this thread: (tensor, position, 4 states, half of the rows)
   const int c_which = tid >> 6;                       // 0: dB from DX and delta*u, 1: dC from X and dy
   const int c_j = ((tid >> 5) & 1) * 4 + ((lane >> 2) & 3);
   const int c_nq = lane & 3;
   const int c_half = lane >> 4;                       // rows 16*c_half .. 16*c_half+15
   const uint32_t c_src = smem_u32(c_which ? sm.X : sm.DX);
-  const uint32_t c_scal = smem_u32(c_which ? sm.TDY : sm.TDU) + (uint32_t)(c_j * kR + c_half * 16) * 4;
+  const uint32_t c_scal = smem_u32(c_which ? sm.TDY : sm.TDU) + (uint32_t)(c_j * kTP + c_half * 16) * 4;
   float* __restrict__ dBC = (c_which ? a.dC : a.dB) + ((int64_t)b * a.ngroups + g) * N * (int64_t)L + (int64_t)(c_nq * 4) * L + c_j;
 
   for (int i = 0; i < n_tiles; ++i) {
@@ -225,11 +228,11 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sd_row + pj * 4), "f"(my_dl[0]), "f"(my_dl[1]) : "memory");
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sdu_row + pj * 4), "f"(du0), "f"(du1) : "memory");
         // transposed copies for the contraction: [position][row]
-        const uint32_t tdu = smem_u32(sm.TDU) + (uint32_t)(pj * kR + r) * 4, tdy = smem_u32(sm.TDY) + (uint32_t)(pj * kR + r) * 4;
+        const uint32_t tdu = smem_u32(sm.TDU) + (uint32_t)(pj * kTP + r) * 4, tdy = smem_u32(sm.TDY) + (uint32_t)(pj * kTP + r) * 4;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu), "f"(du0) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu + kR * 4), "f"(du1) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu + kTP * 4), "f"(du1) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy), "f"(my_dy[0]) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy + kR * 4), "f"(my_dy[1]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy + kTP * 4), "f"(my_dy[1]) : "memory");
       }
       __syncwarp();
       // ---------------- forward recompute from the saved state (states kept, decays recomputed later) ----------------

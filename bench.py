@@ -178,6 +178,66 @@ def run_reference_impl(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def model_leg(world, rank, dev, steps):
+    """MambaUnet (vmamba_tiny, 19.1 M parameters, random init) on synthetic 1x224x224 slices, 4 classes -- BASELINE configs 2-4.
+    The model is the from-scratch caller context (selscan_b200/vssm.py); every SS2D block runs the sm_100a scan."""
+    import torch
+    import torch.distributed as dist
+    from selscan_b200 import workloads as wl
+    from selscan_b200.vssm import DiceLoss, MambaUnet
+
+    torch.manual_seed(1337 + rank)
+    res = {}
+    dice = DiceLoss(4)
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    n = max(2, min(steps, 5))
+    model = MambaUnet(num_classes=4).to(dev)
+    x24 = torch.rand(24, 1, 224, 224, device=dev)
+    y24 = torch.randint(0, 4, (24, 224, 224), device=dev)
+    model.eval()
+    with torch.no_grad():
+        ms = timed(lambda: model(x24), n)
+    res["infer_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
+    model.train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if world > 1 else model
+    opt = wl.make_sgd(net)
+    ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
+    res["train_supervised_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
+    del net, opt, model
+    m1, m2 = MambaUnet(num_classes=4).to(dev).train(), MambaUnet(num_classes=4).to(dev).train()
+    if world > 1:
+        m1 = torch.nn.parallel.DistributedDataParallel(m1, device_ids=[dev.index])
+        m2 = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[dev.index])
+    o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
+    x16, y16 = x24[:16], y24[:16]
+    cw = wl.consistency_weight(3000)
+    ms = timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw), n)
+    res["train_semi_dual_bs16"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 16 / ms * 1e3, 1)}
+    res["note"] = ("img/s is the whole-job aggregate over %d GPU(s); per-GPU batch fixed (weak scaling); DDP gradient all-reduce over "
+                   "NCCL when n_gpus > 1 (19.1 M fp32 gradients per model)" % world)
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +247,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE config: 24)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-model", action="store_true", help="skip the MambaUnet img/s legs")
     ap.add_argument("--stages", default="", help="comma list to restrict (profiling only), e.g. S1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -379,6 +440,13 @@ def main():
                "sample": f"oracle/ref_torch.py (PyTorch port of selective_scan_ref) fwd + autograd bwd, first {dim} of 768 "
                          f"channel rows of config 1 (B=1, K=4, d_state=16, L={L}), one pass"}
 
+    model = None
+    if not args.no_model and not args.stages:
+        for t in bufs.values():
+            t.clear()
+        torch.cuda.empty_cache()
+        model = model_leg(world, rank, dev, args.steps)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -390,7 +458,7 @@ def main():
                        "l2": "inputs larger than L2: every call streams >= 234 MB (no explicit flush)",
                        "algorithmic_bytes_per_step": total_bytes, "parallelism": f"dp{world} (batch-sharded replicas)"},
             "frac_of_hbm_peak": round(value / world / peak, 4),
-            "roofline": roofline, "per_stage": table, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "per_stage": table, "mambaunet": model, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": args.steps * sum(2 * s[3] for s in stages), "wall_s_timed_region": round(t_wall, 3),
         }
         print(json.dumps(line), flush=True)

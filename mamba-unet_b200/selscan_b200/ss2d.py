@@ -1,0 +1,89 @@
+"""The SS2D core around the selective scan -- the second (fused) boundary of the hot path.
+
+Replaces `SS2D.forward_corev0` (/root/reference/code/networks/mamba_sys.py:396-436) with the same inputs, outputs and parameter
+tensors (`x_proj_weight`, `dt_projs_weight`, `dt_projs_bias`, `A_logs`, `Ds`, `out_norm`; mamba_sys.py:316-336), so checkpoints and the
+rest of `SS2D.forward` are untouched:
+
+    x (B, D, H, W)  ->  y (B, H, W, D)
+
+What differs from the reference's ~20 ATen kernels:
+  * cross-scan / cross-merge are single autograd Functions (4 writes / 4 reads instead of the stack+flip+cat and
+    flip+transpose+add chains and their saved intermediates);
+  * the two projections are batched GEMMs writing straight into contiguous (B, K, C, L) / (B, K, D, L) buffers, so `delta` needs no
+    `.contiguous()` copy (mamba_sys.py:412) and B / C are passed as strided views of x_dbl -- the kernels take any strides;
+  * the scan is the sm_100a kernel pair behind `selective_scan_fn`.
+"""
+import torch
+
+from .ops import selective_scan_fn
+
+
+class CrossScan(torch.autograd.Function):
+    """(B, D, H, W) -> (B, 4, D, L): row-major, column-major, and both reversed (mamba_sys.py:403-404)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, D, H, W = x.shape
+        ctx.hw = (H, W)
+        xs = x.new_empty((B, 4, D, H * W))
+        xs[:, 0] = x.reshape(B, D, H * W)
+        xs[:, 1] = x.transpose(2, 3).reshape(B, D, H * W)
+        xs[:, 2:4] = xs[:, 0:2].flip(-1)
+        return xs
+
+    @staticmethod
+    def backward(ctx, g):
+        H, W = ctx.hw
+        B, _, D, L = g.shape
+        row = g[:, 0] + g[:, 2].flip(-1)
+        col = g[:, 1] + g[:, 3].flip(-1)
+        return (row.view(B, D, H, W) + col.view(B, D, W, H).transpose(2, 3)).contiguous()
+
+
+class CrossMerge(torch.autograd.Function):
+    """(B, 4, D, L) scan outputs -> (B, D, L) in row-major order (mamba_sys.py:429-432)."""
+
+    @staticmethod
+    def forward(ctx, ys, H, W):
+        B, _, D, L = ys.shape
+        ctx.hw = (H, W)
+        row = ys[:, 0] + ys[:, 2].flip(-1)
+        col = ys[:, 1] + ys[:, 3].flip(-1)
+        return row + col.view(B, D, W, H).transpose(2, 3).reshape(B, D, L)
+
+    @staticmethod
+    def backward(ctx, g):
+        H, W = ctx.hw
+        B, D, L = g.shape
+        gs = g.new_empty((B, 4, D, L))
+        gs[:, 0] = g
+        gs[:, 1] = g.view(B, D, H, W).transpose(2, 3).reshape(B, D, L)
+        gs[:, 2:4] = gs[:, 0:2].flip(-1)
+        return gs, None, None
+
+
+def forward_core_b200(self, x: torch.Tensor):
+    """Drop-in for SS2D.forward_corev0: `self` is the SS2D module (mamba_sys.py:267-338)."""
+    B, D, H, W = x.shape
+    L = H * W
+    K = 4
+    R, N = self.dt_rank, self.d_state
+    xs = CrossScan.apply(x.float())                                                       # (B, K, D, L)
+    x_dbl = torch.matmul(self.x_proj_weight.float().unsqueeze(0), xs)                     # (B, K, R+2N, L)   :406
+    dts = torch.matmul(self.dt_projs_weight.float().unsqueeze(0), x_dbl[:, :, :R])        # (B, K, D, L)      :409
+    Bs = x_dbl[:, :, R:R + N]                                                             # strided views, no copy
+    Cs = x_dbl[:, :, R + N:]
+    As = -torch.exp(self.A_logs.float()).view(K * D, N)                                   # :417
+    out_y = selective_scan_fn(
+        xs.view(B, K * D, L), dts.view(B, K * D, L), As, Bs, Cs, self.Ds.float().view(-1), z=None,
+        delta_bias=self.dt_projs_bias.float().view(-1), delta_softplus=True, return_last_state=False)   # :420-426
+    y = CrossMerge.apply(out_y.view(B, K, D, L), H, W)                                    # (B, D, L)         :429-432
+    y = y.transpose(1, 2).contiguous().view(B, H, W, D)                                   # :433
+    return self.out_norm(y).to(x.dtype)                                                   # :434
+
+
+def patch_ss2d(ss2d_cls):
+    """Install the core on an SS2D class BEFORE models are built (`self.forward_core = self.forward_corev0` is bound in
+    __init__, mamba_sys.py:332)."""
+    ss2d_cls.forward_corev0 = forward_core_b200
+    return ss2d_cls

@@ -1,0 +1,63 @@
+"""Step bodies of the two training workloads BASELINE.json names, on synthetic tensors (the scripts themselves need ACDC data,
+tensorboardX, medpy ... which neither this image nor the GPU box has -- SURVEY.md section 7, hard part 8).
+
+    supervised_step   /root/reference/code/train_fully_supervised_2D_VIM.py:152-160   (bs 24, 0.5*(CE + Dice), SGD)
+    semi_step         /root/reference/code/train_Semi_Mamba_UNet.py:210-250           (bs 16 = 8 labeled + 8 unlabeled, two networks,
+                      cross pseudo supervision + ConstraLoss (code/utils/losses.py:169-181), one backward, two SGD steps)
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .vssm import DiceLoss
+
+
+def consistency_weight(iter_num, consistency=0.1, rampup=200.0):
+    """train_Semi_Mamba_UNet.py:126-128 with code/utils/ramps.py:20-28 (sigmoid ramp-up, evaluated every 150 iterations)."""
+    cur = min(max(iter_num // 150, 0.0), rampup)
+    phase = 1.0 - cur / rampup
+    return consistency * math.exp(-5.0 * phase * phase)
+
+
+def constra_loss(a, b):
+    """MSE between the L2-normalised global-average-pooled logits of the two networks (losses.py:169-181)."""
+    pa = F.normalize(a.mean(dim=(2, 3)), p=2, dim=1)
+    pb = F.normalize(b.mean(dim=(2, 3)), p=2, dim=1)
+    return ((pa - pb) ** 2).mean()
+
+
+def supervised_step(model, opt, dice, x, y):
+    out = model(x)
+    loss = 0.5 * (dice(torch.softmax(out, dim=1), y.unsqueeze(1)) + F.cross_entropy(out, y.long()))
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+def semi_step(model1, model2, opt1, opt2, dice, x, y, labeled_bs, cw):
+    o1, o2 = model1(x), model2(x)
+    s1, s2 = torch.softmax(o1, dim=1), torch.softmax(o2, dim=1)
+    lb = labeled_bs
+    loss1 = 0.5 * (F.cross_entropy(o1[:lb], y[:lb].long()) + dice(s1[:lb], y[:lb].unsqueeze(1)))
+    loss2 = 0.5 * (F.cross_entropy(o2[:lb], y[:lb].long()) + dice(s2[:lb], y[:lb].unsqueeze(1)))
+    p1 = torch.argmax(s1[lb:].detach(), dim=1)
+    p2 = torch.argmax(s2[lb:].detach(), dim=1)
+    ps1 = dice(s1[lb:], p2.unsqueeze(1))
+    ps2 = dice(s2[lb:], p1.unsqueeze(1))
+    con = constra_loss(o1, o2)
+    loss = (loss1 + cw * ps1 + 0.5 * con) + (loss2 + cw * ps2 + 0.5 * con)
+    opt1.zero_grad(set_to_none=True)
+    opt2.zero_grad(set_to_none=True)
+    loss.backward()
+    opt1.step()
+    opt2.step()
+    return loss
+
+
+def make_sgd(model, lr=0.01):
+    return torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4)
+
+
+__all__ = ["supervised_step", "semi_step", "make_sgd", "consistency_weight", "constra_loss", "DiceLoss"]

@@ -21,6 +21,7 @@ DDP would.  `--impl reference` times the reference's CPU path (the port) instead
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -278,24 +279,33 @@ def main():
     for name, d_inner, L, calls in stages:
         kd = K_DIR * d_inner
         t = {}
-        t["u"] = torch.randn(batch, kd, L, device=dev, generator=gen)
-        t["delta"] = 0.5 * torch.randn(batch, kd, L, device=dev, generator=gen)
+        def rows(fill=None):
+            # (batch, kd, L) with 16-byte aligned rows -- the layout forward_core_b200 / SelectiveScanFn allocate (L = 49 -> pitch 52)
+            r = ops.empty_rows(batch, kd, L, dev)
+            if fill is not None:
+                r.copy_(fill)
+            return r
+
+        t["u"] = rows(torch.randn(batch, kd, L, device=dev, generator=gen))
+        t["delta"] = rows(0.5 * torch.randn(batch, kd, L, device=dev, generator=gen))
         t["A"] = -torch.arange(1, N_STATE + 1, device=dev, dtype=torch.float32).repeat(kd, 1).contiguous()
         t["B"] = torch.randn(batch, K_DIR, N_STATE, L, device=dev, generator=gen)
         t["C"] = torch.randn(batch, K_DIR, N_STATE, L, device=dev, generator=gen)
         t["D"] = torch.ones(kd, device=dev)
-        dtv = torch.exp(torch.rand(kd, device=dev, generator=gen) * (torch.log(torch.tensor(0.1)) - torch.log(torch.tensor(0.001))) + torch.log(torch.tensor(0.001)))
+        dtv = torch.exp(torch.rand(kd, device=dev, generator=gen) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
         t["bias"] = dtv + torch.log(-torch.expm1(-dtv))
-        t["dout"] = torch.randn(batch, kd, L, device=dev, generator=gen)
-        t["out"] = torch.empty(batch, kd, L, device=dev)
+        t["dout"] = rows(torch.randn(batch, kd, L, device=dev, generator=gen))
+        t["out"] = rows()
         t["ckpt"] = torch.empty(max(ops.ckpt_elems(batch, kd, L, N_STATE), 4), device=dev)
-        t["du"] = torch.empty(batch, kd, L, device=dev)
-        t["ddelta"] = torch.empty(batch, kd, L, device=dev)
-        t["dA"] = torch.zeros(kd, N_STATE, device=dev)
-        t["dB"] = torch.zeros(batch, K_DIR, N_STATE, L, device=dev)
-        t["dC"] = torch.zeros(batch, K_DIR, N_STATE, L, device=dev)
-        t["dD"] = torch.zeros(kd, device=dev)
-        t["dbias"] = torch.zeros(kd, device=dev)
+        t["du"] = rows()
+        t["ddelta"] = rows()
+        nbc = batch * K_DIR * N_STATE * L
+        t["flat"] = torch.zeros(2 * nbc + kd * N_STATE + 2 * kd, device=dev)   # dB | dC | dA | dD | dbias: one memset per call
+        t["dB"] = t["flat"][:nbc].view(batch, K_DIR, N_STATE, L)
+        t["dC"] = t["flat"][nbc:2 * nbc].view(batch, K_DIR, N_STATE, L)
+        t["dA"] = t["flat"][2 * nbc:2 * nbc + kd * N_STATE].view(kd, N_STATE)
+        t["dD"] = t["flat"][2 * nbc + kd * N_STATE:2 * nbc + kd * N_STATE + kd]
+        t["dbias"] = t["flat"][2 * nbc + kd * N_STATE + kd:]
         bufs[name] = t
 
     ev_cache = []
@@ -305,8 +315,7 @@ def main():
         for name, d_inner, L, calls in stages:
             t = bufs[name]
             for _ in range(calls):
-                for k in ("dA", "dB", "dC", "dD", "dbias"):
-                    t[k].zero_()
+                t["flat"].zero_()
                 if record is not None:
                     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                     e0.record()
@@ -386,8 +395,8 @@ def main():
         h2d = d2h = 0
         for name, d_inner, L, calls in stages:
             t = bufs[name]
-            hin = {k: torch.empty(t[k].shape, dtype=torch.float32, pin_memory=True).copy_(t[k]) for k in ("u", "delta", "B", "C", "dout")}
-            hout = {k: torch.empty(t[k].shape, dtype=torch.float32, pin_memory=True) for k in ("out", "du", "ddelta", "dB", "dC", "dA", "dD", "dbias")}
+            hin = {k: torch.empty(tuple(t[k].shape), dtype=torch.float32, pin_memory=True).copy_(t[k]) for k in ("u", "delta", "B", "C", "dout")}
+            hout = {k: torch.empty(tuple(t[k].shape), dtype=torch.float32, pin_memory=True) for k in ("out", "du", "ddelta", "dB", "dC", "dA", "dD", "dbias")}
             host[name] = (hin, hout)
             h2d += calls * sum(v.numel() * 4 for v in hin.values())
             d2h += calls * sum(v.numel() * 4 for v in hout.values())

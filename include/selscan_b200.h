@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SELSCAN_B200_ABI_VERSION 1
+#define SELSCAN_B200_ABI_VERSION 2
 /* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
 #define SELSCAN_B200_CKPT_INTERVAL 8
 /* states are padded to this count inside the kernels and in the checkpoint buffer */
@@ -90,9 +90,12 @@ typedef struct selscan_bwd_args {
   int64_t z_batch_stride, z_d_stride;
   int64_t dout_batch_stride, dout_d_stride;
   int64_t out_batch_stride, out_d_stride;
-  float* du;                         /* (batch, dim, seqlen) contiguous, fully written */
-  float* ddelta;                     /* (batch, dim, seqlen) contiguous, fully written */
-  float* dz;                         /* (batch, dim, seqlen) contiguous; required iff z != NULL */
+  int64_t du_batch_stride, du_d_stride;          /* unit stride along seqlen; a row pitch that is a multiple of 4 */
+  int64_t ddelta_batch_stride, ddelta_d_stride;  /* floats keeps rows 16-byte aligned for uneven seqlen (e.g. 49 -> 52) */
+  int64_t dz_batch_stride, dz_d_stride;
+  float* du;                         /* (batch, dim, seqlen), fully written */
+  float* ddelta;                     /* (batch, dim, seqlen), fully written */
+  float* dz;                         /* (batch, dim, seqlen); required iff z != NULL */
   float* dA;                         /* (dim, dstate)                  contiguous, ZERO-INITIALISED by caller */
   float* dB;                         /* (batch, ngroups, dstate, seqlen) contiguous, ZERO-INITIALISED */
   float* dC;                         /* (batch, ngroups, dstate, seqlen) contiguous, ZERO-INITIALISED */

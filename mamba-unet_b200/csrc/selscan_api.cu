@@ -97,11 +97,14 @@ __attribute__((visibility("default"))) int selscan_b200_bwd(const selscan_bwd_ar
   if (p.n_ckpt > 0 && !a.ckpt) return fail("selscan_b200_bwd: ckpt (saved scan states from selscan_b200_fwd) is required when seqlen > %d", SELSCAN_B200_CKPT_INTERVAL);
   if (a.ckpt && !al16(a.ckpt)) return fail("selscan_b200_bwd: ckpt must be 16-byte aligned");
   p.tiles_per_group = (p.dim_per_group + 63) / 64;
-  p.vec_rows = m4(a.seqlen) && al16(a.u) && al16(a.delta) && al16(a.dout) && al16(a.du) && al16(a.ddelta) &&
+  if (a.du_d_stride < a.seqlen || a.ddelta_d_stride < a.seqlen || (a.z && a.dz_d_stride < a.seqlen))
+    return fail("selscan_b200_bwd: du / ddelta / dz channel strides must be >= seqlen");
+  p.vec_rows = al16(a.u) && al16(a.delta) && al16(a.dout) && al16(a.du) && al16(a.ddelta) &&
                m4(a.u_batch_stride) && m4(a.u_d_stride) && m4(a.delta_batch_stride) && m4(a.delta_d_stride) &&
-               m4(a.dout_batch_stride) && m4(a.dout_d_stride) &&
+               m4(a.dout_batch_stride) && m4(a.dout_d_stride) && m4(a.du_batch_stride) && m4(a.du_d_stride) &&
+               m4(a.ddelta_batch_stride) && m4(a.ddelta_d_stride) &&
                (!a.z || (al16(a.z) && al16(a.out) && al16(a.dz) && m4(a.z_batch_stride) && m4(a.z_d_stride) &&
-                         m4(a.out_batch_stride) && m4(a.out_d_stride)));
+                         m4(a.out_batch_stride) && m4(a.out_d_stride) && m4(a.dz_batch_stride) && m4(a.dz_d_stride)));
   const cudaError_t e = selscan::launch_bwd(p, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) {
     fail("selscan_b200_bwd: launch failed: %s", cudaGetErrorString(e));

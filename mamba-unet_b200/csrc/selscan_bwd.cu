@@ -60,15 +60,15 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
   const float* __restrict__ dout = a.dout + (int64_t)b * a.dout_batch_stride + (int64_t)d * a.dout_d_stride;
   const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
   const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
-  float* __restrict__ du = a.du + row * L;
-  float* __restrict__ ddt = a.ddelta + row * L;
+  float* __restrict__ du = a.du + (int64_t)b * a.du_batch_stride + (int64_t)d * a.du_d_stride;
+  float* __restrict__ ddt = a.ddelta + (int64_t)b * a.ddelta_batch_stride + (int64_t)d * a.ddelta_d_stride;
   const float* __restrict__ z = nullptr;
   const float* __restrict__ fout = nullptr;
   float* __restrict__ dz = nullptr;
   if (kHasZ) {
     z = a.z + (int64_t)b * a.z_batch_stride + (int64_t)d * a.z_d_stride;
     fout = a.out + (int64_t)b * a.out_batch_stride + (int64_t)d * a.out_d_stride;
-    dz = a.dz + row * L;
+    dz = a.dz + (int64_t)b * a.dz_batch_stride + (int64_t)d * a.dz_d_stride;
   }
   const float* __restrict__ ck = a.ckpt + row * p.n_ckpt * kStatePad + h * kHalf;
 

@@ -404,12 +404,13 @@ bool bwd_tma_eligible(const BwdLaunch& p) {
   const selscan_bwd_args& a = p.a;
   if (a.z != nullptr) return false;
   if (p.dim_per_group % kR != 0) return false;
-  if (p.n_ckpt < 1 || (a.seqlen & 3) != 0) return false;
+  if (p.n_ckpt < 1) return false;
   const int64_t zero = 0;
   if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : zero)) return false;
   if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : zero)) return false;
   if (!tma_row_ok(a.dout, a.dout_d_stride, a.batch > 1 ? a.dout_batch_stride : zero)) return false;
-  if (!tma_row_ok(a.du, a.seqlen, zero) || !tma_row_ok(a.ddelta, a.seqlen, zero)) return false;
+  if (!tma_row_ok(a.du, a.du_d_stride, a.batch > 1 ? a.du_batch_stride : zero)) return false;
+  if (!tma_row_ok(a.ddelta, a.ddelta_d_stride, a.batch > 1 ? a.ddelta_batch_stride : zero)) return false;
   if ((reinterpret_cast<uintptr_t>(a.ckpt) & 15u) != 0) return false;
   return tensor_map_encoder() != nullptr;
 }
@@ -417,12 +418,11 @@ bool bwd_tma_eligible(const BwdLaunch& p) {
 cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
   CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
-  const int64_t cs = (int64_t)a.dim * a.seqlen;
   if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kT, kR) ||
       !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kT, kR) ||
       !make_row_map(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kT, kR) ||
-      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.seqlen, cs, kT, 8) ||
-      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.seqlen, cs, kT, 8) ||
+      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kT, 8) ||
+      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kT, 8) ||
       !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
     return cudaErrorInvalidValue;
   const int smem = (int)sizeof(BwdTmaSmem) + 1024;

@@ -9,7 +9,7 @@ import threading
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "lib", "libselscan_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 CKPT_INTERVAL = 8
 STATE_PAD = 16
 
@@ -42,7 +42,8 @@ class BwdArgs(ctypes.Structure):
             "B_batch_stride", "B_group_stride", "B_n_stride", "B_l_stride",
             "C_batch_stride", "C_group_stride", "C_n_stride", "C_l_stride",
             "z_batch_stride", "z_d_stride", "dout_batch_stride", "dout_d_stride",
-            "out_batch_stride", "out_d_stride")]
+            "out_batch_stride", "out_d_stride", "du_batch_stride", "du_d_stride",
+            "ddelta_batch_stride", "ddelta_d_stride", "dz_batch_stride", "dz_d_stride")]
         + [(n, _ptr) for n in ("du", "ddelta", "dz", "dA", "dB", "dC", "dD", "ddelta_bias")]
     )
 

@@ -64,9 +64,22 @@ def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
     return batch, dim, seqlen, dstate
 
 
+def empty_rows(batch, dim, seqlen, device):
+    """(batch, dim, seqlen) fp32 with the row pitch rounded up to 4 floats: rows stay 16-byte aligned for uneven seqlen
+    (stage 4 of Mamba-UNet has L = 49), which is what the TMA-staged kernels need.  Contiguous when seqlen % 4 == 0."""
+    pitch = (seqlen + 3) // 4 * 4
+    buf = torch.empty((batch, dim, pitch), device=device, dtype=torch.float32)
+    return buf if pitch == seqlen else buf[:, :, :seqlen]
+
+
 def _rowmajor(t):
-    """Unit stride along seqlen (selective_scan_interface.py:19-22,29-30)."""
-    return t if t.stride(-1) == 1 else t.contiguous()
+    """Unit stride along seqlen (selective_scan_interface.py:19-22,29-30) AND 16-byte aligned rows: a tensor that only misses
+    the alignment (e.g. a contiguous L = 49 tensor) is copied once into a padded-pitch buffer so that it can take the tiled kernels."""
+    if (t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and t.stride(1) % 4 == 0 and (t.shape[0] == 1 or t.stride(0) % 4 == 0)):
+        return t
+    out = empty_rows(t.shape[0], t.shape[1], t.shape[2], t.device)
+    out.copy_(t)
+    return out
 
 
 def _strides2(t):
@@ -113,6 +126,9 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
         z_batch_stride=_strides2(z)[0], z_d_stride=_strides2(z)[1],
         dout_batch_stride=dout.stride(0), dout_d_stride=dout.stride(1),
         out_batch_stride=_strides2(out)[0], out_d_stride=_strides2(out)[1],
+        du_batch_stride=du.stride(0), du_d_stride=du.stride(1),
+        ddelta_batch_stride=ddelta.stride(0), ddelta_d_stride=ddelta.stride(1),
+        dz_batch_stride=_strides2(dz)[0], dz_d_stride=_strides2(dz)[1],
         du=_p(du), ddelta=_p(ddelta), dz=_p(dz), dA=_p(dA), dB=_p(dB), dC=_p(dC), dD=_p(dD),
         ddelta_bias=_p(ddelta_bias))
     with torch.cuda.device(u.device):
@@ -155,8 +171,8 @@ class SelectiveScanFn(torch.autograd.Function):
                                f"got {B.shape[1]} and {C.shape[1]}")
         needs_grad = any(ctx.needs_input_grad)
         with torch.cuda.device(u.device):
-            out = torch.empty((batch, dim, seqlen), device=u.device, dtype=torch.float32)
-            out_z = torch.empty_like(out) if z is not None else None
+            out = empty_rows(batch, dim, seqlen, u.device)
+            out_z = empty_rows(batch, dim, seqlen, u.device) if z is not None else None
             last_state = (torch.empty((batch, dim, dstate), device=u.device, dtype=torch.float32)
                           if return_last_state else None)
             ckpt = None
@@ -191,15 +207,17 @@ class SelectiveScanFn(torch.autograd.Function):
         batch, dim, seqlen = u.shape
         dstate, ngroups = A.shape[1], B.shape[1]
         with torch.cuda.device(u.device):
-            du = torch.empty((batch, dim, seqlen), device=u.device, dtype=torch.float32)
-            ddelta = torch.empty_like(du)
-            dz = torch.empty_like(du) if z is not None else None
-            # reductions are accumulated in fp32 with atomics: zero-initialised, as selective_scan.cpp:458-466
-            dA = torch.zeros((dim, dstate), device=u.device, dtype=torch.float32)
-            dB = torch.zeros((batch, ngroups, dstate, seqlen), device=u.device, dtype=torch.float32)
-            dC = torch.zeros_like(dB)
-            dD = torch.zeros((dim,), device=u.device, dtype=torch.float32) if D is not None else None
-            dbias = torch.zeros((dim,), device=u.device, dtype=torch.float32) if delta_bias is not None else None
+            du = empty_rows(batch, dim, seqlen, u.device)
+            ddelta = empty_rows(batch, dim, seqlen, u.device)
+            dz = empty_rows(batch, dim, seqlen, u.device) if z is not None else None
+            # reductions are accumulated in fp32 with atomics: zero-initialised, as selective_scan.cpp:458-466 -- one memset
+            nbc = batch * ngroups * dstate * seqlen
+            flat = torch.zeros((2 * nbc + dim * dstate + 2 * dim,), device=u.device, dtype=torch.float32)
+            dB = flat[:nbc].view(batch, ngroups, dstate, seqlen)
+            dC = flat[nbc:2 * nbc].view(batch, ngroups, dstate, seqlen)
+            dA = flat[2 * nbc:2 * nbc + dim * dstate].view(dim, dstate)
+            dD = flat[2 * nbc + dim * dstate:2 * nbc + dim * dstate + dim] if D is not None else None
+            dbias = flat[2 * nbc + dim * dstate + dim:] if delta_bias is not None else None
             launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, ctx.delta_softplus,
                        du, ddelta, dA, dB, dC, dD, dz, dbias)
         dB = dB.squeeze(1) if ctx.squeeze_B else dB  # selective_scan_interface.py:67-68

@@ -18,6 +18,13 @@ import torch
 from .ops import selective_scan_fn
 
 
+def _empty_dirs(ref, B, D, L):
+    """(B, 4, D, L) fp32 whose rows are 16-byte aligned for any L (pitch rounded up to 4 floats, cf. ops.empty_rows)."""
+    pitch = (L + 3) // 4 * 4
+    buf = ref.new_empty((B, 4, D, pitch))
+    return buf if pitch == L else buf[..., :L]
+
+
 class CrossScan(torch.autograd.Function):
     """(B, D, H, W) -> (B, 4, D, L): row-major, column-major, and both reversed (mamba_sys.py:403-404)."""
 
@@ -25,7 +32,7 @@ class CrossScan(torch.autograd.Function):
     def forward(ctx, x):
         B, D, H, W = x.shape
         ctx.hw = (H, W)
-        xs = x.new_empty((B, 4, D, H * W))
+        xs = _empty_dirs(x, B, D, H * W)
         xs[:, 0] = x.reshape(B, D, H * W)
         xs[:, 1] = x.transpose(2, 3).reshape(B, D, H * W)
         xs[:, 2:4] = xs[:, 0:2].flip(-1)
@@ -55,7 +62,7 @@ class CrossMerge(torch.autograd.Function):
     def backward(ctx, g):
         H, W = ctx.hw
         B, D, L = g.shape
-        gs = g.new_empty((B, 4, D, L))
+        gs = _empty_dirs(g, B, D, L)
         gs[:, 0] = g
         gs[:, 1] = g.view(B, D, H, W).transpose(2, 3).reshape(B, D, L)
         gs[:, 2:4] = gs[:, 0:2].flip(-1)

@@ -1,28 +1,36 @@
 // Backward selective scan, tiled path for sm_100a: TMA-staged tiles walked from the end of the sequence,
 // mbarrier pipeline, packed f32x2 arithmetic.  Replaces selective_scan_bwd_kernel
 // (/root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489) for the aligned shapes Mamba-UNet
-// produces (channels per group a multiple of 32, 16-byte aligned rows, no z); everything else takes selscan_bwd.cu.
+// produces (channels per group a multiple of 64, 16-byte aligned rows, no z); everything else takes selscan_bwd.cu.
 //
-// CTA = 32 channels of one (batch, group); the sequence is walked backwards in chunks of 8 positions (the checkpoint
-// interval).  52 KB of shared memory and 96 registers per thread: four CTAs = 16 compute warps per SM, which makes a
-// batch-24 stage-1 call exactly one wave.
-//   warp 4 (producer): per chunk one elected lane issues TMA loads of u, delta, dout (box 32 rows x 8 positions) and of
-//       the saved scan state the chunk restarts from (box 32 rows x 16 states; the state "before position 0" is the
-//       tensor map's out-of-bounds zero fill); all lanes gather the chunk's B/C into a [position][32] tile.
-//   warps 0-3 (compute): 8 channels each, four lanes per channel, 4 states per lane.  Per chunk:
-//       prep     lane j of a channel discretises positions 2j, 2j+1 (softplus, sigmoid) and publishes delta and
-//                delta*u for its channel; nothing is computed twice;
-//       forward  restart from the saved state: per position and state pair FMUL2, 2 MUFU.EX2, FMUL2, FFMA2; the
-//                states go to the swizzled X tile (decays are recomputed in the reverse pass: MUFU has slack,
-//                registers do not);
-//       reverse  dx = C*dy + a*dx', in registers; dx goes to the DX tile; partial sums of du / ddelta over the lane's 4
-//                states, dA accumulated in registers;
-//       reduce   the partial sums are reduce-scattered over the 4 lanes (lane j finalises positions 2j, 2j+1: du, ddelta
-//                through softplus', dD, ddelta_bias) into du/ddelta tiles that leave by per-warp TMA stores.
-//   contraction: after a named barrier over the 4 compute warps, the CTA contracts X and DX over its 32 channels
-//       (dC = sum_d dy*x, dB = sum_d delta*u*dx; thread = (tensor, position, 4 states, row parity)) and adds ONE value
-//       per (state, position) to global memory -- the reference issues one atomic per (channel, state, position)
+// What bounds this kernel on B200 is the shared-memory -> register return path (128 B/clk/SM): a 128-bit shared load
+// costs 4 wavefronts even when the whole warp reads the same 64 bytes (measured, profiles/r01_ncu_bwd_*), so the design
+// minimises BYTES PER THREAD through that pipe:
+//   * a thread owns TWO channels x 4 states: every B/C value it loads serves both channels, and the channel-pair
+//     products for dB/dC are summed in registers before they touch shared memory (half the contraction traffic);
+//   * the chunk's states stay in registers (packed pairs); decays are recomputed in the reverse pass (MUFU has slack).
+//
+// CTA = 64 channels of one (batch, group); the sequence is walked backwards in chunks of 8 positions (the checkpoint
+// interval).
+//   staging: one elected thread issues, one chunk ahead, TMA loads of u, delta, dout (box 64 rows x 8 positions) and of the
+//       saved scan state the chunk restarts from (box 64 rows x 16 states; the state "before position 0" is the tensor
+//       map's out-of-bounds zero fill) into a 2-stage ring; all threads prefetch the next chunk's B/C (any strides) into a
+//       [position][32] tile.  There is no dedicated producer warp: 4-warp CTAs put at most 2 warps on an SM
+//       sub-partition, which is what lets a thread hold ~200 registers at 2 CTAs/SM.
+//   4 warps, 8 channel pairs each, four lanes per pair.  Per chunk:
+//       prep     lane j of a pair discretises positions j and 4+j of both channels (softplus, sigmoid) and publishes
+//                delta and delta*u; nothing is computed twice;
+//       forward  restart from the saved state: per position, channel and state pair FMUL2, 2 MUFU.EX2, FMUL2, FFMA2;
+//       reverse  dx = C*dy + a*dx' in registers; partial sums of du / ddelta over the lane's 4 states, dA in registers;
+//                pair products (delta*u)*dx and dy*x go to the swizzled P tile;
+//       reduce   per half chunk the partial sums are reduce-scattered over the 4 lanes (lane j finalises position j of
+//                the half for both channels: du, ddelta through softplus', dD, ddelta_bias) into du/ddelta tiles that
+//                leave by per-warp TMA stores.
+//   contraction: after a named barrier over the 4 compute warps the CTA sums P over its 32 channel pairs and adds ONE
+//       value per (state, position) to global memory -- the reference issues one atomic per (channel, state, position)
 //       (bwd_kernel.cuh:298-316).
+#include <type_traits>
+
 #include "selscan_common.cuh"
 #include "selscan_kernels.h"
 #include "selscan_ptx.cuh"
@@ -32,38 +40,31 @@ namespace selscan {
 
 namespace {
 
-constexpr int kR = 32;            // channels per CTA
-constexpr int kW = 4;             // compute warps
-constexpr int kT = 8;             // positions per staged tile = one chunk
-constexpr int kC = kCkptInterval; // positions per chunk (8)
+constexpr int kR = 64;            // channels per CTA
+constexpr int kNP = kR / 2;       // channel pairs per CTA
+constexpr int kW = 4;             // compute warps (8 pairs = 16 channels each)
+constexpr int kC = kCkptInterval; // positions per chunk = per staged tile (8)
 constexpr int kStg = 2;
 constexpr int kPitch = 36;        // B/C tile pitch (floats)
-constexpr int kThr = (kW + 1) * 32;
+constexpr int kThr = kW * 32;     // no dedicated producer warp: 4-warp CTAs keep <= 2 warps per SM sub-partition (255 regs)
 constexpr int kLS = kStatePad / 4;  // states per lane
-constexpr int kSP = 12;           // row pitch of the per-row scalar scratch (floats)
-constexpr int kTP = 36;           // position pitch of the transposed scalar scratch (floats)
+constexpr int kSP = 12;           // row pitch of the per-row scalar scratch (floats): conflict-free LDS.128
 
 struct BwdTmaSmem {
-  float CK[kStg][kR * kStatePad];   // 2 KB: [row][16 states]
-  float U[kStg][kR * kT];           // 1 KB: [row][8]
-  float DT[kStg][kR * kT];
-  float DY[kStg][kR * kT];
-  float BC[kStg][kT * kPitch];
-  float X[kR * kC * kStatePad];     // 16 KB, swizzled [row][pos][state]
-  float DX[kR * kC * kStatePad];
-  float SD[kR * kSP];               // delta   per (row, position of the chunk): [row][pos], pitch 12 (conflict-free LDS.128)
-  float SDU[kR * kSP];              // delta*u                                    [row][pos]
-  float TDU[kC * kTP];              // delta*u, transposed for the contraction    [pos][row], pitch 36
-  float TDY[kC * kTP];              // dout                                       [pos][row]
-  float DU[kW][2][8 * kT];          // per-warp output tiles, double-buffered (256 B each)
-  float DDT[kW][2][8 * kT];
+  float CK[kStg][kR * kStatePad];   // 4 KB: [row][16 states]
+  float U[kStg][kR * kC];           // 2 KB: [row][8]
+  float DT[kStg][kR * kC];
+  float DY[kStg][kR * kC];
+  float BC[kStg][kC * kPitch];
+  float P[kNP * kC * 32];           // 32 KB, swizzled [pair][pos][dB 0..15 | dC 0..15]
+  float SD[kR * kSP];               // delta   per (row, position of the chunk)
+  float SDU[kR * kSP];              // delta*u
+  float DU[kW][2][16 * kC];         // per-warp output tiles, double-buffered (512 B each)
+  float DDT[kW][2][16 * kC];
   u64 full[kStg];
-  u64 empty[kStg];
 };
 
-__device__ __forceinline__ int swz_row(int r) { return ((r & 1) << 2) | ((r >> 1) & 3); }
-// float index of the 4-state group nq of position j of row r in the X / DX tiles
-__device__ __forceinline__ int xt_idx(int r, int j, int nq) { return r * (kC * kStatePad) + (((j * 4 + nq) ^ swz_row(r)) << 2); }
+__device__ __forceinline__ uint32_t swz8(int p) { return (uint32_t)(((p & 1) << 2) | ((p >> 1) & 3)); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -72,8 +73,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
                "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_2x64(uint32_t addr, u64 a, u64 b) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
 
-__global__ void __launch_bounds__(kThr, 4)
+__global__ void __launch_bounds__(kThr, 2)
 selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                        const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
                        const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt, const BwdLaunch p) {
@@ -88,12 +98,11 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   const int g = bid % a.ngroups;
   const int b = bid / a.ngroups;
   const int d0 = g * p.dim_per_group + tile_g * kR;
-  const int n_tiles = (L + kT - 1) / kT;
+  const int n_tiles = (L + kC - 1) / kC;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStg; ++s) {
-      mbar_init(smem_u32(&sm.full[s]), 32);
-      mbar_init(smem_u32(&sm.empty[s]), kW);
+      mbar_init(smem_u32(&sm.full[s]), 1);   // the elected thread's arrive.expect_tx; TMA completes the bytes
     }
     mbar_fence_init();
     tma_prefetch_desc(&map_u);
@@ -105,262 +114,274 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   }
   __syncthreads();
 
-  if (warp == kW) {
-    // ================================ producer ================================
-    const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
-    const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
-    const bool lanes_along_l = (a.B_l_stride == 1 && a.C_l_stride == 1);
-    const int row0 = b * a.dim + d0;
-    for (int i = 0; i < n_tiles; ++i) {
-      const int t = n_tiles - 1 - i;                 // tiles are consumed last -> first
-      const int s = i % kStg, k = i / kStg;
-      if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
-      const int l0 = t * kT;
-      const uint32_t full = smem_u32(&sm.full[s]);
-      if (lane == 0) {
-        mbar_expect_tx(full, (uint32_t)(3 * kR * kT * 4 + kR * kStatePad * 4));
-        tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
-        tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
-        tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
-        // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
-        tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, row0, full);
-      }
-      float* bc = sm.BC[s];
-      float v[8];
-      if (lanes_along_l) {   // lane = (group of 8 values, position): 32 contiguous bytes per 8 lanes
-        const int pos = lane & 7, grp = lane >> 3;       // values 8*grp .. 8*grp+7 of [B0..15 C0..15]
-        const int l = l0 + pos;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int vi = grp * 8 + q, n = vi & 15;
-          const float* src = (vi >= 16) ? (Cg + (int64_t)n * a.C_n_stride) : (Bg + (int64_t)n * a.B_n_stride);
-          v[q] = (n < N && l < L) ? __ldg(src + l) : 0.f;
-        }
-        const uint32_t dst = smem_u32(bc) + (uint32_t)(pos * kPitch + grp * 8) * 4;
-        sts_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
-        sts_f4(dst + 16, make_float4(v[4], v[5], v[6], v[7]));
-      } else {               // lane = (B|C, state): the 16 B and 16 C values of one position are contiguous
-        const int n = lane & 15;
-        const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
-        const int64_t ls = (lane < 16) ? a.B_l_stride : a.C_l_stride;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bc[j * kPitch + lane] = v[j];
-      }
-      mbar_arrive(full);
-    }
-    return;
+  // ---- staging (no dedicated producer warp): thread 0 issues the TMA loads of a chunk, all 128 threads gather its B/C ----
+  const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
+  const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
+  const bool lanes_along_l = (a.B_l_stride == 1 && a.C_l_stride == 1);
+  const int row0 = b * a.dim + d0;
+  auto issue_tma = [&](int i) {           // chunk index in processing order -> stage i % kStg
+    const int t = n_tiles - 1 - i, s = i % kStg, l0 = t * kC;
+    const uint32_t full = smem_u32(&sm.full[s]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(3 * kR * kC * 4 + kR * kStatePad * 4)) : "memory");
+    tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
+    tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
+    tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
+    // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
+    tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, row0, full);
+  };
+  // element e (0..255) of a chunk's [8 positions][B0..15 C0..15] tile handled by thread (e & 127), two per thread
+  auto bc_load = [&](int i, int e) -> float {
+    const int t = n_tiles - 1 - i, l0 = t * kC;
+    const int pos = lanes_along_l ? (e & 7) : (e >> 5), val = lanes_along_l ? (e >> 3) : (e & 31);
+    const int n = val & 15, l = l0 + pos;
+    const float* src = (val >= 16) ? (Cg + (int64_t)n * a.C_n_stride + (int64_t)l * a.C_l_stride)
+                                   : (Bg + (int64_t)n * a.B_n_stride + (int64_t)l * a.B_l_stride);
+    return (n < N && l < L) ? __ldg(src) : 0.f;
+  };
+  auto bc_store = [&](int i, int e, float v) {
+    const int pos = lanes_along_l ? (e & 7) : (e >> 5), val = lanes_along_l ? (e >> 3) : (e & 31);
+    sm.BC[i % kStg][pos * kPitch + val] = v;
+  };
+  {
+    if (threadIdx.x == 0) issue_tma(0);
+    const float v0 = bc_load(0, threadIdx.x), v1 = bc_load(0, threadIdx.x + kThr);
+    bc_store(0, threadIdx.x, v0);
+    bc_store(0, threadIdx.x + kThr, v1);
   }
+  __syncthreads();
 
   // ================================ compute warps ================================
-  const int tid = threadIdx.x;            // 0..127
   const int sq = lane & 3;                // which 4 states
-  const int rw = lane >> 2;               // channel inside the warp
-  const int r = warp * 8 + rw;            // channel inside the CTA
-  const int d = d0 + r;
+  const int pr = lane >> 2;               // channel pair inside the warp
+  const int pp = warp * 8 + pr;           // channel pair inside the CTA
+  const int rA = 2 * pp;                  // rows (channels inside the CTA) rA and rA + 1
   const bool hi1 = (sq & 2) != 0, hi0 = (sq & 1) != 0;
-  u64 A2p[2], dA2[2], w2[2];
+  u64 A2p[2][2], dA2[2][2], w2[2][2];
+  float Dv[2], bias[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int n0 = sq * kLS + 2 * q;
-    const float a0 = (n0 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n0 * a.A_n_stride) * kLog2e : 0.f;
-    const float a1 = (n0 + 1 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + 1) * a.A_n_stride) * kLog2e : 0.f;
-    A2p[q] = pk2(a0, a1);
-    dA2[q] = pk2(0.f, 0.f);
-    w2[q] = pk2(0.f, 0.f);   // a_{l+1} * dx_{l+1}: zero beyond the last position
+  for (int c = 0; c < 2; ++c) {
+    const int d = d0 + rA + c;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int n0 = sq * kLS + 2 * q;
+      const float a0 = (n0 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n0 * a.A_n_stride) * kLog2e : 0.f;
+      const float a1 = (n0 + 1 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + 1) * a.A_n_stride) * kLog2e : 0.f;
+      A2p[c][q] = pk2(a0, a1);
+      dA2[c][q] = pk2(0.f, 0.f);
+      w2[c][q] = pk2(0.f, 0.f);   // a_{l+1} * dx_{l+1}: zero beyond the last position
+    }
+    Dv[c] = a.D ? __ldg(a.D + d) : 0.f;
+    bias[c] = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
   }
-  const float Dv = a.D ? __ldg(a.D + d) : 0.f;
-  const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
   const bool softplus = a.delta_softplus != 0;
-  float dD_acc = 0.f, dbias_acc = 0.f;
+  float dD_acc[2] = {0.f, 0.f}, dbias_acc[2] = {0.f, 0.f};
   // shared-space addresses of this thread's slots
-  const uint32_t x_row = smem_u32(sm.X) + (uint32_t)r * (kC * kStatePad * 4);
-  const uint32_t dx_row = smem_u32(sm.DX) + (uint32_t)r * (kC * kStatePad * 4);
-  const uint32_t xsw = (uint32_t)swz_row(r);
-  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)r * (kSP * 4);
-  const uint32_t sdu_row = smem_u32(sm.SDU) + (uint32_t)r * (kSP * 4);
-  // contraction role of this thread: (tensor, position, 4 states, half of the rows)
-  const int c_which = tid >> 6;                       // 0: dB from DX and delta*u, 1: dC from X and dy
-  const int c_j = ((tid >> 5) & 1) * 4 + ((lane >> 2) & 3);
-  const int c_nq = lane & 3;
-  const int c_half = lane >> 4;                       // rows 16*c_half .. 16*c_half+15
-  const uint32_t c_src = smem_u32(c_which ? sm.X : sm.DX);
-  const uint32_t c_scal = smem_u32(c_which ? sm.TDY : sm.TDU) + (uint32_t)(c_j * kTP + c_half * 16) * 4;
-  float* __restrict__ dBC = (c_which ? a.dC : a.dB) + ((int64_t)b * a.ngroups + g) * N * (int64_t)L + (int64_t)(c_nq * 4) * L + c_j;
+  const uint32_t p_row = smem_u32(sm.P) + (uint32_t)pp * (kC * 32 * 4);
+  const uint32_t psw = swz8(pr);
+  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)rA * (kSP * 4);
+  const uint32_t sdu_row = smem_u32(sm.SDU) + (uint32_t)rA * (kSP * 4);
+  // contraction role: 16-byte chunk q of the [8 positions][32 values] output, half h of the channel pairs
+  const int c_q = warp * 16 + (lane & 15);
+  const int c_j = c_q >> 3, c_c = c_q & 7;
+  const int c_h = lane >> 4;
+  float* __restrict__ dBC = ((c_c >= 4) ? a.dC : a.dB) + ((int64_t)b * a.ngroups + g) * N * (int64_t)L + (int64_t)((c_c & 3) * 4) * L + c_j;
 
   for (int i = 0; i < n_tiles; ++i) {
     const int t = n_tiles - 1 - i;
     const int s = i % kStg, k = i / kStg;
-    const int l0 = t * kT;
+    const int c0 = t * kC;                  // first position of the chunk
+    // prefetch the next chunk: its stage was released by the barrier that ended chunk i-1
+    const bool has_next = (i + 1 < n_tiles);
+    float nb0 = 0.f, nb1 = 0.f;
+    if (has_next) {
+      if (threadIdx.x == 0) issue_tma(i + 1);
+      nb0 = bc_load(i + 1, threadIdx.x);
+      nb1 = bc_load(i + 1, threadIdx.x + kThr);
+    }
     mbar_wait(smem_u32(&sm.full[s]), k & 1);
-    const uint32_t u_row = smem_u32(sm.U[s]) + r * (kT * 4);
-    const uint32_t dt_row = smem_u32(sm.DT[s]) + r * (kT * 4);
-    const uint32_t dy_row = smem_u32(sm.DY[s]) + r * (kT * 4);
-    const uint32_t ck_row = smem_u32(sm.CK[s]) + r * (kStatePad * 4);
+    const uint32_t u_row = smem_u32(sm.U[s]) + rA * (kC * 4);
+    const uint32_t dt_row = smem_u32(sm.DT[s]) + rA * (kC * 4);
+    const uint32_t dy_row = smem_u32(sm.DY[s]) + rA * (kC * 4);
+    const uint32_t ck_row = smem_u32(sm.CK[s]) + rA * (kStatePad * 4) + sq * 16;
+    const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLS * 4);
     const uint32_t du_tile = smem_u32(sm.DU[warp][i & 1]);
     const uint32_t ddt_tile = smem_u32(sm.DDT[warp][i & 1]);
 
-    {
-      const int c0 = l0;                    // first position of the chunk
-      // ---------------- prep: my two positions (2sq, 2sq+1) of the chunk ----------------
-      const int pj = 2 * sq;
-      float my_dl[2], my_sg[2], my_u[2], my_dy[2];
-      {
-        const uint32_t off = (uint32_t)pj * 4;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(my_u[0]), "=f"(my_u[1]) : "r"(u_row + off));
-        float din[2];
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(din[0]), "=f"(din[1]) : "r"(dt_row + off));
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(my_dy[0]), "=f"(my_dy[1]) : "r"(dy_row + off));
+    // ---------------- prep: positions sq and 4+sq of both channels ----------------
+    float my_sg[2][2];   // [channel][half]; u, dy and delta of my elements are re-read from shared memory when finalising
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float xb = din[e] + bias;
-          float v = xb, sgm = 1.f;
-          if (softplus) {
-            float wexp;
-            v = softplus_fast(xb, wexp);
-            sgm = sigmoid_from_w(xb, wexp);   // softplus' (bwd_kernel.cuh:446-450; == 1 to rounding for x > 20)
-          }
-          my_dl[e] = ((c0 + pj + e) < L) ? v : 0.f;   // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
-          my_sg[e] = sgm;
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t off = (uint32_t)(c * kC + hf * 4 + sq) * 4;
+        const float my_u = lds_f1(u_row + off);
+        const float xb = lds_f1(dt_row + off) + bias[c];
+        float v = xb, sgm = 1.f;
+        if (softplus) {
+          float wexp;
+          v = softplus_fast(xb, wexp);
+          sgm = sigmoid_from_w(xb, wexp);   // softplus' (bwd_kernel.cuh:446-450; == 1 to rounding for x > 20)
         }
-        const float du0 = my_dl[0] * my_u[0], du1 = my_dl[1] * my_u[1];
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sd_row + pj * 4), "f"(my_dl[0]), "f"(my_dl[1]) : "memory");
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sdu_row + pj * 4), "f"(du0), "f"(du1) : "memory");
-        // transposed copies for the contraction: [position][row]
-        const uint32_t tdu = smem_u32(sm.TDU) + (uint32_t)(pj * kTP + r) * 4, tdy = smem_u32(sm.TDY) + (uint32_t)(pj * kTP + r) * 4;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu), "f"(du0) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdu + kTP * 4), "f"(du1) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy), "f"(my_dy[0]) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(tdy + kTP * 4), "f"(my_dy[1]) : "memory");
+        v = ((c0 + hf * 4 + sq) < L) ? v : 0.f;   // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
+        my_sg[c][hf] = sgm;
+        const uint32_t so = (uint32_t)(c * kSP + hf * 4 + sq) * 4;
+        sts_f1(sd_row + so, v);
+        sts_f1(sdu_row + so, v * my_u);
       }
-      __syncwarp();
-      // ---------------- forward recompute from the saved state (states kept, decays recomputed later) ----------------
-      u64 x0[2];
-      lds_2x64(ck_row + (uint32_t)sq * 16, x0[0], x0[1]);
-      const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLS * 4);
-      {
-        const float4 dA_ = lds_f4(sd_row), dB_ = lds_f4(sd_row + 16);
-        const float4 uA_ = lds_f4(sdu_row), uB_ = lds_f4(sdu_row + 16);
-        const float dl[kC] = {dA_.x, dA_.y, dA_.z, dA_.w, dB_.x, dB_.y, dB_.z, dB_.w};
-        const float du_[kC] = {uA_.x, uA_.y, uA_.z, uA_.w, uB_.x, uB_.y, uB_.z, uB_.w};
-        u64 xr0 = x0[0], xr1 = x0[1];   // running state; every x_j goes to the X tile (also read back by the reverse pass)
-#pragma unroll
-        for (int j = 0; j < kC; ++j) {
-          u64 Bp[2];
-          lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
-          const u64 dd = pk2(dl[j], dl[j]);
-          const u64 duu = pk2(du_[j], du_[j]);
-          float t0, t1, t2, t3;
-          upk2(mul2(dd, A2p[0]), t0, t1);
-          upk2(mul2(dd, A2p[1]), t2, t3);
-          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
-          xr0 = fma2(e0, xr0, mul2(duu, Bp[0]));
-          xr1 = fma2(e1, xr1, mul2(duu, Bp[1]));
-          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(x_row + ((((uint32_t)(j * 4 + sq)) ^ xsw) << 4)), "l"(xr0), "l"(xr1) : "memory");
-        }
-      }
-      // ---------------- reverse recurrence ----------------
-      float s1p[kC], s2p[kC];
-      {
-        const float4 dA_ = lds_f4(sd_row), dB_ = lds_f4(sd_row + 16);
-        const float4 yA_ = lds_f4(dy_row), yB_ = lds_f4(dy_row + 16);
-        const float dl[kC] = {dA_.x, dA_.y, dA_.z, dA_.w, dB_.x, dB_.y, dB_.z, dB_.w};
-        const float dy[kC] = {yA_.x, yA_.y, yA_.z, yA_.w, yB_.x, yB_.y, yB_.z, yB_.w};
-#pragma unroll
-        for (int j = kC - 1; j >= 0; --j) {
-          u64 Bp[2], Cp[2];
-          lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
-          lds_2x64(bc_base + (uint32_t)j * (kPitch * 4) + 64, Cp[0], Cp[1]);
-          const u64 dyy = pk2(dy[j], dy[j]);
-          const u64 dd = pk2(dl[j], dl[j]);
-          float t0, t1, t2, t3;                                          // decays again: MUFU has slack, registers do not
-          upk2(mul2(dd, A2p[0]), t0, t1);
-          upk2(mul2(dd, A2p[1]), t2, t3);
-          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
-          const u64 dx0 = fma2(Cp[0], dyy, w2[0]);                      // dx_{l,n}
-          const u64 dx1 = fma2(Cp[1], dyy, w2[1]);
-          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(dx_row + ((((uint32_t)(j * 4 + sq)) ^ xsw) << 4)), "l"(dx0), "l"(dx1) : "memory");
-          s1p[j] = hsum2(fma2(dx1, Bp[1], mul2(dx0, Bp[0])));           // sum_n dx * B          (bwd_kernel.cuh:280-281)
-          u64 xp0 = x0[0], xp1 = x0[1];                                   // x_{l-1}: my own slot of the X tile
-          if (j > 0) lds_2x64(x_row + ((((uint32_t)((j - 1) * 4 + sq)) ^ xsw) << 4), xp0, xp1);
-          const u64 wg0 = mul2(dx0, mul2(e0, xp0));                       // dx * a_l * x_{l-1}  (:283, x - b form)
-          const u64 wg1 = mul2(dx1, mul2(e1, xp1));
-          s2p[j] = hsum2(fma2(wg1, A2p[1], mul2(wg0, A2p[0])));          // in units of log2(e)
-          dA2[0] = fma2(wg0, dd, dA2[0]);                                 // :286
-          dA2[1] = fma2(wg1, dd, dA2[1]);
-          w2[0] = mul2(e0, dx0);                                          // carried to position l-1
-          w2[1] = mul2(e1, dx1);
-        }
-      }
-      // ---------------- reduce-scatter s1 / s2 over the 4 lanes: lane sq finalises positions 2sq, 2sq+1 ----------------
-      float f1[2], f2[2];
-      {
-        float k1[4], k2[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float snd1 = hi1 ? s1p[e] : s1p[4 + e], snd2 = hi1 ? s2p[e] : s2p[4 + e];
-          k1[e] = (hi1 ? s1p[4 + e] : s1p[e]) + __shfl_xor_sync(0xffffffffu, snd1, 2);
-          k2[e] = (hi1 ? s2p[4 + e] : s2p[e]) + __shfl_xor_sync(0xffffffffu, snd2, 2);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float snd1 = hi0 ? k1[e] : k1[2 + e], snd2 = hi0 ? k2[e] : k2[2 + e];
-          f1[e] = (hi0 ? k1[2 + e] : k1[e]) + __shfl_xor_sync(0xffffffffu, snd1, 1);
-          f2[e] = (hi0 ? k2[2 + e] : k2[e]) + __shfl_xor_sync(0xffffffffu, snd2, 1);
-        }
-      }
-      {
-        float o_du[2], o_dd[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          o_du[e] = fmaf(my_dl[e], f1[e], Dv * my_dy[e]);                          // :211, :280
-          o_dd[e] = fmaf(my_u[e], f1[e], f2[e] * kLn2) * my_sg[e];                 // :281-284, :446-450
-          dbias_acc += ((c0 + pj + e) < L) ? o_dd[e] : 0.f;
-          dD_acc = fmaf(my_dy[e], my_u[e], dD_acc);                                // :213
-        }
-        const uint32_t off = (uint32_t)(rw * kT + pj) * 4;
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(du_tile + off), "f"(o_du[0]), "f"(o_du[1]) : "memory");
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ddt_tile + off), "f"(o_dd[0]), "f"(o_dd[1]) : "memory");
-      }
-      named_bar_sync(1, kW * 32);   // X, DX, TDU, TDY complete for the CTA's 32 channels
-      // ---------------- contraction over the channels ----------------
-      {
-        u64 acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
-#pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
-          const float4 sc4 = lds_f4(c_scal + r4 * 16);
-          const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int r2 = c_half * 16 + r4 * 4 + e;
-            u64 v0, v1;
-            lds_2x64(c_src + (uint32_t)r2 * (kC * kStatePad * 4) + ((((uint32_t)(c_j * 4 + c_nq)) ^ (uint32_t)swz_row(r2)) << 4), v0, v1);
-            const u64 ss = pk2(sc[e], sc[e]);
-            acc0 = fma2(ss, v0, acc0);
-            acc1 = fma2(ss, v1, acc1);
-          }
-        }
-        float o[4];
-        upk2(acc0, o[0], o[1]);
-        upk2(acc1, o[2], o[3]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
-        if (c_half == 0 && c0 + c_j < L) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (c_nq * 4 + e < N) atomicAdd(dBC + (int64_t)e * L + c0, o[e]);
-        }
-      }
-      named_bar_sync(1, kW * 32);   // tiles free for the next chunk
     }
-    // ---------------- tile done: release the stage, ship du / ddelta ----------------
+    __syncwarp();
+    float dl[2][kC];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float4 t0 = lds_f4(sd_row + c * (kSP * 4)), t1 = lds_f4(sd_row + c * (kSP * 4) + 16);
+      dl[c][0] = t0.x; dl[c][1] = t0.y; dl[c][2] = t0.z; dl[c][3] = t0.w;
+      dl[c][4] = t1.x; dl[c][5] = t1.y; dl[c][6] = t1.z; dl[c][7] = t1.w;
+    }
+    // ---------------- forward recompute from the saved state ----------------
+    u64 x0[2][2], xs[2][kC][2];
+    lds_2x64(ck_row, x0[0][0], x0[0][1]);
+    lds_2x64(ck_row + kStatePad * 4, x0[1][0], x0[1][1]);
+    auto fwd_half = [&](auto HF) {
+      constexpr int hf = decltype(HF)::value;   // compile-time half: keeps xs[][][] in registers
+      float duh[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 v4 = lds_f4(sdu_row + c * (kSP * 4) + hf * 16);
+        duh[c][0] = v4.x; duh[c][1] = v4.y; duh[c][2] = v4.z; duh[c][3] = v4.w;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = hf * 4 + jj;
+        u64 Bp[2];
+        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const u64 dd = pk2(dl[c][j], dl[c][j]);
+          const u64 duu = pk2(duh[c][jj], duh[c][jj]);
+          float t0, t1, t2, t3;
+          upk2(mul2(dd, A2p[c][0]), t0, t1);
+          upk2(mul2(dd, A2p[c][1]), t2, t3);
+          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
+          xs[c][j][0] = fma2(e0, j == 0 ? x0[c][0] : xs[c][j - 1][0], mul2(duu, Bp[0]));
+          xs[c][j][1] = fma2(e1, j == 0 ? x0[c][1] : xs[c][j - 1][1], mul2(duu, Bp[1]));
+        }
+      }
+    };
+    fwd_half(std::integral_constant<int, 0>{});
+    fwd_half(std::integral_constant<int, 1>{});
+    // ---------------- reverse recurrence, one half chunk at a time ----------------
+    auto rev_half = [&](auto HF) {
+      constexpr int hf = decltype(HF)::value;
+      float duh[2][4], dyh[2][4], s1p[2][4], s2p[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 v4 = lds_f4(sdu_row + c * (kSP * 4) + hf * 16);
+        const float4 y4 = lds_f4(dy_row + c * (kC * 4) + hf * 16);
+        duh[c][0] = v4.x; duh[c][1] = v4.y; duh[c][2] = v4.z; duh[c][3] = v4.w;
+        dyh[c][0] = y4.x; dyh[c][1] = y4.y; dyh[c][2] = y4.z; dyh[c][3] = y4.w;
+      }
+#pragma unroll
+      for (int jj = 3; jj >= 0; --jj) {
+        const int j = hf * 4 + jj;
+        u64 Bp[2], Cp[2];
+        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bp[0], Bp[1]);
+        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4) + 64, Cp[0], Cp[1]);
+        u64 pB0 = 0, pB1 = 0, pC0 = 0, pC1 = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const u64 dyy = pk2(dyh[c][jj], dyh[c][jj]);
+          const u64 dd = pk2(dl[c][j], dl[c][j]);
+          const u64 duu = pk2(duh[c][jj], duh[c][jj]);
+          float t0, t1, t2, t3;                                          // decays again: MUFU has slack, registers do not
+          upk2(mul2(dd, A2p[c][0]), t0, t1);
+          upk2(mul2(dd, A2p[c][1]), t2, t3);
+          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
+          const u64 dx0 = fma2(Cp[0], dyy, w2[c][0]);                    // dx_{l,n}
+          const u64 dx1 = fma2(Cp[1], dyy, w2[c][1]);
+          s1p[c][jj] = hsum2(fma2(dx1, Bp[1], mul2(dx0, Bp[0])));        // sum_n dx * B          (bwd_kernel.cuh:280-281)
+          const u64 wg0 = mul2(dx0, mul2(e0, j == 0 ? x0[c][0] : xs[c][j - 1][0]));   // dx * a_l * x_{l-1}  (:283)
+          const u64 wg1 = mul2(dx1, mul2(e1, j == 0 ? x0[c][1] : xs[c][j - 1][1]));
+          s2p[c][jj] = hsum2(fma2(wg1, A2p[c][1], mul2(wg0, A2p[c][0])));  // in units of log2(e)
+          dA2[c][0] = fma2(wg0, dd, dA2[c][0]);                          // :286
+          dA2[c][1] = fma2(wg1, dd, dA2[c][1]);
+          w2[c][0] = mul2(e0, dx0);                                      // carried to position l-1
+          w2[c][1] = mul2(e1, dx1);
+          if (c == 0) {                                                  // channel-pair products for dB / dC
+            pB0 = mul2(duu, dx0); pB1 = mul2(duu, dx1);
+            pC0 = mul2(dyy, xs[c][j][0]); pC1 = mul2(dyy, xs[c][j][1]);
+          } else {
+            pB0 = fma2(duu, dx0, pB0); pB1 = fma2(duu, dx1, pB1);
+            pC0 = fma2(dyy, xs[c][j][0], pC0); pC1 = fma2(dyy, xs[c][j][1], pC1);
+          }
+        }
+        const uint32_t prow = p_row + (uint32_t)j * 128;
+        sts_2x64(prow + ((((uint32_t)sq) ^ psw) << 4), pB0, pB1);
+        sts_2x64(prow + ((((uint32_t)(4 + sq)) ^ psw) << 4), pC0, pC1);
+      }
+      // ---- reduce-scatter over the 4 lanes: lane sq finalises position hf*4 + sq of both channels ----
+      float f1[2], f2[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float a1 = hi1 ? s1p[c][0] : s1p[c][2], b1 = hi1 ? s1p[c][1] : s1p[c][3];
+        const float a2 = hi1 ? s2p[c][0] : s2p[c][2], b2 = hi1 ? s2p[c][1] : s2p[c][3];
+        const float k1a = (hi1 ? s1p[c][2] : s1p[c][0]) + __shfl_xor_sync(0xffffffffu, a1, 2);
+        const float k1b = (hi1 ? s1p[c][3] : s1p[c][1]) + __shfl_xor_sync(0xffffffffu, b1, 2);
+        const float k2a = (hi1 ? s2p[c][2] : s2p[c][0]) + __shfl_xor_sync(0xffffffffu, a2, 2);
+        const float k2b = (hi1 ? s2p[c][3] : s2p[c][1]) + __shfl_xor_sync(0xffffffffu, b2, 2);
+        f1[c] = (hi0 ? k1b : k1a) + __shfl_xor_sync(0xffffffffu, hi0 ? k1a : k1b, 1);
+        f2[c] = (hi0 ? k2b : k2a) + __shfl_xor_sync(0xffffffffu, hi0 ? k2a : k2b, 1);
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t eo = (uint32_t)(c * kC + hf * 4 + sq) * 4;
+        const float e_u = lds_f1(u_row + eo), e_dy = lds_f1(dy_row + eo);
+        const float e_dl = lds_f1(sd_row + (uint32_t)(c * kSP + hf * 4 + sq) * 4);
+        const float o_du = fmaf(e_dl, f1[c], Dv[c] * e_dy);                                 // :211, :280
+        const float o_dd = fmaf(e_u, f1[c], f2[c] * kLn2) * my_sg[c][hf];                   // :281-284, :446-450
+        dbias_acc[c] += ((c0 + hf * 4 + sq) < L) ? o_dd : 0.f;
+        dD_acc[c] = fmaf(e_dy, e_u, dD_acc[c]);                                             // :213
+        const uint32_t off = (uint32_t)((2 * pr + c) * kC + hf * 4 + sq) * 4;
+        sts_f1(du_tile + off, o_du);
+        sts_f1(ddt_tile + off, o_dd);
+      }
+    };
+    rev_half(std::integral_constant<int, 1>{});
+    rev_half(std::integral_constant<int, 0>{});
+    named_bar_sync(1, kW * 32);   // P complete for the CTA's 32 channel pairs
+    if (has_next) {               // the other stage's B/C tile: last read in chunk i-1, next read after the barrier below
+      bc_store(i + 1, threadIdx.x, nb0);
+      bc_store(i + 1, threadIdx.x + kThr, nb1);
+    }
+    // ---------------- contraction over the channel pairs ----------------
+    {
+      u64 acc0 = pk2(0.f, 0.f), acc1 = pk2(0.f, 0.f);
+      const uint32_t src = smem_u32(sm.P) + (uint32_t)c_j * 128;
+#pragma unroll
+      for (int e = 0; e < kNP / 2; ++e) {
+        const int p2 = c_h * (kNP / 2) + e;
+        u64 v0, v1;
+        lds_2x64(src + (uint32_t)p2 * (kC * 32 * 4) + ((((uint32_t)c_c) ^ swz8(p2 & 7)) << 4), v0, v1);
+        acc0 = add2(acc0, v0);
+        acc1 = add2(acc1, v1);
+      }
+      float o[4];
+      upk2(acc0, o[0], o[1]);
+      upk2(acc1, o[2], o[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+      if (c_h == 0 && c0 + c_j < L) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if ((c_c & 3) * 4 + e < N) atomicAdd(dBC + (int64_t)e * L + c0, o[e]);
+      }
+    }
+    named_bar_sync(1, kW * 32);   // P free for the next chunk
+    // ---------------- chunk done: ship du / ddelta ----------------
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(smem_u32(&sm.empty[s]));
-      tma_store_3d(&map_du, du_tile, l0, d0 + warp * 8, b);
-      tma_store_3d(&map_ddt, ddt_tile, l0, d0 + warp * 8, b);
+      tma_store_3d(&map_du, du_tile, c0, d0 + warp * 16, b);
+      tma_store_3d(&map_ddt, ddt_tile, c0, d0 + warp * 16, b);
       tma_store_commit();
       tma_store_wait_read<1>();
     }
@@ -368,22 +389,24 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   }
   if (lane == 0) tma_store_wait_all<0>();
 
-  // dA: sum over batch through atomics (one per (channel, state) per CTA)
-  {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int d = d0 + rA + c;
     float da[4];
-    upk2(dA2[0], da[0], da[1]);
-    upk2(dA2[1], da[2], da[3]);
+    upk2(dA2[c][0], da[0], da[1]);
+    upk2(dA2[c][1], da[2], da[3]);
 #pragma unroll
     for (int n = 0; n < kLS; ++n)
-      if (sq * kLS + n < N) atomicAdd(a.dA + (int64_t)d * N + sq * kLS + n, da[n]);
-  }
-  dD_acc += __shfl_xor_sync(0xffffffffu, dD_acc, 1);
-  dD_acc += __shfl_xor_sync(0xffffffffu, dD_acc, 2);
-  dbias_acc += __shfl_xor_sync(0xffffffffu, dbias_acc, 1);
-  dbias_acc += __shfl_xor_sync(0xffffffffu, dbias_acc, 2);
-  if (sq == 0) {
-    if (a.dD != nullptr) atomicAdd(a.dD + d, dD_acc);
-    if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbias_acc);
+      if (sq * kLS + n < N) atomicAdd(a.dA + (int64_t)d * N + sq * kLS + n, da[n]);   // sum over batch
+    float dDs = dD_acc[c], dbs = dbias_acc[c];
+    dDs += __shfl_xor_sync(0xffffffffu, dDs, 1);
+    dDs += __shfl_xor_sync(0xffffffffu, dDs, 2);
+    dbs += __shfl_xor_sync(0xffffffffu, dbs, 1);
+    dbs += __shfl_xor_sync(0xffffffffu, dbs, 2);
+    if (sq == 0) {
+      if (a.dD != nullptr) atomicAdd(a.dD + d, dDs);
+      if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbs);
+    }
   }
 }
 
@@ -418,11 +441,11 @@ bool bwd_tma_eligible(const BwdLaunch& p) {
 cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
   CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
-  if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kT, kR) ||
-      !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kT, kR) ||
-      !make_row_map(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kT, kR) ||
-      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kT, 8) ||
-      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kT, 8) ||
+  if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR) ||
+      !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kC, kR) ||
+      !make_row_map(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR) ||
+      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kC, 16) ||
+      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kC, 16) ||
       !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
     return cudaErrorInvalidValue;
   const int smem = (int)sizeof(BwdTmaSmem) + 1024;

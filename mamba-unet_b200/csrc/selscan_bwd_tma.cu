@@ -52,15 +52,15 @@ constexpr int kSP = 12;           // row pitch of the per-row scalar scratch (fl
 
 struct BwdTmaSmem {
   float CK[kStg][kR * kStatePad];   // 4 KB: [row][16 states]
-  float U[kStg][kR * kC];           // 2 KB: [row][8]
-  float DT[kStg][kR * kC];
+  float U[kStg][kR * kC];           // 2 KB: [half chunk][row][4 positions] (two 16-byte-wide TMA boxes): lane (pair, quad)
+  float DT[kStg][kR * kC];          //       reads bank 4*pair + quad -> no conflicts on the scalar accesses
   float DY[kStg][kR * kC];
   float BC[kStg][kC * kPitch];
   float P[kNP * kC * 32];           // 32 KB, swizzled [pair][pos][dB 0..15 | dC 0..15]
   float SD[kR * kSP];               // delta   per (row, position of the chunk)
   float SDU[kR * kSP];              // delta*u
-  float DU[kW][2][16 * kC];         // per-warp output tiles, double-buffered (512 B each)
-  float DDT[kW][2][16 * kC];
+  float DU[2][kR * kC];             // CTA-wide output tiles [half][row][4], double-buffered (2 KB each)
+  float DDT[2][kR * kC];
   u64 full[kStg];
 };
 
@@ -123,9 +123,12 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     const int t = n_tiles - 1 - i, s = i % kStg, l0 = t * kC;
     const uint32_t full = smem_u32(&sm.full[s]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(3 * kR * kC * 4 + kR * kStatePad * 4)) : "memory");
-    tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
-    tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
-    tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      tma_load_3d(smem_u32(sm.U[s]) + hf * (kR * 16), &map_u, l0 + 4 * hf, d0, b, full);
+      tma_load_3d(smem_u32(sm.DT[s]) + hf * (kR * 16), &map_dt, l0 + 4 * hf, d0, b, full);
+      tma_load_3d(smem_u32(sm.DY[s]) + hf * (kR * 16), &map_dy, l0 + 4 * hf, d0, b, full);
+    }
     // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
     tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, row0, full);
   };
@@ -154,13 +157,13 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   const int sq = lane & 3;                // which 4 states
   const int pr = lane >> 2;               // channel pair inside the warp
   const int pp = warp * 8 + pr;           // channel pair inside the CTA
-  const int rA = 2 * pp;                  // rows (channels inside the CTA) rA and rA + 1
+  const int rA = pp;                      // rows (channels inside the CTA) rA and rA + 32
   const bool hi1 = (sq & 2) != 0, hi0 = (sq & 1) != 0;
   u64 A2p[2][2], dA2[2][2], w2[2][2];
   float Dv[2], bias[2];
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const int d = d0 + rA + c;
+    const int d = d0 + rA + c * kNP;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int n0 = sq * kLS + 2 * q;
@@ -178,8 +181,11 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   // shared-space addresses of this thread's slots
   const uint32_t p_row = smem_u32(sm.P) + (uint32_t)pp * (kC * 32 * 4);
   const uint32_t psw = swz8(pr);
-  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)rA * (kSP * 4);
+  const uint32_t sd_row = smem_u32(sm.SD) + (uint32_t)rA * (kSP * 4);       // channel c: + c * kNP * kSP * 4
   const uint32_t sdu_row = smem_u32(sm.SDU) + (uint32_t)rA * (kSP * 4);
+  constexpr uint32_t kCS = kNP * kSP * 4;   // byte offset of the pair's second channel in SD / SDU
+  constexpr uint32_t kCT = kNP * 16;        // ... in a [half][row][4] tile
+  constexpr uint32_t kHT = kR * 16;         // byte offset of the second half chunk in a tile
   // contraction role: 16-byte chunk q of the [8 positions][32 values] output, half h of the channel pairs
   const int c_q = warp * 16 + (lane & 15);
   const int c_j = c_q >> 3, c_c = c_q & 7;
@@ -199,13 +205,13 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       nb1 = bc_load(i + 1, threadIdx.x + kThr);
     }
     mbar_wait(smem_u32(&sm.full[s]), k & 1);
-    const uint32_t u_row = smem_u32(sm.U[s]) + rA * (kC * 4);
-    const uint32_t dt_row = smem_u32(sm.DT[s]) + rA * (kC * 4);
-    const uint32_t dy_row = smem_u32(sm.DY[s]) + rA * (kC * 4);
+    const uint32_t u_row = smem_u32(sm.U[s]) + rA * 16;      // + hf * kHT + c * kCT + position-in-half * 4
+    const uint32_t dt_row = smem_u32(sm.DT[s]) + rA * 16;
+    const uint32_t dy_row = smem_u32(sm.DY[s]) + rA * 16;
     const uint32_t ck_row = smem_u32(sm.CK[s]) + rA * (kStatePad * 4) + sq * 16;
     const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLS * 4);
-    const uint32_t du_tile = smem_u32(sm.DU[warp][i & 1]);
-    const uint32_t ddt_tile = smem_u32(sm.DDT[warp][i & 1]);
+    const uint32_t du_tile = smem_u32(sm.DU[i & 1]);
+    const uint32_t ddt_tile = smem_u32(sm.DDT[i & 1]);
 
     // ---------------- prep: positions sq and 4+sq of both channels ----------------
     float my_sg[2][2];   // [channel][half]; u, dy and delta of my elements are re-read from shared memory when finalising
@@ -213,7 +219,7 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t off = (uint32_t)(c * kC + hf * 4 + sq) * 4;
+        const uint32_t off = (uint32_t)hf * kHT + (uint32_t)c * kCT + (uint32_t)sq * 4;
         const float my_u = lds_f1(u_row + off);
         const float xb = lds_f1(dt_row + off) + bias[c];
         float v = xb, sgm = 1.f;
@@ -224,7 +230,7 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         }
         v = ((c0 + hf * 4 + sq) < L) ? v : 0.f;   // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
         my_sg[c][hf] = sgm;
-        const uint32_t so = (uint32_t)(c * kSP + hf * 4 + sq) * 4;
+        const uint32_t so = (uint32_t)c * kCS + (uint32_t)(hf * 4 + sq) * 4;
         sts_f1(sd_row + so, v);
         sts_f1(sdu_row + so, v * my_u);
       }
@@ -233,20 +239,20 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     float dl[2][kC];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const float4 t0 = lds_f4(sd_row + c * (kSP * 4)), t1 = lds_f4(sd_row + c * (kSP * 4) + 16);
+      const float4 t0 = lds_f4(sd_row + c * kCS), t1 = lds_f4(sd_row + c * kCS + 16);
       dl[c][0] = t0.x; dl[c][1] = t0.y; dl[c][2] = t0.z; dl[c][3] = t0.w;
       dl[c][4] = t1.x; dl[c][5] = t1.y; dl[c][6] = t1.z; dl[c][7] = t1.w;
     }
     // ---------------- forward recompute from the saved state ----------------
     u64 x0[2][2], xs[2][kC][2];
     lds_2x64(ck_row, x0[0][0], x0[0][1]);
-    lds_2x64(ck_row + kStatePad * 4, x0[1][0], x0[1][1]);
+    lds_2x64(ck_row + kNP * kStatePad * 4, x0[1][0], x0[1][1]);
     auto fwd_half = [&](auto HF) {
       constexpr int hf = decltype(HF)::value;   // compile-time half: keeps xs[][][] in registers
       float duh[2][4];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const float4 v4 = lds_f4(sdu_row + c * (kSP * 4) + hf * 16);
+        const float4 v4 = lds_f4(sdu_row + c * kCS + hf * 16);
         duh[c][0] = v4.x; duh[c][1] = v4.y; duh[c][2] = v4.z; duh[c][3] = v4.w;
       }
 #pragma unroll
@@ -275,8 +281,8 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       float duh[2][4], dyh[2][4], s1p[2][4], s2p[2][4];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const float4 v4 = lds_f4(sdu_row + c * (kSP * 4) + hf * 16);
-        const float4 y4 = lds_f4(dy_row + c * (kC * 4) + hf * 16);
+        const float4 v4 = lds_f4(sdu_row + c * kCS + hf * 16);
+        const float4 y4 = lds_f4(dy_row + hf * kHT + c * kCT);
         duh[c][0] = v4.x; duh[c][1] = v4.y; duh[c][2] = v4.z; duh[c][3] = v4.w;
         dyh[c][0] = y4.x; dyh[c][1] = y4.y; dyh[c][2] = y4.z; dyh[c][3] = y4.w;
       }
@@ -333,21 +339,30 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const uint32_t eo = (uint32_t)(c * kC + hf * 4 + sq) * 4;
+        const uint32_t eo = (uint32_t)hf * kHT + (uint32_t)c * kCT + (uint32_t)sq * 4;
         const float e_u = lds_f1(u_row + eo), e_dy = lds_f1(dy_row + eo);
-        const float e_dl = lds_f1(sd_row + (uint32_t)(c * kSP + hf * 4 + sq) * 4);
+        const float e_dl = lds_f1(sd_row + (uint32_t)c * kCS + (uint32_t)(hf * 4 + sq) * 4);
         const float o_du = fmaf(e_dl, f1[c], Dv[c] * e_dy);                                 // :211, :280
         const float o_dd = fmaf(e_u, f1[c], f2[c] * kLn2) * my_sg[c][hf];                   // :281-284, :446-450
         dbias_acc[c] += ((c0 + hf * 4 + sq) < L) ? o_dd : 0.f;
         dD_acc[c] = fmaf(e_dy, e_u, dD_acc[c]);                                             // :213
-        const uint32_t off = (uint32_t)((2 * pr + c) * kC + hf * 4 + sq) * 4;
-        sts_f1(du_tile + off, o_du);
-        sts_f1(ddt_tile + off, o_dd);
+        sts_f1(du_tile + eo + rA * 16, o_du);     // same [half][row][4] layout as the input tiles
+        sts_f1(ddt_tile + eo + rA * 16, o_dd);
       }
     };
     rev_half(std::integral_constant<int, 1>{});
     rev_half(std::integral_constant<int, 0>{});
-    named_bar_sync(1, kW * 32);   // P complete for the CTA's 32 channel pairs
+    fence_proxy_async_smem();     // my du / ddelta writes -> visible to the TMA store
+    named_bar_sync(1, kW * 32);   // P and the output tiles complete for the CTA's 64 channels
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        tma_store_3d(&map_du, du_tile + hf * kHT, c0 + 4 * hf, d0, b);
+        tma_store_3d(&map_ddt, ddt_tile + hf * kHT, c0 + 4 * hf, d0, b);
+      }
+      tma_store_commit();
+      tma_store_wait_read<1>();   // the other output buffer (chunk i-1) has been read: free for chunk i+1
+    }
     if (has_next) {               // the other stage's B/C tile: last read in chunk i-1, next read after the barrier below
       bc_store(i + 1, threadIdx.x, nb0);
       bc_store(i + 1, threadIdx.x + kThr, nb1);
@@ -376,22 +391,12 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       }
     }
     named_bar_sync(1, kW * 32);   // P free for the next chunk
-    // ---------------- chunk done: ship du / ddelta ----------------
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_3d(&map_du, du_tile, c0, d0 + warp * 16, b);
-      tma_store_3d(&map_ddt, ddt_tile, c0, d0 + warp * 16, b);
-      tma_store_commit();
-      tma_store_wait_read<1>();
-    }
-    __syncwarp();
   }
-  if (lane == 0) tma_store_wait_all<0>();
+  if (threadIdx.x == 0) tma_store_wait_all<0>();
 
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const int d = d0 + rA + c;
+    const int d = d0 + rA + c * kNP;
     float da[4];
     upk2(dA2[c][0], da[0], da[1]);
     upk2(dA2[c][1], da[2], da[3]);
@@ -441,11 +446,11 @@ bool bwd_tma_eligible(const BwdLaunch& p) {
 cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
   CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
-  if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR) ||
-      !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kC, kR) ||
-      !make_row_map(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR) ||
-      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kC, 16) ||
-      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kC, 16) ||
+  if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, 4, kR) ||
+      !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, 4, kR) ||
+      !make_row_map(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, 4, kR) ||
+      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, 4, kR) ||
+      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, 4, kR) ||
       !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
     return cudaErrorInvalidValue;
   const int smem = (int)sizeof(BwdTmaSmem) + 1024;

@@ -112,6 +112,14 @@ int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int3
 int selscan_b200_fwd(const selscan_fwd_args* args, void* stream);
 int selscan_b200_bwd(const selscan_bwd_args* args, void* stream);
 
+/* The 4-direction CrossScan / CrossMerge of SS2D (code/networks/mamba_sys.py:403-404 and :429-432), one pass each.
+ *   cross_scan : x  (batch, dim, H, W) contiguous -> xs (batch, 4, dim, H*W) with row pitch `row_pitch` floats
+ *                k=0 row-major, k=1 column-major, k=2 / k=3 the same two reversed
+ *   cross_merge: ys (batch, 4, dim, H*W), pitch `row_pitch` -> y (batch, dim, H*W) contiguous, row-major
+ * Each is the other's backward.  row_pitch >= H*W; the (batch, 4, dim) dimensions are dense on top of it. */
+int selscan_b200_cross_scan(const float* x, float* xs, int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream);
+int selscan_b200_cross_merge(const float* ys, float* y, int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

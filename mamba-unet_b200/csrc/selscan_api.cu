@@ -113,4 +113,28 @@ __attribute__((visibility("default"))) int selscan_b200_bwd(const selscan_bwd_ar
   return 0;
 }
 
+static int cross_common(bool scatter, const float* in, float* out, int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t pitch, void* stream) {
+  const char* who = scatter ? "selscan_b200_cross_scan" : "selscan_b200_cross_merge";
+  if (!in || !out) return fail("%s: NULL pointer", who);
+  if (batch < 0 || dim <= 0 || H <= 0 || W <= 0) return fail("%s: bad sizes batch=%d dim=%d H=%d W=%d", who, batch, dim, H, W);
+  if (pitch < (int64_t)H * W) return fail("%s: row_pitch (%lld) must be >= H*W (%d)", who, (long long)pitch, H * W);
+  if ((int64_t)H * (W + 1) * 4 > 200 * 1024) return fail("%s: image plane of %dx%d does not fit in shared memory", who, H, W);
+  const cudaError_t e = selscan::launch_cross(scatter, in, out, batch, dim, H, W, pitch, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    fail("%s: launch failed: %s", who, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+__attribute__((visibility("default"))) int selscan_b200_cross_scan(const float* x, float* xs, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                                                                 int64_t row_pitch, void* stream) {
+  return cross_common(true, x, xs, batch, dim, H, W, row_pitch, stream);
+}
+
+__attribute__((visibility("default"))) int selscan_b200_cross_merge(const float* ys, float* y, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                                                                  int64_t row_pitch, void* stream) {
+  return cross_common(false, ys, y, batch, dim, H, W, row_pitch, stream);
+}
+
 }  // extern "C"

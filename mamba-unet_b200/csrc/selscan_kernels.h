@@ -33,4 +33,7 @@ cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);
 bool bwd_tma_eligible(const BwdLaunch& p);
 cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream);
 
+// CrossScan (scatter = true) / CrossMerge (scatter = false) plane kernels (selscan_cross.cu)
+cudaError_t launch_cross(bool scatter, const float* in, float* out, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream);
+
 }  // namespace selscan

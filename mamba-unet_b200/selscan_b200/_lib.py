@@ -76,6 +76,9 @@ def load():
         lib.selscan_b200_fwd.argtypes = [ctypes.POINTER(FwdArgs), _ptr]
         lib.selscan_b200_bwd.restype = ctypes.c_int
         lib.selscan_b200_bwd.argtypes = [ctypes.POINTER(BwdArgs), _ptr]
+        for fn in (lib.selscan_b200_cross_scan, lib.selscan_b200_cross_merge):
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
         if lib.selscan_b200_abi_version() != ABI_VERSION:
             raise RuntimeError("libselscan_b200.so ABI version mismatch: rebuild with mamba-unet_b200/build.py")
         _lib = lib

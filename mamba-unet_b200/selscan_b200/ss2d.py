@@ -15,6 +15,7 @@ What differs from the reference's ~20 ATen kernels:
 """
 import torch
 
+from . import _lib
 from .ops import selective_scan_fn
 
 
@@ -25,26 +26,46 @@ def _empty_dirs(ref, B, D, L):
     return buf if pitch == L else buf[..., :L]
 
 
+def _scatter(x):
+    """x (B, D, H, W) -> (B, 4, D, L): one pass of the plane kernel (selscan_b200_cross_scan)."""
+    B, D, H, W = x.shape
+    x = x.contiguous()
+    xs = _empty_dirs(x, B, D, H * W)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.selscan_b200_cross_scan(x.data_ptr(), xs.data_ptr(), B, D, H, W, xs.stride(2),
+                                               torch.cuda.current_stream(x.device).cuda_stream), "selscan_b200_cross_scan")
+    return xs
+
+
+def _gather(ys, H, W):
+    """ys (B, 4, D, L) -> (B, D, L) row-major: one pass of the plane kernel (selscan_b200_cross_merge)."""
+    B, _, D, L = ys.shape
+    if not (ys.stride(3) == 1 and ys.stride(1) == D * ys.stride(2) and ys.stride(0) == 4 * D * ys.stride(2)):
+        buf = _empty_dirs(ys, B, D, L)
+        buf.copy_(ys)
+        ys = buf
+    y = ys.new_empty((B, D, L))
+    lib = _lib.load()
+    with torch.cuda.device(ys.device):
+        _lib.check(lib.selscan_b200_cross_merge(ys.data_ptr(), y.data_ptr(), B, D, H, W, ys.stride(2),
+                                                torch.cuda.current_stream(ys.device).cuda_stream), "selscan_b200_cross_merge")
+    return y
+
+
 class CrossScan(torch.autograd.Function):
     """(B, D, H, W) -> (B, 4, D, L): row-major, column-major, and both reversed (mamba_sys.py:403-404)."""
 
     @staticmethod
     def forward(ctx, x):
-        B, D, H, W = x.shape
-        ctx.hw = (H, W)
-        xs = _empty_dirs(x, B, D, H * W)
-        xs[:, 0] = x.reshape(B, D, H * W)
-        xs[:, 1] = x.transpose(2, 3).reshape(B, D, H * W)
-        xs[:, 2:4] = xs[:, 0:2].flip(-1)
-        return xs
+        ctx.hw = x.shape[2:]
+        return _scatter(x)
 
     @staticmethod
     def backward(ctx, g):
         H, W = ctx.hw
         B, _, D, L = g.shape
-        row = g[:, 0] + g[:, 2].flip(-1)
-        col = g[:, 1] + g[:, 3].flip(-1)
-        return (row.view(B, D, H, W) + col.view(B, D, W, H).transpose(2, 3)).contiguous()
+        return _gather(g, H, W).view(B, D, H, W)
 
 
 class CrossMerge(torch.autograd.Function):
@@ -52,21 +73,28 @@ class CrossMerge(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ys, H, W):
-        B, _, D, L = ys.shape
         ctx.hw = (H, W)
-        row = ys[:, 0] + ys[:, 2].flip(-1)
-        col = ys[:, 1] + ys[:, 3].flip(-1)
-        return row + col.view(B, D, W, H).transpose(2, 3).reshape(B, D, L)
+        return _gather(ys, H, W)
 
     @staticmethod
     def backward(ctx, g):
         H, W = ctx.hw
         B, D, L = g.shape
-        gs = _empty_dirs(g, B, D, L)
-        gs[:, 0] = g
-        gs[:, 1] = g.view(B, D, H, W).transpose(2, 3).reshape(B, D, L)
-        gs[:, 2:4] = gs[:, 0:2].flip(-1)
-        return gs, None, None
+        return _scatter(g.reshape(B, D, H, W)), None, None
+
+
+def cross_scan_torch(x):
+    """Plain-torch statement of CrossScan (the reference's stack / transpose / flip / cat); used by the tests."""
+    B, D, H, W = x.shape
+    a = torch.stack([x.reshape(B, D, H * W), x.transpose(2, 3).reshape(B, D, H * W)], dim=1)
+    return torch.cat([a, a.flip(-1)], dim=1)
+
+
+def cross_merge_torch(ys, H, W):
+    B, _, D, L = ys.shape
+    row = ys[:, 0] + ys[:, 2].flip(-1)
+    col = ys[:, 1] + ys[:, 3].flip(-1)
+    return row + col.view(B, D, W, H).transpose(2, 3).reshape(B, D, L)
 
 
 def forward_core_b200(self, x: torch.Tensor):

@@ -63,9 +63,12 @@ def main():
             w = timeit(lambda: ref_cuda.ref_bwd(u, dt, A, Bm, Cm, D, None, bias, dout, x_r, None, True))
             row["reference"] = {"fwd_ms": f, "bwd_ms": w, "fwd_gbps": bf / f / 1e6, "bwd_gbps": bb / w / 1e6,
                                 "fwdbwd_gbps": (bf + bb) / (f + w) / 1e6, "frac": (bf + bb) / (f + w) / 1e6 / peak}
-        out = torch.empty_like(u)
+        # ours: rows with a 16-byte aligned pitch, as the public op / forward_core_b200 allocate them (L = 49 -> pitch 52)
+        pad = lambda t: ops.empty_rows(b, kd, L, dev).copy_(t)
+        u, dt, dout = pad(u), pad(dt), pad(dout)
+        out = ops.empty_rows(b, kd, L, dev)
         ck = torch.empty(max(ops.ckpt_elems(b, kd, L, N), 4), device=dev)
-        du, dd = torch.empty_like(u), torch.empty_like(u)
+        du, dd = ops.empty_rows(b, kd, L, dev), ops.empty_rows(b, kd, L, dev)
         dA, dB, dC = torch.zeros(kd, N, device=dev), torch.zeros_like(Bm), torch.zeros_like(Cm)
         dD, db = torch.zeros(kd, device=dev), torch.zeros(kd, device=dev)
         f = timeit(lambda: ops.launch_fwd(u, dt, A, Bm, Cm, D, None, bias, True, out, None, None, ck))

@@ -31,7 +31,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]; idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[idx['# Samples']].strip().isdigit()]   # all kernels of the report
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 tot = sum(int(r[idx['# Samples']] or 0) for r in data)
 print("total samples", tot, " instructions", len(data))

@@ -19,7 +19,8 @@
  *    > 0 the cudaError_t of a failed launch.
  *  - dtype: fp32 real (u, delta, A, B, C, D, z, delta_bias).  B and C are "variable" (input dependent):
  *    (batch, ngroups, dstate, seqlen), any element strides; channel d uses group d / (dim / ngroups)
- *    (selective_scan_fwd_kernel.cuh:99).  dstate <= 16 (Mamba-UNet uses 16).  fp16/bf16 I/O, complex A and
+ *    (selective_scan_fwd_kernel.cuh:99).  dstate <= 256 as in the reference; <= 16 (Mamba-UNet: 16) is one launch on the tiled kernels, larger
+ *    state counts run 16 states per launch on the generic kernels.  fp16/bf16 I/O, complex A and
  *    constant (dim, dstate) B/C -- which Mamba-UNet never passes -- are rejected with a message.
  *  - u, delta, z, out, dout, du, ddelta, dz have unit stride along seqlen (the reference requires the
  *    same, selective_scan.cpp:252-253); batch/channel strides are free.
@@ -106,7 +107,8 @@ typedef struct selscan_bwd_args {
 int selscan_b200_abi_version(void);
 const char* selscan_b200_last_error(void);
 
-/* number of floats the `ckpt` scratch of one (batch, dim, seqlen, dstate) problem needs (may be 0) */
+/* number of floats the `ckpt` scratch of one (batch, dim, seqlen, dstate) problem needs (may be 0):
+ * ceil(dstate / 16) * batch * dim * (ceil(seqlen / 8) - 1) * 16 */
 int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
 
 int selscan_b200_fwd(const selscan_fwd_args* args, void* stream);

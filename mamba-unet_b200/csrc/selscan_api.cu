@@ -28,9 +28,7 @@ template <typename Args>
 int check_common(const Args& a, const char* who) {
   if (a.batch < 0 || a.dim <= 0 || a.seqlen < 0) return fail("%s: bad sizes batch=%d dim=%d seqlen=%d", who, a.batch, a.dim, a.seqlen);
   if (a.dstate < 1) return fail("%s: dstate must be >= 1 (got %d)", who, a.dstate);
-  if (a.dstate > SELSCAN_B200_STATE_PAD)
-    return fail("%s: selective_scan only supports state dimension <= %d in this build (got %d); the reference allows 256",
-                who, SELSCAN_B200_STATE_PAD, a.dstate);
+  if (a.dstate > 256) return fail("%s: selective_scan only supports state dimension <= 256 (got %d)", who, a.dstate);
   if (a.ngroups < 1 || a.dim % a.ngroups != 0) return fail("%s: dim (%d) must be divisible by ngroups (%d)", who, a.dim, a.ngroups);
   if (!a.u || !a.delta || !a.A || !a.B || !a.C) return fail("%s: u, delta, A, B, C must not be NULL", who);
   return 0;
@@ -45,10 +43,10 @@ __attribute__((visibility("default"))) int selscan_b200_abi_version(void) { retu
 __attribute__((visibility("default"))) const char* selscan_b200_last_error(void) { return g_err; }
 
 __attribute__((visibility("default"))) int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
-  (void)dstate;
-  if (batch <= 0 || dim <= 0 || seqlen <= 0) return 0;
+  if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0) return 0;
   const int64_t n_ckpt = (seqlen + SELSCAN_B200_CKPT_INTERVAL - 1) / SELSCAN_B200_CKPT_INTERVAL - 1;
-  return (int64_t)batch * dim * n_ckpt * SELSCAN_B200_STATE_PAD;
+  const int64_t n_blocks = (dstate + SELSCAN_B200_STATE_PAD - 1) / SELSCAN_B200_STATE_PAD;   // states are processed 16 at a time
+  return n_blocks * batch * dim * n_ckpt * SELSCAN_B200_STATE_PAD;
 }
 
 __attribute__((visibility("default"))) int selscan_b200_fwd(const selscan_fwd_args* args, void* stream) {
@@ -70,10 +68,13 @@ __attribute__((visibility("default"))) int selscan_b200_fwd(const selscan_fwd_ar
   p.vec_bc = al16(a.B) && al16(a.C) && a.B_l_stride == 1 && a.C_l_stride == 1 && m4(a.B_batch_stride) &&
              m4(a.B_group_stride) && m4(a.B_n_stride) && m4(a.C_batch_stride) && m4(a.C_group_stride) &&
              m4(a.C_n_stride);
-  const cudaError_t e = selscan::launch_fwd(p, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) {
-    fail("selscan_b200_fwd: launch failed: %s", cudaGetErrorString(e));
-    return (int)e;
+  p.n_state_blocks = (a.dstate + selscan::kStatePad - 1) / selscan::kStatePad;
+  for (p.state_block = 0; p.state_block < p.n_state_blocks; ++p.state_block) {   // one launch for dstate <= 16 (Mamba-UNet)
+    const cudaError_t e = selscan::launch_fwd(p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+      fail("selscan_b200_fwd: launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
   }
   return 0;
 }
@@ -105,10 +106,13 @@ __attribute__((visibility("default"))) int selscan_b200_bwd(const selscan_bwd_ar
                m4(a.ddelta_batch_stride) && m4(a.ddelta_d_stride) &&
                (!a.z || (al16(a.z) && al16(a.out) && al16(a.dz) && m4(a.z_batch_stride) && m4(a.z_d_stride) &&
                          m4(a.out_batch_stride) && m4(a.out_d_stride) && m4(a.dz_batch_stride) && m4(a.dz_d_stride)));
-  const cudaError_t e = selscan::launch_bwd(p, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) {
-    fail("selscan_b200_bwd: launch failed: %s", cudaGetErrorString(e));
-    return (int)e;
+  p.n_state_blocks = (a.dstate + selscan::kStatePad - 1) / selscan::kStatePad;
+  for (p.state_block = 0; p.state_block < p.n_state_blocks; ++p.state_block) {
+    const cudaError_t e = selscan::launch_bwd(p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+      fail("selscan_b200_bwd: launch failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
   }
   return 0;
 }

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
   const selscan_bwd_args& a = p.a;
   const int L = a.seqlen, N = a.dstate;
+  const int n0 = p.state_block * kStatePad;   // first state of this launch's block
+  const bool first_blk = p.state_block == 0;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -60,8 +62,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
   const float* __restrict__ dout = a.dout + (int64_t)b * a.dout_batch_stride + (int64_t)d * a.dout_d_stride;
   const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
   const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
-  float* __restrict__ du = a.du + (int64_t)b * a.du_batch_stride + (int64_t)d * a.du_d_stride;
-  float* __restrict__ ddt = a.ddelta + (int64_t)b * a.ddelta_batch_stride + (int64_t)d * a.ddelta_d_stride;
+  float* du = a.du + (int64_t)b * a.du_batch_stride + (int64_t)d * a.du_d_stride;
+  float* ddt = a.ddelta + (int64_t)b * a.ddelta_batch_stride + (int64_t)d * a.ddelta_d_stride;
   const float* __restrict__ z = nullptr;
   const float* __restrict__ fout = nullptr;
   float* __restrict__ dz = nullptr;
@@ -70,17 +72,17 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
     fout = a.out + (int64_t)b * a.out_batch_stride + (int64_t)d * a.out_d_stride;
     dz = a.dz + (int64_t)b * a.dz_batch_stride + (int64_t)d * a.dz_d_stride;
   }
-  const float* __restrict__ ck = a.ckpt + row * p.n_ckpt * kStatePad + h * kHalf;
+  const float* __restrict__ ck = a.ckpt + ((int64_t)p.state_block * a.batch * a.dim + row) * p.n_ckpt * kStatePad + h * kHalf;
 
   float A2[kHalf], dA[kHalf], w[kHalf];
 #pragma unroll
   for (int n = 0; n < kHalf; ++n) {
-    const int ng = h * kHalf + n;
+    const int ng = n0 + h * kHalf + n;
     A2[n] = (active && ng < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)ng * a.A_n_stride) * kLog2e : 0.f;
     dA[n] = 0.f;
     w[n] = 0.f;  // a_{l+1} * dx_{l+1}, zero beyond the last position
   }
-  const float Dv = (active && a.D) ? __ldg(a.D + d) : 0.f;
+  const float Dv = (active && a.D && first_blk) ? __ldg(a.D + d) : 0.f;
   const float bias = (active && a.delta_bias) ? __ldg(a.delta_bias + d) : 0.f;
   const bool softplus = a.delta_softplus != 0;
   const bool vr = p.vec_rows != 0;
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
 #pragma unroll
     for (int i = tid; i < kCk * 2 * kStatePad; i += kBwdThreads) {
       const int j = i & (kCk - 1), col = i >> 3;  // consecutive threads -> consecutive positions
-      const int n = col & (kStatePad - 1);
+      const int n = n0 + (col & (kStatePad - 1));
       float v = 0.f;
       if (n < N && l0 + j < L) {
         v = (col < kStatePad) ? __ldg(Bg + (int64_t)n * a.B_n_stride + (int64_t)(l0 + j) * a.B_l_stride)
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
           dzv[j] = t2[j] * ov[j] * s * (1.f + zv[j] * (1.f - s));
           t2[j] = t2[j] * zv[j] * s;
         }
-        if (active && h == 0) store_row4(dz, l0 + 4 * q, L, vr, dzv);
+        if (active && h == 0 && first_blk) store_row4(dz, l0 + 4 * q, L, vr, dzv);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -207,13 +209,19 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
       const float dd = fmaf(uv[j], s1, s2 * kLn2) * sg[j]; // :281-284, :446-450
       ov[j] = (h == 0) ? duj : dd;
       dbias_acc += (l0 + j < L) ? dd : 0.f;
-      dD_acc = fmaf(dy[j], uv[j], dD_acc);                 // :213
+      dD_acc = first_blk ? fmaf(dy[j], uv[j], dD_acc) : 0.f;   // :213
     }
     if (active) {
 #pragma unroll
       for (int q = 0; q < kCk / 4; ++q) {
-        const float o[4] = {ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]};
-        store_row4(h == 0 ? du : ddt, l0 + 4 * q, L, vr, o);
+        float o[4] = {ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]};
+        float* dst = h == 0 ? du : ddt;
+        if (!first_blk) {   // accumulate over state blocks (du and ddelta are linear in the per-block sums)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (l0 + 4 * q + j < L) o[j] += dst[l0 + 4 * q + j];
+        }
+        store_row4(dst, l0 + 4 * q, L, vr, o);
       }
     }
     __syncthreads();  // X, DX, SDY, SDU complete
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
         const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (nq * 4 + i < N) atomicAdd(dst + (int64_t)(nq * 4 + i) * L, vals[i]);
+          if (n0 + nq * 4 + i < N) atomicAdd(dst + (int64_t)(n0 + nq * 4 + i) * L, vals[i]);
       }
     }
     __syncthreads();  // tiles free for the next chunk
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
   if (active) {
 #pragma unroll
     for (int n = 0; n < kHalf; ++n)
-      if (h * kHalf + n < N) atomicAdd(a.dA + (int64_t)d * N + h * kHalf + n, dA[n]);  // sum over batch
+      if (n0 + h * kHalf + n < N) atomicAdd(a.dA + (int64_t)d * N + n0 + h * kHalf + n, dA[n]);  // sum over batch
     if (h == 0 && a.dD != nullptr) atomicAdd(a.dD + d, dD_acc);
     if (h == 1 && a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbias_acc);
   }

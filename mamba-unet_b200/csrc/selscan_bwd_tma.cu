@@ -430,7 +430,7 @@ inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int
 
 bool bwd_tma_eligible(const BwdLaunch& p) {
   const selscan_bwd_args& a = p.a;
-  if (a.z != nullptr) return false;
+  if (a.z != nullptr || a.dstate > kStatePad) return false;
   if (p.dim_per_group % kR != 0) return false;
   if (p.n_ckpt < 1) return false;
   const int64_t zero = 0;

@@ -27,12 +27,14 @@ __global__ void __launch_bounds__(kFwdThreads) selscan_fwd_rowserial_kernel(cons
   const int g = d / p.dim_per_group;
   const int L = a.seqlen;
   const int N = a.dstate;
+  const int n0 = p.state_block * kStatePad;   // first state of this launch's block
+  const bool first_blk = p.state_block == 0, last_blk = p.state_block == p.n_state_blocks - 1;
 
   const float* __restrict__ u = a.u + (int64_t)b * a.u_batch_stride + (int64_t)d * a.u_d_stride;
   const float* __restrict__ dt = a.delta + (int64_t)b * a.delta_batch_stride + (int64_t)d * a.delta_d_stride;
   const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
   const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
-  float* __restrict__ out = a.out + (int64_t)b * a.out_batch_stride + (int64_t)d * a.out_d_stride;
+  float* out = a.out + (int64_t)b * a.out_batch_stride + (int64_t)d * a.out_d_stride;
   const float* __restrict__ z = nullptr;
   float* __restrict__ out_z = nullptr;
   if (kHasZ) {
@@ -43,19 +45,20 @@ __global__ void __launch_bounds__(kFwdThreads) selscan_fwd_rowserial_kernel(cons
   float A2[kStatePad], x[kStatePad];
 #pragma unroll
   for (int n = 0; n < kStatePad; ++n) {
-    A2[n] = (n < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n * a.A_n_stride) * kLog2e : 0.f;
+    A2[n] = (n0 + n < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + n) * a.A_n_stride) * kLog2e : 0.f;
     x[n] = 0.f;
   }
   const float Dv = a.D ? __ldg(a.D + d) : 0.f;
   const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
   const bool softplus = a.delta_softplus != 0;
   const bool vr = p.vec_rows != 0, vb = p.vec_bc != 0;
-  float* __restrict__ ck = a.ckpt ? a.ckpt + (int64_t)row * p.n_ckpt * kStatePad : nullptr;
+  float* __restrict__ ck = a.ckpt ? a.ckpt + ((int64_t)p.state_block * a.batch * a.dim + row) * p.n_ckpt * kStatePad : nullptr;
 
   for (int l0 = 0; l0 < L; l0 += 4) {
-    float uv[4], dl[4], du[4], y[4];
+    float uv[4], dl[4], du[4], y[4], acc[4];
     load_row4(u, l0, L, vr, uv);
     load_row4(dt, l0, L, vr, dl);
+    if (!first_blk) load_row4(out, l0, L, vr, acc);   // partial sum over the previous state blocks
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float v = dl[j] + bias;
@@ -63,14 +66,14 @@ __global__ void __launch_bounds__(kFwdThreads) selscan_fwd_rowserial_kernel(cons
       v = (l0 + j < L) ? v : 0.f;  // past the end: a = 1, b = 0, the state is carried unchanged
       dl[j] = v;
       du[j] = v * uv[j];
-      y[j] = Dv * uv[j];
+      y[j] = first_blk ? Dv * uv[j] : acc[j];
     }
 #pragma unroll
     for (int n = 0; n < kStatePad; ++n) {
       float Bv[4], Cv[4];
-      if (n < N) {
-        load_bc4(Bg + (int64_t)n * a.B_n_stride, a.B_l_stride, l0, L, vb, Bv);
-        load_bc4(Cg + (int64_t)n * a.C_n_stride, a.C_l_stride, l0, L, vb, Cv);
+      if (n0 + n < N) {
+        load_bc4(Bg + (int64_t)(n0 + n) * a.B_n_stride, a.B_l_stride, l0, L, vb, Bv);
+        load_bc4(Cg + (int64_t)(n0 + n) * a.C_n_stride, a.C_l_stride, l0, L, vb, Cv);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) Bv[j] = Cv[j] = 0.f;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kFwdThreads) selscan_fwd_rowserial_kernel(cons
       }
     }
     store_row4(out, l0, L, vr, y);
-    if (kHasZ) {
+    if (kHasZ && last_blk) {
       float zv[4];
       load_row4(z, l0, L, vr, zv);
 #pragma unroll
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kFwdThreads) selscan_fwd_rowserial_kernel(cons
   if (a.last_state != nullptr) {
 #pragma unroll
     for (int n = 0; n < kStatePad; ++n)
-      if (n < N) a.last_state[(int64_t)row * N + n] = x[n];
+      if (n0 + n < N) a.last_state[(int64_t)row * N + n0 + n] = x[n];
   }
 }
 

@@ -241,7 +241,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
 
 bool fwd_tma_eligible(const FwdLaunch& p) {
   const selscan_fwd_args& a = p.a;
-  if (a.z != nullptr) return false;                       // the gated variant stays on the generic kernel
+  if (a.z != nullptr || a.dstate > kStatePad) return false;                       // the gated variant stays on the generic kernel
   if (p.dim_per_group % kRows != 0) return false;
   if (a.seqlen < 1) return false;
   if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : 0)) return false;

@@ -12,6 +12,8 @@ struct FwdLaunch {
   int n_ckpt;         // saved states per row = ceil(seqlen / interval) - 1
   int vec_rows;       // u/delta/z/out rows are 16-byte aligned at every multiple-of-4 position
   int vec_bc;         // B and C rows likewise (and unit position stride)
+  int state_block;    // generic kernels only: states [16*state_block, 16*state_block + 16) of dstate (<= 256) per launch;
+  int n_state_blocks; // block 0 starts `out` (D*u), later blocks accumulate into it, the last one applies the z gate
 };
 
 struct BwdLaunch {
@@ -20,6 +22,8 @@ struct BwdLaunch {
   int n_ckpt;
   int tiles_per_group;  // ceil(dim_per_group / rows per CTA)
   int vec_rows;         // u/delta/dout/z/out/du/ddelta/dz rows 16-byte aligned at multiples of 4
+  int state_block;      // generic kernel only: see FwdLaunch; block 0 stores du / ddelta / dz / dD, later blocks accumulate
+  int n_state_blocks;
 };
 
 cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream);

@@ -77,6 +77,7 @@ def test_ckpt_elems(lib):
     assert L.selscan_b200_ckpt_elems(1, 4, 9, 16) == 4 * 16
     assert L.selscan_b200_ckpt_elems(24, 768, 3136, 16) == 24 * 768 * 391 * 16
     assert L.selscan_b200_ckpt_elems(0, 4, 100, 16) == 0
+    assert L.selscan_b200_ckpt_elems(2, 4, 17, 40) == 3 * 2 * 4 * 2 * 16   # 3 state blocks of 16
 
 
 def test_argument_validation_reports_errors(lib):
@@ -84,7 +85,7 @@ def test_argument_validation_reports_errors(lib):
     a = lib.FwdArgs(batch=1, dim=4, seqlen=8, dstate=16, ngroups=1)
     assert L.selscan_b200_fwd(a, None) == -1  # NULL pointers
     assert b"must not be NULL" in L.selscan_b200_last_error()
-    a = lib.FwdArgs(batch=1, dim=4, seqlen=8, dstate=32, ngroups=1)
+    a = lib.FwdArgs(batch=1, dim=4, seqlen=8, dstate=300, ngroups=1)
     assert L.selscan_b200_fwd(a, None) == -1
     assert b"state dimension" in L.selscan_b200_last_error()
     a = lib.FwdArgs(batch=1, dim=6, seqlen=8, dstate=16, ngroups=4)

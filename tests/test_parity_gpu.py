@@ -106,6 +106,12 @@ def test_optional_args_groups_states(oracle, has_z, has_D, has_bias, softplus, N
     _oracle_case(oracle, 2, G * dpg, 100, N, G, "T", 77, has_z, has_D, has_bias, softplus)
 
 
+# state dimensions beyond 16 (the reference allows up to 256): 16 states per launch on the generic kernels
+@pytest.mark.parametrize("N,has_z", [(17, False), (24, True), (40, False), (64, True), (256, False)])
+def test_large_state_dimension(oracle, N, has_z):
+    _oracle_case(oracle, 2, 8, 37, N, 2, "T", 99, has_z, True, True, True)
+
+
 # the four SS2D stages of MambaUnet, full channel counts, batch 2
 @pytest.mark.parametrize("D,L", [(192, 3136), (384, 784), (768, 196), (1536, 49)])
 @pytest.mark.parametrize("dist", ["T", "M"])
@@ -194,8 +200,8 @@ def test_no_grad_and_errors():
     with pytest.raises(RuntimeError):
         selective_scan_fn(u.cpu(), u.abs().cpu(), A.cpu(), B.cpu(), B.cpu())
     with pytest.raises(RuntimeError):
-        selective_scan_fn(u, u.abs(), torch.zeros(4, 32, device="cuda"), torch.zeros(1, 1, 32, 16, device="cuda"),
-                          torch.zeros(1, 1, 32, 16, device="cuda"))
+        selective_scan_fn(u, u.abs(), torch.zeros(4, 300, device="cuda"), torch.zeros(1, 1, 300, 16, device="cuda"),
+                          torch.zeros(1, 1, 300, 16, device="cuda"))
 
 
 def test_checkpoint_recompute_and_double_backward_call():

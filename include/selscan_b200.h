@@ -20,8 +20,8 @@
  *  - dtype: fp32 real (u, delta, A, B, C, D, z, delta_bias).  B and C are "variable" (input dependent):
  *    (batch, ngroups, dstate, seqlen), any element strides; channel d uses group d / (dim / ngroups)
  *    (selective_scan_fwd_kernel.cuh:99).  dstate <= 256 as in the reference; <= 16 (Mamba-UNet: 16) is one launch on the tiled kernels, larger
- *    state counts run 16 states per launch on the generic kernels.  fp16/bf16 I/O, complex A and
- *    constant (dim, dstate) B/C -- which Mamba-UNet never passes -- are rejected with a message.
+ *    state counts run 16 states per launch on the generic kernels.  fp16/bf16 I/O and constant (dim, dstate)
+ *    B/C are handled by the host shim (widening; zero-stride broadcast views); complex A is rejected with a message.
  *  - u, delta, z, out, dout, du, ddelta, dz have unit stride along seqlen (the reference requires the
  *    same, selective_scan.cpp:252-253); batch/channel strides are free.
  */

@@ -45,9 +45,13 @@ def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
     if dstate > 256:
         raise RuntimeError("selective_scan only supports state dimension <= 256")
     for name, t in (("B", B), ("C", C)):
-        if t.dim() < 3:
-            raise RuntimeError(f"selective_scan_fn: constant (dim, dstate) {name} is not supported by the B200 build; "
-                               f"pass the input-dependent (batch, [groups,] dstate, seqlen) form Mamba-UNet uses")
+        if t.dim() == 2:   # constant (dim, dstate) weights (selective_scan.cpp:238-246): fp32, one row per channel
+            if tuple(t.shape) != (dim, dstate) or t.dtype != torch.float32:
+                raise RuntimeError(f"selective_scan_fn: constant {name} must be float32 of shape ({dim}, {dstate}); got "
+                                   f"{t.dtype} {tuple(t.shape)}")
+            continue
+        if t.dim() not in (3, 4):
+            raise RuntimeError(f"selective_scan_fn: {name} must have 2, 3 or 4 dimensions")
         if t.dtype != u.dtype:
             raise RuntimeError(f"selective_scan_fn: {name} must have the same dtype as u")
         want = (batch, dstate, seqlen) if t.dim() == 3 else (batch, t.shape[1], dstate, seqlen)
@@ -165,6 +169,24 @@ class SelectiveScanFn(torch.autograd.Function):
             B = B.unsqueeze(1)  # selective_scan_interface.py:31-36
         if ctx.squeeze_C:
             C = C.unsqueeze(1)
+        # constant (dim, dstate) B / C (selective_scan.cpp:238-246): a zero-stride broadcast view with one group per channel --
+        # the kernels take any strides.  Mamba-UNet never passes them; this keeps the reference's API surface.
+        ctx.const_B = B.dim() == 2
+        ctx.const_C = C.dim() == 2
+        if ctx.const_B:
+            B = B.float().contiguous().view(1, dim, dstate, 1).expand(batch, dim, dstate, seqlen)
+        if ctx.const_C:
+            C = C.float().contiguous().view(1, dim, dstate, 1).expand(batch, dim, dstate, seqlen)
+        ctx.rep_B = ctx.rep_C = 1
+        if B.shape[1] != C.shape[1]:   # different groupings (e.g. constant B with variable C): use the finer one for both
+            g = max(B.shape[1], C.shape[1])
+            if g % B.shape[1] or g % C.shape[1]:
+                raise RuntimeError(f"selective_scan_fn: B has {B.shape[1]} groups and C has {C.shape[1]}: incompatible")
+            ctx.rep_B, ctx.rep_C = g // B.shape[1], g // C.shape[1]
+            if ctx.rep_B > 1:
+                B = B.repeat_interleave(ctx.rep_B, dim=1)
+            if ctx.rep_C > 1:
+                C = C.repeat_interleave(ctx.rep_C, dim=1)
         ngroups = B.shape[1]
         if C.shape[1] != ngroups or dim % ngroups != 0:
             raise RuntimeError(f"selective_scan_fn: B and C must share a group count dividing dim={dim}; "
@@ -220,8 +242,12 @@ class SelectiveScanFn(torch.autograd.Function):
             dbias = flat[2 * nbc + dim * dstate + dim:] if delta_bias is not None else None
             launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, ctx.delta_softplus,
                        du, ddelta, dA, dB, dC, dD, dz, dbias)
-        dB = dB.squeeze(1) if ctx.squeeze_B else dB  # selective_scan_interface.py:67-68
-        dC = dC.squeeze(1) if ctx.squeeze_C else dC
+        if ctx.rep_B > 1:   # gradients of a coarser grouping: sum over the channels that shared a group
+            dB = dB.view(batch, ngroups // ctx.rep_B, ctx.rep_B, dstate, seqlen).sum(2)
+        if ctx.rep_C > 1:
+            dC = dC.view(batch, ngroups // ctx.rep_C, ctx.rep_C, dstate, seqlen).sum(2)
+        dB = dB.sum(dim=(0, 3)) if ctx.const_B else (dB.squeeze(1) if ctx.squeeze_B else dB)  # selective_scan_interface.py:67-68
+        dC = dC.sum(dim=(0, 3)) if ctx.const_C else (dC.squeeze(1) if ctx.squeeze_C else dC)
         if ctx.in_dtype != torch.float32:
             du, ddelta = du.to(ctx.in_dtype), ddelta.to(ctx.in_dtype)
             dB, dC = dB.to(ctx.in_dtype), dC.to(ctx.in_dtype)
@@ -249,11 +275,15 @@ def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
         delta = delta + delta_bias[..., None].float()
     if delta_softplus:
         delta = F.softplus(delta)
-    if A.is_complex() or B.dim() < 3 or C.dim() < 3:
-        raise RuntimeError("selective_scan_ref (B200 build): only real A with input-dependent B and C is provided")
+    if A.is_complex():
+        raise RuntimeError("selective_scan_ref (B200 build): complex A is not provided")
     batch, dim, seqlen = u.shape
     dstate = A.shape[1]
     B, C = B.float(), C.float()
+    if B.dim() == 2:   # constant (dim, dstate)
+        B = B.view(1, dim, dstate, 1).expand(batch, dim, dstate, seqlen)
+    if C.dim() == 2:
+        C = C.view(1, dim, dstate, 1).expand(batch, dim, dstate, seqlen)
     if B.dim() == 3:
         B = B.unsqueeze(1)
     if C.dim() == 3:

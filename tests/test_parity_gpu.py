@@ -283,3 +283,29 @@ def test_full_batch_properties(oracle, D, L):
     close(grads[1][b0:b0 + 1, sl].cpu().numpy(), ref_g["ddelta"], BWD_RTOL, BWD_ATOL, "ddelta[subset]")
     close(grads[3][b0:b0 + 1, g0:g0 + 1].cpu().numpy(), ref_g["dB"], BWD_RTOL, BWD_ATOL, "dB[subset]")
     close(grads[4][b0:b0 + 1, g0:g0 + 1].cpu().numpy(), ref_g["dC"], BWD_RTOL, BWD_ATOL, "dC[subset]")
+
+
+@pytest.mark.parametrize("const_B,const_C", [(True, True), (True, False), (False, True)])
+def test_constant_B_C(const_B, const_C):
+    """Constant (dim, dstate) B / C (reference: selective_scan.cpp:238-246, selective_scan_interface.py:122-123,135-136),
+    checked against the shipped plain-torch statement of the op run on the GPU in fp64-free fp32 + autograd."""
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn, selective_scan_ref
+
+    torch.manual_seed(3)
+    batch, dim, L, N = 2, 6, 29, 16
+    mk = lambda *s: torch.randn(*s, device="cuda")
+    base = dict(u=mk(batch, dim, L), delta=0.5 * torch.rand(batch, dim, L, device="cuda"), A=-0.5 * torch.rand(dim, N, device="cuda"),
+                B=mk(dim, N) if const_B else mk(batch, 2, N, L), C=mk(dim, N) if const_C else mk(batch, N, L), D=mk(dim),
+                bias=0.5 * torch.rand(dim, device="cuda"))
+    dout = mk(batch, dim, L)
+    res = []
+    for fn in (selective_scan_fn, selective_scan_ref):
+        t = {k: v.clone().requires_grad_() for k, v in base.items()}
+        out = fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], None, t["bias"], True)
+        out.backward(dout)
+        res.append((out.detach(), {k: v.grad for k, v in t.items()}))
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-4, atol=1e-4)
+    for k in base:
+        assert res[0][1][k].shape == base[k].shape
+        scale = max(1.0, float(res[1][1][k].abs().max()))
+        torch.testing.assert_close(res[0][1][k], res[1][1][k], rtol=1e-3, atol=1e-4 * scale, msg=lambda m: f"{k}: {m}")

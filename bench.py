@@ -65,7 +65,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -75,7 +75,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -242,7 +242,7 @@ def model_leg(world, rank, dev, steps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE config: 24)")
@@ -328,9 +328,8 @@ def main():
                 if record is not None:
                     e2.record()
                     record.append((name, e0, e1, e2))
-                if world > 1:  # what DDP would reduce for this op's parameters
-                    for k in ("dA", "dD", "dbias"):
-                        dist.all_reduce(t[k])
+                if world > 1:  # what DDP would reduce for this op's parameters: dA | dD | dbias are contiguous -> one bucket
+                    dist.all_reduce(t["flat"][t["dB"].numel() + t["dC"].numel():])
 
     def barrier():
         if world > 1:

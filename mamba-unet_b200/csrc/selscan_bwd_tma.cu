@@ -305,13 +305,13 @@ selscan_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
           const u64 dx0 = fma2(Cp[0], dyy, w2[c][0]);                    // dx_{l,n}
           const u64 dx1 = fma2(Cp[1], dyy, w2[c][1]);
           s1p[c][jj] = hsum2(fma2(dx1, Bp[1], mul2(dx0, Bp[0])));        // sum_n dx * B          (bwd_kernel.cuh:280-281)
-          const u64 wg0 = mul2(dx0, mul2(e0, j == 0 ? x0[c][0] : xs[c][j - 1][0]));   // dx * a_l * x_{l-1}  (:283)
-          const u64 wg1 = mul2(dx1, mul2(e1, j == 0 ? x0[c][1] : xs[c][j - 1][1]));
+          w2[c][0] = mul2(e0, dx0);                                      // a_l * dx_l: carried to position l-1 ...
+          w2[c][1] = mul2(e1, dx1);
+          const u64 wg0 = mul2(w2[c][0], j == 0 ? x0[c][0] : xs[c][j - 1][0]);   // ... and dx * a_l * x_{l-1}  (:283)
+          const u64 wg1 = mul2(w2[c][1], j == 0 ? x0[c][1] : xs[c][j - 1][1]);
           s2p[c][jj] = hsum2(fma2(wg1, A2p[c][1], mul2(wg0, A2p[c][0])));  // in units of log2(e)
           dA2[c][0] = fma2(wg0, dd, dA2[c][0]);                          // :286
           dA2[c][1] = fma2(wg1, dd, dA2[c][1]);
-          w2[c][0] = mul2(e0, dx0);                                      // carried to position l-1
-          w2[c][1] = mul2(e1, dx1);
           if (c == 0) {                                                  // channel-pair products for dB / dC
             pB0 = mul2(duu, dx0); pB1 = mul2(duu, dx1);
             pC0 = mul2(dyy, xs[c][j][0]); pC1 = mul2(dyy, xs[c][j][1]);

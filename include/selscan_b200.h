@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SELSCAN_B200_ABI_VERSION 2
+#define SELSCAN_B200_ABI_VERSION 3
 /* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
 #define SELSCAN_B200_CKPT_INTERVAL 8
 /* states are padded to this count inside the kernels and in the checkpoint buffer */
@@ -65,6 +65,8 @@ typedef struct selscan_fwd_args {
   int64_t out_z_batch_stride, out_z_d_stride;
   float* last_state;                 /* (batch, dim, dstate) contiguous, or NULL */
   float* ckpt;                       /* selscan_b200_ckpt_elems() floats, or NULL (inference) */
+  float* workspace;                  /* selscan_b200_fwd_workspace_elems() floats or NULL: lets small-batch calls split the
+                                        sequence into segments that run concurrently (results identical to rounding) */
 } selscan_fwd_args;
 
 /* replaces selective_scan_cuda.bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_,
@@ -110,6 +112,9 @@ const char* selscan_b200_last_error(void);
 /* number of floats the `ckpt` scratch of one (batch, dim, seqlen, dstate) problem needs (may be 0):
  * ceil(dstate / 16) * batch * dim * (ceil(seqlen / 8) - 1) * 16 */
 int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+
+/* floats of forward `workspace` that make the segmented small-batch path available; 0 when the call fills the chip anyway */
+int64_t selscan_b200_fwd_workspace_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups);
 
 int selscan_b200_fwd(const selscan_fwd_args* args, void* stream);
 int selscan_b200_bwd(const selscan_bwd_args* args, void* stream);

@@ -49,6 +49,15 @@ __attribute__((visibility("default"))) int64_t selscan_b200_ckpt_elems(int32_t b
   return n_blocks * batch * dim * n_ckpt * SELSCAN_B200_STATE_PAD;
 }
 
+__attribute__((visibility("default"))) int64_t selscan_b200_fwd_workspace_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate,
+                                                                              int32_t ngroups) {
+  if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0 || dstate > SELSCAN_B200_STATE_PAD || ngroups <= 0) return 0;
+  int n_segs = 1, seg_tiles = 0;
+  selscan::fwd_plan_segments(batch, dim, seqlen, ngroups, &n_segs, &seg_tiles);
+  if (n_segs < 2) return 0;
+  return (int64_t)batch * dim * n_segs * (SELSCAN_B200_STATE_PAD + 1);   // segment states + sums of delta
+}
+
 __attribute__((visibility("default"))) int selscan_b200_fwd(const selscan_fwd_args* args, void* stream) {
   if (!args) return fail("selscan_b200_fwd: args is NULL");
   const selscan_fwd_args& a = *args;
@@ -68,6 +77,10 @@ __attribute__((visibility("default"))) int selscan_b200_fwd(const selscan_fwd_ar
   p.vec_bc = al16(a.B) && al16(a.C) && a.B_l_stride == 1 && a.C_l_stride == 1 && m4(a.B_batch_stride) &&
              m4(a.B_group_stride) && m4(a.B_n_stride) && m4(a.C_batch_stride) && m4(a.C_group_stride) &&
              m4(a.C_n_stride);
+  p.seg_ws = a.workspace;
+  p.n_segs = 1;
+  p.seg_tiles = 0;
+  if (a.workspace && (reinterpret_cast<uintptr_t>(a.workspace) & 15u)) return fail("selscan_b200_fwd: workspace must be 16-byte aligned");
   p.n_state_blocks = (a.dstate + selscan::kStatePad - 1) / selscan::kStatePad;
   for (p.state_block = 0; p.state_block < p.n_state_blocks; ++p.state_block) {   // one launch for dstate <= 16 (Mamba-UNet)
     const cudaError_t e = selscan::launch_fwd(p, static_cast<cudaStream_t>(stream));

@@ -17,6 +17,12 @@
 //       a per-warp TMA store, so HBM only ever sees full 128-byte rows.
 // Full/empty mbarriers per stage are the only synchronisation: warps drift freely, there is no __syncthreads in
 // the loop.  All waits are bounded (trap instead of hang).
+//
+// Low-parallelism shapes (small batch: the reference validates slice by slice, val_2D.py:35-47) split the SEQUENCE into
+// segments so that the whole chip works on a call: pass A (kMode 1) runs every segment from a zero state and keeps only
+// its end state and sum of delta; a tiny combine kernel turns those into the true state at every segment start
+// (h_s = exp2(A2 * sum_delta_{s-1}) * h_{s-1} + xend_{s-1}); pass C (kMode 2) re-runs the segments from those states and
+// produces the outputs.  1.7x the arithmetic for n_segs x the parallelism; results identical to rounding.
 #include "selscan_common.cuh"
 #include "selscan_kernels.h"
 #include "selscan_ptx.cuh"
@@ -44,6 +50,8 @@ struct FwdTmaSmem {
   u64 empty[kStages];
 };
 
+// kMode 0: whole sequence per CTA.  1: segment aggregates only (no outputs).  2: segment with an initial state.
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 2)
 selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                        const __grid_constant__ CUtensorMap map_out, const FwdLaunch p) {
@@ -54,11 +62,16 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_group = p.dim_per_group / kRows;
   int bid = blockIdx.x;
+  const int seg = (kMode == 0) ? 0 : bid % p.n_segs;
+  if (kMode != 0) bid /= p.n_segs;
   const int tile_g = bid % tiles_per_group; bid /= tiles_per_group;
   const int g = bid % a.ngroups;
   const int b = bid / a.ngroups;
   const int d0 = g * p.dim_per_group + tile_g * kRows;
-  const int n_tiles = (L + kTL - 1) / kTL;
+  const int n_tiles_all = (L + kTL - 1) / kTL;
+  const int t_begin = (kMode == 0) ? 0 : seg * p.seg_tiles;
+  const int t_end = (kMode == 0) ? n_tiles_all : min(n_tiles_all, t_begin + p.seg_tiles);
+  const int n_tiles = t_end - t_begin;   // tiles of this CTA; ring positions are counted from 0
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -80,7 +93,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kStages, k = t / kStages;
       if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
-      const int l0 = t * kTL;
+      const int l0 = (t_begin + t) * kTL;
       const uint32_t full = smem_u32(&sm.full[s]);
       if (lane == 0) {
         mbar_expect_tx(full, 2u * kRows * kTL * 4u);
@@ -128,6 +141,16 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     A2p[q] = pk2(a0, a1);
     x2[q] = pk2(0.f, 0.f);
   }
+  float* __restrict__ ws_state = nullptr;   // [row][segment][16]: end states (pass A) -> start states (after the combine)
+  if (kMode != 0) {
+    ws_state = p.seg_ws + (row * p.n_segs + seg) * kStatePad + sq * kLaneStates;
+    if (kMode == 2) {
+      const float4 h = *reinterpret_cast<const float4*>(ws_state);
+      x2[0] = pk2(h.x, h.y);
+      x2[1] = pk2(h.z, h.w);
+    }
+  }
+  float sum_delta = 0.f;
   const float Dv = a.D ? __ldg(a.D + d) : 0.f;
   const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
   const bool softplus = a.delta_softplus != 0;
@@ -138,7 +161,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
 
   for (int t = 0; t < n_tiles; ++t) {
     const int s = t % kStages, k = t / kStages;
-    const int l0 = t * kTL;
+    const int l0 = (t_begin + t) * kTL;
     mbar_wait(smem_u32(&sm.full[s]), k & 1);
     const uint32_t u_row = smem_u32(sm.U[s]) + rr * (kTL * 4);
     const uint32_t dt_row = smem_u32(sm.DT[s]) + rr * (kTL * 4);
@@ -188,7 +211,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         const uint32_t bc = bc_base + (uint32_t)(4 * q + j) * (kBCPitch * 4);
         u64 Bp[2], Cp[2];
         lds_2x64(bc, Bp[0], Bp[1]);
-        lds_2x64(bc + 64, Cp[0], Cp[1]);
+        if (kMode != 1) lds_2x64(bc + 64, Cp[0], Cp[1]);
         const u64 dd = pk2(dl[j], dl[j]);
         const float du = dl[j] * uv[j];
         const u64 duu = pk2(du, du);
@@ -199,13 +222,17 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         const u64 e1 = pk2(ex2(t2), ex2(t3));
         x2[0] = fma2(e0, x2[0], mul2(duu, Bp[0]));
         x2[1] = fma2(e1, x2[1], mul2(duu, Bp[1]));
-        y[j] = hsum2(fma2(Cp[1], x2[1], mul2(Cp[0], x2[0])));
+        if (kMode != 1) y[j] = hsum2(fma2(Cp[1], x2[1], mul2(Cp[0], x2[0])));
+      }
+      if (kMode == 1) {                      // aggregates only: the segment's sum of delta (identical in the 4 lanes)
+        sum_delta += (dl[0] + dl[1]) + (dl[2] + dl[3]);
+        continue;
       }
       if (q > 0) finish(q - 1, yp, up);
 #pragma unroll
       for (int j = 0; j < 4; ++j) yp[j] = y[j];
       up = hi1 ? (hi0 ? uv[3] : uv[2]) : (hi0 ? uv[1] : uv[0]);
-      if ((q & 1) && ck != nullptr) {   // position l0 + 4q + 3 closes an interval of 8
+      if ((q & 1) && ck != nullptr) {   // position l0 + 4q + 3 closes an interval of 8 (never reached in aggregate mode)
         const int done = l0 + 4 * q + 4;
         if (done < L) {
           float xs[4];
@@ -214,6 +241,11 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
           *reinterpret_cast<float4*>(ck + (int64_t)(done / kCkptInterval - 1) * kStatePad) = make_float4(xs[0], xs[1], xs[2], xs[3]);
         }
       }
+    }
+    if (kMode == 1) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
+      continue;
     }
     finish(kTL / 4 - 1, yp, up);
     fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
@@ -226,8 +258,16 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     }
     __syncwarp();
   }
+  if (kMode == 1) {   // end state of the segment (from a zero start) and its sum of delta
+    float xs[4];
+    upk2(x2[0], xs[0], xs[1]);
+    upk2(x2[1], xs[2], xs[3]);
+    *reinterpret_cast<float4*>(ws_state) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    if (sq == 0) p.seg_ws[(int64_t)a.batch * a.dim * p.n_segs * kStatePad + row * p.n_segs + seg] = sum_delta;
+    return;
+  }
   if (lane == 0) tma_store_wait_all<0>();
-  if (a.last_state != nullptr) {
+  if (a.last_state != nullptr && (kMode == 0 || seg == p.n_segs - 1)) {
     float xs[4];
     upk2(x2[0], xs[0], xs[1]);
     upk2(x2[1], xs[2], xs[3]);
@@ -237,7 +277,42 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   }
 }
 
+// Carry combine of the segmented forward: thread = (row, state); sequential over the (few) segments.
+__global__ void selscan_fwd_combine_kernel(const FwdLaunch p) {
+  const selscan_fwd_args& a = p.a;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t rows = (int64_t)a.batch * a.dim;
+  if (idx >= rows * kStatePad) return;
+  const int64_t row = idx / kStatePad;
+  const int n = (int)(idx % kStatePad);
+  const int d = (int)(row % a.dim);
+  const float A2 = (n < a.dstate) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n * a.A_n_stride) * kLog2e : 0.f;
+  float* st = p.seg_ws + row * p.n_segs * kStatePad + n;
+  const float* sd = p.seg_ws + rows * p.n_segs * kStatePad + row * p.n_segs;
+  float h = 0.f;
+  for (int s = 0; s < p.n_segs; ++s) {
+    const float xe = st[(int64_t)s * kStatePad];
+    st[(int64_t)s * kStatePad] = h;                 // state at the start of segment s
+    h = fmaf(ex2(A2 * sd[s]), h, xe);
+  }
+}
+
 }  // namespace
+
+// Segment plan shared by the workspace query and the launcher: split only when the call cannot fill the chip.
+void fwd_plan_segments(int batch, int dim, int seqlen, int ngroups, int* n_segs, int* seg_tiles) {
+  *n_segs = 1;
+  *seg_tiles = (seqlen + kTL - 1) / kTL;
+  if (batch <= 0 || dim <= 0 || ngroups <= 0 || dim % ngroups || (dim / ngroups) % kRows) return;
+  const int64_t n_ctas = (int64_t)batch * (dim / kRows);
+  const int n_tiles = (seqlen + kTL - 1) / kTL;
+  if (n_ctas * 3 > 296 || n_tiles < 4) return;      // at least a third of the 2 x 148 CTA slots is busy anyway
+  int want = (int)(296 / n_ctas);
+  if (want > n_tiles / 2) want = n_tiles / 2;
+  if (want < 2) return;
+  *seg_tiles = (n_tiles + want - 1) / want;
+  *n_segs = (n_tiles + *seg_tiles - 1) / *seg_tiles;
+}
 
 bool fwd_tma_eligible(const FwdLaunch& p) {
   const selscan_fwd_args& a = p.a;
@@ -258,10 +333,24 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
       !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, kWarpRows))
     return cudaErrorInvalidValue;
   const int smem = (int)sizeof(FwdTmaSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(selscan_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kRows));
-  selscan_fwd_tma_kernel<<<grid, kThreads, smem, stream>>>(mu, mdt, mout, p);
+  cudaError_t e;
+  FwdLaunch q = p;
+  fwd_plan_segments(a.batch, a.dim, a.seqlen, a.ngroups, &q.n_segs, &q.seg_tiles);
+  if (p.seg_ws == nullptr || q.n_segs < 2) {
+    e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    selscan_fwd_tma_kernel<0><<<grid, kThreads, smem, stream>>>(mu, mdt, mout, p);
+    return cudaGetLastError();
+  }
+  e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  selscan_fwd_tma_kernel<1><<<grid * q.n_segs, kThreads, smem, stream>>>(mu, mdt, mout, q);
+  const int64_t n_comb = (int64_t)a.batch * a.dim * kStatePad;
+  selscan_fwd_combine_kernel<<<(unsigned)((n_comb + 255) / 256), 256, 0, stream>>>(q);
+  selscan_fwd_tma_kernel<2><<<grid * q.n_segs, kThreads, smem, stream>>>(mu, mdt, mout, q);
   return cudaGetLastError();
 }
 

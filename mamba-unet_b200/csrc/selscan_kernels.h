@@ -14,6 +14,9 @@ struct FwdLaunch {
   int vec_bc;         // B and C rows likewise (and unit position stride)
   int state_block;    // generic kernels only: states [16*state_block, 16*state_block + 16) of dstate (<= 256) per launch;
   int n_state_blocks; // block 0 starts `out` (D*u), later blocks accumulate into it, the last one applies the z gate
+  float* seg_ws;      // tiled forward only: workspace of the segmented (small-batch) path or nullptr
+  int n_segs;         //   number of sequence segments and tiles of 32 positions per segment (fwd_plan_segments)
+  int seg_tiles;
 };
 
 struct BwdLaunch {
@@ -29,6 +32,7 @@ struct BwdLaunch {
 cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream);
 // tiled TMA path (selscan_fwd_tma.cu): aligned shapes with channels-per-group % 64 == 0 and no z
 bool fwd_tma_eligible(const FwdLaunch& p);
+void fwd_plan_segments(int batch, int dim, int seqlen, int ngroups, int* n_segs, int* seg_tiles);
 cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream);
 // SELSCAN_B200_GENERIC=1 in the environment forces the generic kernels (debugging / A-B timing only)
 bool force_generic();

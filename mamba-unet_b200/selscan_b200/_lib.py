@@ -9,7 +9,7 @@ import threading
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "lib", "libselscan_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 CKPT_INTERVAL = 8
 STATE_PAD = 16
 
@@ -28,7 +28,7 @@ class FwdArgs(ctypes.Structure):
             "z_batch_stride", "z_d_stride")]
         + [("out", _ptr), ("out_batch_stride", _i64), ("out_d_stride", _i64),
            ("out_z", _ptr), ("out_z_batch_stride", _i64), ("out_z_d_stride", _i64),
-           ("last_state", _ptr), ("ckpt", _ptr)]
+           ("last_state", _ptr), ("ckpt", _ptr), ("workspace", _ptr)]
     )
 
 
@@ -72,6 +72,8 @@ def load():
         lib.selscan_b200_last_error.restype = ctypes.c_char_p
         lib.selscan_b200_ckpt_elems.restype = ctypes.c_int64
         lib.selscan_b200_ckpt_elems.argtypes = [_i32] * 4
+        lib.selscan_b200_fwd_workspace_elems.restype = ctypes.c_int64
+        lib.selscan_b200_fwd_workspace_elems.argtypes = [_i32] * 5
         lib.selscan_b200_fwd.restype = ctypes.c_int
         lib.selscan_b200_fwd.argtypes = [ctypes.POINTER(FwdArgs), _ptr]
         lib.selscan_b200_bwd.restype = ctypes.c_int

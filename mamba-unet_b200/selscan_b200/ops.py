@@ -90,7 +90,8 @@ def _strides2(t):
     return (0, 0) if t is None else (t.stride(0), t.stride(1))
 
 
-def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=None, last_state=None, ckpt=None):
+def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=None, last_state=None, ckpt=None,
+               workspace=None):
     """One selscan_b200_fwd call on the current stream.  All tensors fp32 CUDA; B, C 4-D (batch, G, N, L);
     u/delta/z/out unit-stride along seqlen; outputs preallocated by the caller (the library never allocates)."""
     lib = _lib.load()
@@ -107,7 +108,7 @@ def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=N
         z_batch_stride=_strides2(z)[0], z_d_stride=_strides2(z)[1],
         out=_p(out), out_batch_stride=out.stride(0), out_d_stride=out.stride(1),
         out_z=_p(out_z), out_z_batch_stride=_strides2(out_z)[0], out_z_d_stride=_strides2(out_z)[1],
-        last_state=_p(last_state), ckpt=_p(ckpt))
+        last_state=_p(last_state), ckpt=_p(ckpt), workspace=_p(workspace))
     with torch.cuda.device(u.device):
         _lib.check(lib.selscan_b200_fwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_fwd")
 
@@ -141,6 +142,11 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
 
 def ckpt_elems(batch, dim, seqlen, dstate):
     return int(_lib.load().selscan_b200_ckpt_elems(batch, dim, seqlen, dstate))
+
+
+def fwd_workspace_elems(batch, dim, seqlen, dstate, ngroups):
+    """Floats of scratch that let a small-batch forward split the sequence into concurrent segments (0: not useful)."""
+    return int(_lib.load().selscan_b200_fwd_workspace_elems(batch, dim, seqlen, dstate, ngroups))
 
 
 class SelectiveScanFn(torch.autograd.Function):
@@ -201,7 +207,9 @@ class SelectiveScanFn(torch.autograd.Function):
             if needs_grad:  # saved scan states, the role of the reference's `x` (selective_scan.cpp:313)
                 ckpt = torch.empty((max(ckpt_elems(batch, dim, seqlen, dstate), 4),), device=u.device,
                                    dtype=torch.float32)
-            launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z, last_state, ckpt)
+            n_ws = fwd_workspace_elems(batch, dim, seqlen, dstate, ngroups) if z is None else 0
+            ws = torch.empty((n_ws,), device=u.device, dtype=torch.float32) if n_ws > 0 else None
+            launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z, last_state, ckpt, ws)
         ctx.delta_softplus = bool(delta_softplus)
         ctx.has_z = z is not None
         ctx.in_dtype = in_dtype

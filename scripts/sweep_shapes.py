@@ -31,10 +31,12 @@ for name, d_inner, L, _ in STAGES:
             t["dB"], t["dC"] = t["flat"][:nbc].view(b, K, N, L), t["flat"][nbc:2 * nbc].view(b, K, N, L)
             t["dA"] = t["flat"][2 * nbc:2 * nbc + kd * N].view(kd, N)
             t["dD"], t["db"] = t["flat"][2 * nbc + kd * N:2 * nbc + kd * N + kd], t["flat"][2 * nbc + kd * N + kd:]
+            n_ws = ops.fwd_workspace_elems(b, kd, L, N, K)
+            t["ws"] = torch.empty(n_ws, device=dev) if n_ws > 0 else None   # small batches: segmented forward
             sets.append(t)
 
         def fwd(t):
-            ops.launch_fwd(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], None, t["bias"], True, t["out"], None, None, t["ck"])
+            ops.launch_fwd(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], None, t["bias"], True, t["out"], None, None, t["ck"], t["ws"])
 
         def bwd(t):
             t["flat"].zero_()
@@ -57,7 +59,7 @@ for name, d_inner, L, _ in STAGES:
         rows.append({"stage": name, "batch": b, "KD": kd, "L": L, "fwd_ms": round(f, 4), "bwd_ms": round(w, 4),
                      "fwd_gbps": round(bf / f / 1e6, 1), "bwd_gbps": round(bb / w / 1e6, 1),
                      "fwdbwd_gbps": round((bf + bb) / (f + w) / 1e6, 1), "frac_of_peak": round((bf + bb) / (f + w) / 1e6 / peak, 4),
-                     "rotating_sets": nsets})
+                     "rotating_sets": nsets, "fwd_segmented": sets[0]["ws"] is not None})
         print(rows[-1], flush=True)
         del sets
         torch.cuda.empty_cache()

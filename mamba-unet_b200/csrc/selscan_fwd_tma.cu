@@ -310,8 +310,12 @@ void fwd_plan_segments(int batch, int dim, int seqlen, int ngroups, int* n_segs,
   int want = (int)(296 / n_ctas);
   if (want > n_tiles / 2) want = n_tiles / 2;
   if (want < 2) return;
-  *seg_tiles = (n_tiles + want - 1) / want;
-  *n_segs = (n_tiles + *seg_tiles - 1) / *seg_tiles;
+  const int st = (n_tiles + want - 1) / want;
+  // Two passes over st tiles + two extra launches (~10 tiles' worth of time) must beat one pass over n_tiles (measured on
+  // B200: profiles/r01_roofline_sweep.json; stage 3/4 lengths never qualify).
+  if (n_tiles - 2 * st < 12) return;
+  *seg_tiles = st;
+  *n_segs = (n_tiles + st - 1) / st;
 }
 
 bool fwd_tma_eligible(const FwdLaunch& p) {

@@ -312,7 +312,7 @@ def test_constant_B_C(const_B, const_C):
         torch.testing.assert_close(res[0][1][k], res[1][1][k], rtol=1e-3, atol=1e-4 * scale, msg=lambda m: f"{k}: {m}")
 
 
-@pytest.mark.parametrize("batch,D,L", [(1, 192, 3136), (2, 64, 1000), (1, 384, 784), (4, 64, 132)])
+@pytest.mark.parametrize("batch,D,L", [(1, 192, 3136), (2, 64, 1000), (1, 384, 784), (3, 64, 777)])
 def test_segmented_small_batch_forward(oracle, batch, D, L):
     """Small batches split the sequence into concurrent segments (selscan_b200_fwd_workspace_elems > 0): outputs, last
     state and -- through the saved states the backward restarts from -- all gradients must still match the oracle."""

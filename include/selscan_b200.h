@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SELSCAN_B200_ABI_VERSION 3
+#define SELSCAN_B200_ABI_VERSION 4
 /* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
 #define SELSCAN_B200_CKPT_INTERVAL 8
 /* states are padded to this count inside the kernels and in the checkpoint buffer */
@@ -126,6 +126,33 @@ int selscan_b200_bwd(const selscan_bwd_args* args, void* stream);
  * Each is the other's backward.  row_pitch >= H*W; the (batch, 4, dim) dimensions are dense on top of it. */
 int selscan_b200_cross_scan(const float* x, float* xs, int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream);
 int selscan_b200_cross_merge(const float* ys, float* y, int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream);
+
+/* The two edges of SS2D.forward around the scan (code/networks/mamba_sys.py:527-540), one kernel per direction of autograd.
+ * "channels-last" tensors are (batch, H, W, channels) with a free POSITION stride (floats between two pixels), so the x and z
+ * halves of in_proj's output (mamba_sys.py:530-531, `xz.chunk(2, dim=-1)`) are read, and their gradients written, in place.
+ *
+ * ss2d_in_fwd : x (batch,H,W,dim) channels-last -> permute (:533) -> depthwise 3x3 conv, padding 1, + bias (:534; conv_w is
+ *               (dim,1,3,3) contiguous, conv_b (dim) or NULL) -> SiLU (:534) -> CrossScan (:403-404) -> xs (batch,4,dim,H*W), row
+ *               pitch `row_pitch` floats (k=0 row-major, 1 column-major, 2/3 reversed)
+ * ss2d_in_bwd : dxs (layout of xs) -> dx (channels-last, stride dx_pos_stride); dconv_part (batch, dim, 10): per-image sums for
+ *               d conv_w (9 taps) and d conv_b, summed over batch by the caller
+ * ss2d_out_fwd: ys (batch,4,dim,H*W) scan outputs -> CrossMerge (:429-432) -> transpose (:433) -> LayerNorm over dim (:434,
+ *               ln_weight, ln_bias, eps) -> * silu(z) (:536; z channels-last or NULL = no gate) -> out (batch,H,W,dim) contiguous.
+ *               xhat (batch*H*W, dim) and rstd (batch*H*W) are saved for the backward when both are non-NULL.
+ * ss2d_out_bwd: dout (batch,H,W,dim) contiguous -> dz (channels-last, stride dz_pos_stride; iff z), dys (layout of ys), and
+ *               dln_part: selscan_b200_ss2d_out_partial_elems() floats = (n_tiles, 2, dim) per-tile sums for d ln_weight, d ln_bias */
+int selscan_b200_ss2d_in_fwd(const float* x, int64_t x_pos_stride, const float* conv_w, const float* conv_b, float* xs,
+                             int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream);
+int selscan_b200_ss2d_in_bwd(const float* dxs, const float* x, int64_t x_pos_stride, const float* conv_w, const float* conv_b,
+                             float* dx, int64_t dx_pos_stride, float* dconv_part, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                             int64_t row_pitch, void* stream);
+int64_t selscan_b200_ss2d_out_partial_elems(int32_t batch, int32_t dim, int32_t H, int32_t W);
+int selscan_b200_ss2d_out_fwd(const float* ys, int64_t row_pitch, const float* z, int64_t z_pos_stride, const float* ln_weight,
+                              const float* ln_bias, float eps, float* out, float* xhat, float* rstd, int32_t batch, int32_t dim,
+                              int32_t H, int32_t W, void* stream);
+int selscan_b200_ss2d_out_bwd(const float* dout, const float* z, int64_t z_pos_stride, const float* xhat, const float* rstd,
+                              const float* ln_weight, const float* ln_bias, float* dz, int64_t dz_pos_stride, float* dys,
+                              int64_t row_pitch, float* dln_part, int32_t batch, int32_t dim, int32_t H, int32_t W, void* stream);
 
 #ifdef __cplusplus
 }

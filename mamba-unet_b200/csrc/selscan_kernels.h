@@ -44,4 +44,19 @@ cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream);
 // CrossScan (scatter = true) / CrossMerge (scatter = false) plane kernels (selscan_cross.cu)
 cudaError_t launch_cross(bool scatter, const float* in, float* out, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream);
 
+// SS2D edge kernels (selscan_ss2d.cu): prologue = permute + depthwise 3x3 conv + SiLU + CrossScan, epilogue = CrossMerge +
+// transpose + LayerNorm + silu(z) gate, and their backwards
+bool ss2d_in_supported(int H, int W);
+bool ss2d_out_supported(int D);
+int64_t ss2d_out_ctas(int B, int D, int H, int W);
+cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, const float* cb, float* xs, int B, int D, int H, int W,
+                               int64_t pitch, cudaStream_t stream);
+cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, const float* cw, const float* cb, float* dx, int64_t dld,
+                               float* wpart, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream);
+cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, int64_t zld, const float* gamma, const float* beta,
+                                float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, cudaStream_t stream);
+cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, const float* xhat, const float* rstd,
+                                const float* gamma, const float* beta, float* dz, int64_t dzld, float* dys, int64_t pitch,
+                                float* part, int B, int D, int H, int W, cudaStream_t stream);
+
 }  // namespace selscan

@@ -9,7 +9,7 @@ import threading
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "lib", "libselscan_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 CKPT_INTERVAL = 8
 STATE_PAD = 16
 
@@ -81,6 +81,19 @@ def load():
         for fn in (lib.selscan_b200_cross_scan, lib.selscan_b200_cross_merge):
             fn.restype = ctypes.c_int
             fn.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
+        _f32 = ctypes.c_float
+        lib.selscan_b200_ss2d_in_fwd.restype = ctypes.c_int
+        lib.selscan_b200_ss2d_in_fwd.argtypes = [_ptr, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
+        lib.selscan_b200_ss2d_in_bwd.restype = ctypes.c_int
+        lib.selscan_b200_ss2d_in_bwd.argtypes = [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
+        lib.selscan_b200_ss2d_out_partial_elems.restype = ctypes.c_int64
+        lib.selscan_b200_ss2d_out_partial_elems.argtypes = [_i32] * 4
+        lib.selscan_b200_ss2d_out_fwd.restype = ctypes.c_int
+        lib.selscan_b200_ss2d_out_fwd.argtypes = [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32,
+                                                  _ptr]
+        lib.selscan_b200_ss2d_out_bwd.restype = ctypes.c_int
+        lib.selscan_b200_ss2d_out_bwd.argtypes = [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i32,
+                                                  _i32, _i32, _ptr]
         if lib.selscan_b200_abi_version() != ABI_VERSION:
             raise RuntimeError("libselscan_b200.so ABI version mismatch: rebuild with mamba-unet_b200/build.py")
         _lib = lib

@@ -16,6 +16,7 @@ What differs from the reference's ~20 ATen kernels:
 import torch
 
 from . import _lib
+from . import ops
 from .ops import selective_scan_fn
 
 
@@ -117,8 +118,174 @@ def forward_core_b200(self, x: torch.Tensor):
     return self.out_norm(y).to(x.dtype)                                                   # :434
 
 
-def patch_ss2d(ss2d_cls):
+# ----------------------------------------------------------------------------------------------------------------------
+# SS2D.forward with fused edges: everything between in_proj and out_proj
+# ----------------------------------------------------------------------------------------------------------------------
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def edge_in_fwd(xz, D, conv_w, conv_b):
+    """x half of xz (B, H, W, >= D) channels-last -> conv3x3 + bias + SiLU -> the four scan orders (B, 4, D, L)."""
+    B, H, W, ld = xz.shape
+    xs = _empty_dirs(xz, B, D, H * W)
+    lib = _lib.load()
+    with torch.cuda.device(xz.device):
+        _lib.check(lib.selscan_b200_ss2d_in_fwd(xz.data_ptr(), ld, conv_w.data_ptr(), ops._p(conv_b), xs.data_ptr(), B, D, H, W,
+                                                xs.stride(2), _stream(xz)), "selscan_b200_ss2d_in_fwd")
+    return xs
+
+
+def edge_in_bwd(d_xs, xz, D, conv_w, conv_b, d_xz):
+    """Backward of edge_in_fwd: writes d x into d_xz[..., :D]; returns (d conv_w (D,1,3,3), d conv_b (D))."""
+    B, H, W, ld = xz.shape
+    part = xz.new_empty((B, D, 10))
+    lib = _lib.load()
+    with torch.cuda.device(xz.device):
+        _lib.check(lib.selscan_b200_ss2d_in_bwd(d_xs.data_ptr(), xz.data_ptr(), ld, conv_w.data_ptr(), ops._p(conv_b),
+                                                d_xz.data_ptr(), d_xz.shape[-1], part.data_ptr(), B, D, H, W, d_xs.stride(2),
+                                                _stream(xz)), "selscan_b200_ss2d_in_bwd")
+    part = part.sum(0)
+    return part[:, :9].reshape(D, 1, 3, 3), part[:, 9]
+
+
+def edge_out_fwd(ys, H, W, z, zld, ln_w, ln_b, eps, save):
+    """ys (B, 4, D, L) -> merge -> LayerNorm(D) -> * silu(z) -> (B, H, W, D); z is a data pointer (or None) + position stride."""
+    B, _, D, L = ys.shape
+    out = ys.new_empty((B, H, W, D))
+    xhat = ys.new_empty((B * L, D)) if save else None
+    rstd = ys.new_empty((B * L,)) if save else None
+    lib = _lib.load()
+    with torch.cuda.device(ys.device):
+        _lib.check(lib.selscan_b200_ss2d_out_fwd(ys.data_ptr(), ys.stride(2), z, zld, ln_w.data_ptr(), ln_b.data_ptr(), float(eps),
+                                                 out.data_ptr(), ops._p(xhat), ops._p(rstd), B, D, H, W, _stream(ys)),
+                   "selscan_b200_ss2d_out_fwd")
+    return out, xhat, rstd
+
+
+def edge_out_bwd(g, H, W, z, zld, xhat, rstd, ln_w, ln_b, dz, dzld):
+    """Backward of edge_out_fwd: returns (d ys (B, 4, D, L), d ln_w, d ln_b); writes dz through the pointer `dz` when gated."""
+    B, D = g.shape[0], g.shape[-1]
+    L = H * W
+    d_ys = _empty_dirs(g, B, D, L)
+    lib = _lib.load()
+    part = g.new_empty((int(lib.selscan_b200_ss2d_out_partial_elems(B, D, H, W)),))
+    with torch.cuda.device(g.device):
+        _lib.check(lib.selscan_b200_ss2d_out_bwd(g.data_ptr(), z, zld, xhat.data_ptr(), rstd.data_ptr(), ln_w.data_ptr(),
+                                                 ln_b.data_ptr(), dz, dzld, d_ys.data_ptr(), d_ys.stride(2), part.data_ptr(), B, D,
+                                                 H, W, _stream(g)), "selscan_b200_ss2d_out_bwd")
+    part = part.view(-1, 2, D).sum(0)
+    return d_ys, part[0], part[1]
+
+
+class SS2DFusedFn(torch.autograd.Function):
+    """xz = in_proj(x) (B, H, W, 2*D)  ->  LayerNorm(merge(scan(...))) * silu(z)  (B, H, W, D)  (mamba_sys.py:530-537).
+
+    One autograd node with a hand-written backward: prologue kernel, the two projections as batched GEMMs (cuBLAS), the scan,
+    epilogue kernel.  d(xz) is ONE buffer whose halves are written in place by the two edge kernels; d(xs) is the scan's du
+    with the projection's contribution accumulated by the GEMM itself (beta = 1)."""
+
+    @staticmethod
+    def forward(ctx, xz, conv_w, conv_b, x_proj_w, dt_w, dt_b, A_logs, Ds, ln_w, ln_b, eps):
+        B, H, W, D2 = xz.shape
+        D, L, K = D2 // 2, H * W, 4
+        R, N = dt_w.shape[2], A_logs.shape[1]
+        xz = xz.contiguous()
+        conv_w, ln_w, ln_b = conv_w.contiguous(), ln_w.contiguous(), ln_b.contiguous()
+        conv_b = conv_b.contiguous() if conv_b is not None else None
+        needs_grad = any(ctx.needs_input_grad)
+        xs = edge_in_fwd(xz, D, conv_w, conv_b)                                          # (B, K, D, L)
+        x_dbl = torch.matmul(x_proj_w.unsqueeze(0), xs)                                  # (B, K, R+2N, L)   :406
+        dts = torch.matmul(dt_w.unsqueeze(0), x_dbl[:, :, :R])                           # (B, K, D, L)      :409
+        if L % 4:                                                                        # rows must stay 16-byte aligned
+            dts = _empty_dirs(xz, B, D, L).copy_(dts)
+        As = -torch.exp(A_logs.float()).view(K * D, N)                                   # :417
+        Dsf, dtb = Ds.float().reshape(-1).contiguous(), dt_b.float().reshape(-1).contiguous()
+        out_y = _empty_dirs(xz, B, D, L)
+        ckpt = ws = None
+        if needs_grad:
+            ckpt = xz.new_empty((max(ops.ckpt_elems(B, K * D, L, N), 4),))
+        n_ws = ops.fwd_workspace_elems(B, K * D, L, N, K)
+        if n_ws > 0:
+            ws = xz.new_empty((n_ws,))
+        ops.launch_fwd(xs.view(B, K * D, L), dts.view(B, K * D, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], Dsf, None,
+                       dtb, True, out_y.view(B, K * D, L), None, None, ckpt, ws)      # :420-426
+        zptr = xz.data_ptr() + D * xz.element_size()
+        y, xhat, rstd = edge_out_fwd(out_y, H, W, zptr, D2, ln_w, ln_b, eps, needs_grad)  # :429-434, :536
+        if needs_grad:
+            ctx.save_for_backward(xz, xs, x_dbl, dts, As, ckpt, xhat, rstd, conv_w, conv_b, x_proj_w, dt_w, Dsf, dtb, ln_w, ln_b)
+            ctx.shape_A, ctx.shape_D, ctx.shape_dtb = A_logs.shape, Ds.shape, dt_b.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xz, xs, x_dbl, dts, As, ckpt, xhat, rstd, conv_w, conv_b, x_proj_w, dt_w, Dsf, dtb, ln_w, ln_b = ctx.saved_tensors
+        B, H, W, D2 = xz.shape
+        D, L, K = D2 // 2, H * W, 4
+        R, N = dt_w.shape[2], As.shape[1]
+        KD = K * D
+        g = g.contiguous()
+        d_xz = torch.empty_like(xz)
+        esz = xz.element_size()
+        d_ys, d_ln_w, d_ln_b = edge_out_bwd(g, H, W, xz.data_ptr() + D * esz, D2, xhat, rstd, ln_w, ln_b,
+                                            d_xz.data_ptr() + D * esz, D2)
+        du, ddelta = _empty_dirs(xz, B, D, L), _empty_dirs(xz, B, D, L)
+        nbc = B * K * N * L
+        flat = xz.new_zeros((2 * nbc + KD * N + 2 * KD,))
+        dB, dC = flat[:nbc].view(B, K, N, L), flat[nbc:2 * nbc].view(B, K, N, L)
+        dA = flat[2 * nbc:2 * nbc + KD * N].view(KD, N)
+        dD, dbias = flat[2 * nbc + KD * N:2 * nbc + KD * N + KD], flat[2 * nbc + KD * N + KD:]
+        ops.launch_bwd(xs.view(B, KD, L), dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], Dsf, None, dtb,
+                       d_ys.view(B, KD, L), None, ckpt, True, du.view(B, KD, L), ddelta.view(B, KD, L), dA, dB, dC, dD,
+                       None, dbias)
+        x_dt = x_dbl[:, :, :R]
+        d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                      # (K, D, R)
+        d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)                 # (B, K, R, L)
+        d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                       # (B, K, R+2N, L)
+        d_x_proj_w = torch.matmul(d_x_dbl, xs.transpose(-1, -2)).sum(0)                   # (K, R+2N, D)
+        wT = x_proj_w.transpose(-1, -2).unsqueeze(0).expand(B, K, D, R + 2 * N).reshape(B * K, D, R + 2 * N)
+        d_xs = du.view(B * K, D, L)
+        d_xs.baddbmm_(wT, d_x_dbl.view(B * K, R + 2 * N, L))                              # du + W^T d(x_dbl), no extra pass
+        d_conv_w, d_conv_b = edge_in_bwd(du, xz, D, conv_w, conv_b, d_xz)
+        d_A_logs = (dA * As).view(ctx.shape_A)
+        return (d_xz, d_conv_w, d_conv_b if conv_b is not None else None, d_x_proj_w, d_dt_w, dbias.view(ctx.shape_dtb), d_A_logs,
+                dD.view(ctx.shape_D), d_ln_w, d_ln_b, None)
+
+
+def ss2d_inner_b200(self, xz):
+    """in_proj output -> out_proj input, through SS2DFusedFn, with this module's parameters."""
+    conv, ln = self.conv2d, self.out_norm
+    return SS2DFusedFn.apply(xz.float(), conv.weight.float(), conv.bias.float() if conv.bias is not None else None,
+                             self.x_proj_weight.float(), self.dt_projs_weight.float(), self.dt_projs_bias.float(), self.A_logs,
+                             self.Ds, ln.weight.float(), ln.bias.float(), ln.eps)
+
+
+def fused_supported(self, H, W):
+    conv = self.conv2d
+    return (tuple(conv.kernel_size) == (3, 3) and tuple(conv.padding) == (1, 1) and tuple(conv.stride) == (1, 1)
+            and conv.groups == conv.in_channels == conv.out_channels and (H + 2) * ((W + 2) | 1) * 4 * 2 * 4 <= 200 * 1024
+            and self.out_norm.elementwise_affine and self.d_inner <= 16384)
+
+
+def forward_b200(self, x: torch.Tensor, **kwargs):
+    """Drop-in for SS2D.forward (mamba_sys.py:527-540): (B, H, W, d_model) -> (B, H, W, d_model)."""
+    B, H, W, C = x.shape
+    xz = self.in_proj(x)                                                                  # :530
+    if fused_supported(self, H, W):
+        y = ss2d_inner_b200(self, xz).to(x.dtype)
+    else:  # plane too large for the edge kernels' shared memory: same math through the separate kernels
+        xh, z = xz.chunk(2, dim=-1)
+        xh = torch.nn.functional.silu(self.conv2d(xh.permute(0, 3, 1, 2).contiguous()))
+        y = forward_core_b200(self, xh) * torch.nn.functional.silu(z)
+    out = self.out_proj(y)                                                                # :538
+    drop = getattr(self, "dropout", None)
+    return drop(out) if drop is not None else out
+
+
+def patch_ss2d(ss2d_cls, fused=True):
     """Install the core on an SS2D class BEFORE models are built (`self.forward_core = self.forward_corev0` is bound in
-    __init__, mamba_sys.py:332)."""
+    __init__, mamba_sys.py:332); with `fused` also SS2D.forward (conv / CrossScan / CrossMerge / LayerNorm / gate kernels)."""
     ss2d_cls.forward_corev0 = forward_core_b200
+    if fused:
+        ss2d_cls.forward = forward_b200
     return ss2d_cls

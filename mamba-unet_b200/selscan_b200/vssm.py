@@ -8,7 +8,8 @@ checkpoints load with `load_state_dict` (tests/test_vssm_gpu.py checks outputs a
     SS2D          :267-338, :527-540   in_proj -> depthwise 3x3 conv + SiLU -> forward_core -> * silu(z) -> out_proj
     PatchEmbed2D  :165-188,  PatchMerging2D :191-230,  PatchExpand :232-246,  FinalPatchExpand_X4 :248-263
     MambaUnet     /root/reference/code/networks/vision_mamba.py:23-46  (1 -> 3 channel repeat, attribute `mamba_unet`)
-Everything except the scan is stock torch (cuBLAS / cuDNN); only `forward_core_b200` touches the custom kernels.
+Linear layers / GEMMs are stock torch (cuBLAS); everything between in_proj and out_proj of an SS2D block runs on this
+repo's kernels (`ss2d.forward_b200`: conv + SiLU + CrossScan, scan, CrossMerge + LayerNorm + gate).
 """
 import math
 
@@ -16,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ss2d import forward_core_b200
+from .ss2d import forward_b200, forward_core_b200
 
 
 class DropPath(nn.Module):
@@ -61,8 +62,11 @@ class SS2D(nn.Module):
             self.A_logs.copy_(torch.log(torch.arange(1, N + 1, dtype=torch.float32)).repeat(K * D, 1))
 
     forward_core = forward_core_b200
+    fused = True        # conv / CrossScan / CrossMerge / LayerNorm / gate through the SS2D edge kernels (ss2d.forward_b200)
 
     def forward(self, x):                                   # (B, H, W, C), mamba_sys.py:527-540
+        if self.fused:
+            return forward_b200(self, x)
         xz = self.in_proj(x)
         x, z = xz.chunk(2, dim=-1)
         x = F.silu(self.conv2d(x.permute(0, 3, 1, 2).contiguous()))

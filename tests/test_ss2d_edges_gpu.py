@@ -1,0 +1,129 @@
+"""The SS2D edge kernels against the plain-torch chains they replace
+(/root/reference/code/networks/mamba_sys.py:533-534 + :403-404 and :429-434 + :536), forward and backward, through the C ABI."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(2, 8, 7, 7), (1, 5, 4, 9), (2, 192, 56, 56), (3, 64, 14, 14), (2, 40, 28, 28), (1, 384, 7, 7), (2, 33, 9, 5),
+          (1, 1536, 7, 7), (1, 768, 14, 14)]
+
+
+def _fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _close(got, ref, rtol, atol_rel, name):
+    scale = max(1.0, float(ref.abs().max()))
+    torch.testing.assert_close(got, ref, rtol=rtol, atol=atol_rel * scale, msg=lambda m: f"{name}: {m}")
+
+
+@pytest.mark.parametrize("B,D,H,W", SHAPES)
+def test_prologue_conv_silu_cross_scan(B, D, H, W):
+    from selscan_b200.ss2d import cross_scan_torch, edge_in_bwd, edge_in_fwd
+
+    _fp32()
+    torch.manual_seed(B * 1000 + D + H)
+    xz = torch.randn(B, H, W, 2 * D, device="cuda")
+    w = (0.4 * torch.randn(D, 1, 3, 3, device="cuda")).requires_grad_()
+    b = (0.2 * torch.randn(D, device="cuda")).requires_grad_()
+    xh = xz[..., :D].detach().clone().requires_grad_()
+    ref = cross_scan_torch(F.silu(F.conv2d(xh.permute(0, 3, 1, 2).contiguous(), w, b, padding=1, groups=D)))
+    xs = edge_in_fwd(xz, D, w.detach(), b.detach())
+    assert xs.shape == ref.shape
+    _close(xs, ref.detach(), 1e-5, 1e-6, "xs")
+    g = torch.randn_like(ref)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(ref, (xh, w, b), g)
+    L = H * W
+    pitch = (L + 3) // 4 * 4
+    gp = torch.empty(B, 4, D, pitch, device="cuda")[..., :L]
+    gp.copy_(g)
+    d_xz = torch.full_like(xz, 7.0)
+    gw, gb = edge_in_bwd(gp, xz, D, w.detach(), b.detach(), d_xz)
+    assert torch.equal(d_xz[..., D:], torch.full_like(d_xz[..., D:], 7.0))      # the z half belongs to the other edge
+    _close(d_xz[..., :D], gx_ref, 1e-4, 1e-5, "dx")
+    _close(gw, gw_ref, 1e-3, 1e-4, "dconv_w")
+    _close(gb, gb_ref, 1e-3, 1e-4, "dconv_b")
+
+
+@pytest.mark.parametrize("gated", [True, False])
+@pytest.mark.parametrize("B,D,H,W", SHAPES)
+def test_epilogue_merge_layernorm_gate(B, D, H, W, gated):
+    from selscan_b200.ss2d import cross_merge_torch, edge_out_bwd, edge_out_fwd
+
+    _fp32()
+    torch.manual_seed(B * 1000 + D + W)
+    L = H * W
+    pitch = (L + 3) // 4 * 4
+    ys = torch.empty(B, 4, D, pitch, device="cuda")[..., :L]
+    ys.copy_(torch.randn(B, 4, D, L, device="cuda") + 0.3)
+    xz = torch.randn(B, H, W, 2 * D, device="cuda")
+    gamma = (1.0 + 0.3 * torch.randn(D, device="cuda")).requires_grad_()
+    beta = (0.2 * torch.randn(D, device="cuda")).requires_grad_()
+    ys_r = ys.detach().clone().requires_grad_()
+    z_r = xz[..., D:].detach().clone().requires_grad_()
+    y = cross_merge_torch(ys_r, H, W).transpose(1, 2).contiguous().view(B, H, W, D)
+    ref = F.layer_norm(y, (D,), gamma, beta, 1e-5)
+    if gated:
+        ref = ref * F.silu(z_r)
+    esz = xz.element_size()
+    zptr = xz.data_ptr() + D * esz if gated else None
+    out, xhat, rstd = edge_out_fwd(ys, H, W, zptr, 2 * D, gamma.detach(), beta.detach(), 1e-5, True)
+    _close(out, ref.detach(), 1e-4, 1e-5, "out")
+    out2, xh2, rs2 = edge_out_fwd(ys, H, W, zptr, 2 * D, gamma.detach(), beta.detach(), 1e-5, False)   # inference: nothing saved
+    assert xh2 is None and rs2 is None and torch.equal(out, out2)
+    g = torch.randn_like(ref)
+    grads = torch.autograd.grad(ref, (ys_r, gamma, beta) + ((z_r,) if gated else ()), g)
+    d_xz = torch.full_like(xz, 7.0)
+    d_ys, d_gamma, d_beta = edge_out_bwd(g, H, W, zptr, 2 * D, xhat, rstd, gamma.detach(), beta.detach(),
+                                         d_xz.data_ptr() + D * esz if gated else None, 2 * D)
+    assert torch.equal(d_xz[..., :D], torch.full_like(d_xz[..., :D], 7.0))
+    _close(d_ys, grads[0], 1e-3, 1e-5, "dys")
+    _close(d_gamma, grads[1], 1e-3, 1e-4, "dgamma")
+    _close(d_beta, grads[2], 1e-3, 1e-4, "dbeta")
+    if gated:
+        _close(d_xz[..., D:], grads[3], 1e-3, 1e-5, "dz")
+
+
+@pytest.mark.parametrize("B,d_model,H,W", [(2, 16, 8, 8), (1, 20, 7, 7), (2, 96, 56, 56), (2, 24, 5, 9), (3, 192, 14, 14)])
+def test_fused_ss2d_block_matches_separate_kernels(B, d_model, H, W):
+    """SS2D.forward through SS2DFusedFn (hand-written backward) == the same block through conv2d / CrossScan / autograd."""
+    from selscan_b200.vssm import SS2D
+
+    _fp32()
+    torch.manual_seed(d_model + H)
+    blk = SS2D(d_model).cuda()
+    with torch.no_grad():
+        blk.out_norm.weight.add_(0.2 * torch.randn_like(blk.out_norm.weight))
+        blk.out_norm.bias.add_(0.2 * torch.randn_like(blk.out_norm.bias))
+        blk.Ds.add_(0.3 * torch.randn_like(blk.Ds))
+    x = torch.randn(B, H, W, d_model, device="cuda")
+    g = torch.randn(B, H, W, d_model, device="cuda")
+    res = []
+    for fused in (True, False):
+        blk.fused = fused
+        blk.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_()
+        out = blk(xi)
+        out.backward(g)
+        res.append((out.detach(), xi.grad, {k: p.grad.clone() for k, p in blk.named_parameters()}))
+    _close(res[0][0], res[1][0], 1e-4, 1e-5, "out")
+    _close(res[0][1], res[1][1], 1e-3, 1e-4, "dx")
+    assert set(res[0][2]) == {k for k, _ in blk.named_parameters()}
+    for k in res[1][2]:
+        _close(res[0][2][k], res[1][2][k], 2e-3, 2e-4, k)
+    with torch.no_grad():
+        blk.fused = True
+        _close(blk(x), res[1][0], 1e-4, 1e-5, "inference out")
+
+
+def test_patch_ss2d_installs_forward():
+    from selscan_b200.ss2d import forward_b200, forward_core_b200, patch_ss2d
+
+    class Dummy:
+        pass
+
+    patch_ss2d(Dummy)
+    assert Dummy.forward is forward_b200 and Dummy.forward_corev0 is forward_core_b200

@@ -6,16 +6,18 @@
 //   epilogue  :429-434 + :536-537   CrossMerge (flip, 2 x transpose.contiguous, 3 adds) -> transpose(1,2).contiguous()
 //                                   -> LayerNorm(d_inner) -> * silu(z): ~10 kernels, ~14 passes
 // and roughly twice that in their backward.  Here:
-//   ss2d_in_fwd   reads the x half of in_proj's output IN PLACE (channels-last, strided), one CTA per (image, group of
-//                 4 / 8 channels) stages the zero-padded planes in shared memory, and writes the four scan orders directly.
+//   ss2d_in_fwd   reads the x half of in_proj's output IN PLACE (channels-last, strided); one CTA per (image, group of
+//                 4 / 8 channels) stages the zero-padded planes in shared memory, evaluates conv + SiLU once (two rows per
+//                 thread), writes the row-major orders from registers and the column-major orders through a second plane.
 //   ss2d_in_bwd   gathers the four incoming gradients into the plane, recomputes the pre-activation, applies SiLU', the
-//                 transposed conv, and writes dx channels-last into its half of d(xz); per-CTA conv weight/bias partials.
+//                 transposed conv, and writes dx channels-last into its half of d(xz); per-image conv weight/bias partials.
 //   ss2d_out_fwd  one CTA per (image, TH x TW tile of positions) x ALL channels: merges the four scan outputs through a
 //                 shared tile [position][channel], LayerNorm per position (two-pass moments), gate, channels-last store.
 //   ss2d_out_bwd  gate', LayerNorm backward, per-CTA gamma/beta partials, dz into its half of d(xz), and the four
 //                 directional gradients written straight in scan layout.
 // Tile runs along a scan direction are TW (or TH) floats = one 32-byte sector at 8, so the strided side of every
-// transpose still moves whole sectors.
+// transpose still moves whole sectors.  These kernels are latency-bound unless many loads are in flight: every global
+// phase is unrolled so that a thread issues 4-8 independent loads before it uses the first.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,8 +28,23 @@ namespace selscan {
 namespace {
 
 constexpr int kEdgeThreads = 256;
+constexpr int kEdgeWarps = kEdgeThreads / 32;
 
-__device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
+// division by a runtime constant as one IMAD.HI (exact while p * d < 2^32); m == 0 encodes d == 1
+struct FastDiv {
+  int d;
+  unsigned m;
+};
+FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d;
+  f.m = d > 1 ? (unsigned)(((1ull << 32) + (unsigned)d - 1) / (unsigned)d) : 0u;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int p, FastDiv f) { return f.m ? (int)__umulhi((unsigned)p, f.m) : p; }
+
+// 1 / (1 + e^-v): ex2.approx + rcp.approx (rel. error ~2e-7, the level at which torch's own CPU and CUDA silu differ)
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -38,112 +55,201 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------------------------
 // prologue
 // ------------------------------------------------------------------------------------------------------------------
-// Shared plane of one channel: (H + 2) rows x RP floats with a zero border, RP odd (column walks hit distinct banks);
-// channel pitch PP == 32 / kCT (mod 32) so the channels-fastest global <-> shared transposes are conflict-free too.
+// X: zero-bordered plane per channel, (H + 2) rows x RP floats, RP odd; channel pitch PP == 32 / kCT (mod 32) so that the
+// channels-fastest global <-> shared transposes are bank-conflict free.  V: plain plane, row pitch VP odd (column walks
+// hit distinct banks).
+struct InGeom {
+  int D, H, W, L, RP, PP, VP, VPP;
+  FastDiv dW, dH, dL, dH2;       // dH2: by ceil(H / 2)
+  int64_t pitch;
+  int vec;                        // channels-last rows can be moved as float4
+};
 
 template <int kCT>
-__device__ __forceinline__ void load_planes(float* sm, const float* __restrict__ xb, int64_t ld, int c0, int D, int L, int W,
-                                            int RP, int PP) {
-  for (int i = threadIdx.x; i < L * kCT; i += kEdgeThreads) {
-    const int c = i % kCT, p = i / kCT;
-    const int h = p / W, w = p - h * W;
-    if (c0 + c < D) sm[c * PP + (h + 1) * RP + (w + 1)] = __ldg(xb + (int64_t)p * ld + c);
+__device__ __forceinline__ void load_planes(float* sm, const float* __restrict__ xb, int64_t ld, int c0, const InGeom& g) {
+  constexpr int kParts = kCT / 4;
+  if (g.vec && c0 + kCT <= g.D) {
+    const int n = g.L * kParts;
+    for (int i0 = threadIdx.x; i0 < n; i0 += kEdgeThreads * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kEdgeThreads;
+        if (i < n) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)(i / kParts) * ld + (i % kParts) * 4));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kEdgeThreads;
+        if (i < n) {
+          const int p = i / kParts, c = (i % kParts) * 4;
+          const int h = fdiv(p, g.dW), w = p - h * g.W;
+          float* q = sm + c * g.PP + (h + 1) * g.RP + (w + 1);
+          q[0] = v[u].x;
+          q[g.PP] = v[u].y;
+          q[2 * g.PP] = v[u].z;
+          q[3 * g.PP] = v[u].w;
+        }
+      }
+    }
+    return;
+  }
+  const int n = g.L * kCT;
+  for (int i0 = threadIdx.x; i0 < n; i0 += kEdgeThreads * 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kEdgeThreads;
+      v[u] = (i < n && c0 + i % kCT < g.D) ? __ldg(xb + (int64_t)(i / kCT) * ld + i % kCT) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kEdgeThreads;
+      if (i < n) {
+        const int p = i / kCT, c = i % kCT;
+        const int h = fdiv(p, g.dW), w = p - h * g.W;
+        sm[c * g.PP + (h + 1) * g.RP + (w + 1)] = v[u];
+      }
+    }
   }
 }
 
-__device__ __forceinline__ float conv9(const float* q, int RP, const float* w, float bias) {
-  float acc = bias;
-  acc = fmaf(w[0], q[0], acc);
-  acc = fmaf(w[1], q[1], acc);
-  acc = fmaf(w[2], q[2], acc);
-  acc = fmaf(w[3], q[RP], acc);
-  acc = fmaf(w[4], q[RP + 1], acc);
-  acc = fmaf(w[5], q[RP + 2], acc);
-  acc = fmaf(w[6], q[2 * RP], acc);
-  acc = fmaf(w[7], q[2 * RP + 1], acc);
-  acc = fmaf(w[8], q[2 * RP + 2], acc);
-  return acc;
-}
-
 template <int kCT>
-__global__ void __launch_bounds__(kEdgeThreads)
-ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ cw, const float* __restrict__ cb,
-                   float* __restrict__ xs, int D, int H, int W, int RP, int PP, int64_t pitch) {
-  extern __shared__ __align__(16) float sm[];
-  float* wsm = sm + kCT * PP;                  // [kCT][10]: 9 taps + bias
-  const int L = H * W;
-  const int ngrp = (D + kCT - 1) / kCT;
-  const int b = blockIdx.x / ngrp, c0 = (blockIdx.x - b * ngrp) * kCT;
-  for (int i = threadIdx.x; i < kCT * PP / 4; i += kEdgeThreads) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ void load_taps(float* wsm, const float* __restrict__ cw, const float* __restrict__ cb, int c0, int D) {
   if (threadIdx.x < kCT * 10) {
     const int c = threadIdx.x / 10, j = threadIdx.x - c * 10;
     float v = 0.f;
     if (c0 + c < D) v = j < 9 ? __ldg(cw + (int64_t)(c0 + c) * 9 + j) : (cb ? __ldg(cb + c0 + c) : 0.f);
     wsm[threadIdx.x] = v;
   }
+}
+
+template <int kCT>
+__global__ void __launch_bounds__(kEdgeThreads)
+ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ cw, const float* __restrict__ cb,
+                   float* __restrict__ xs, InGeom g) {
+  extern __shared__ __align__(16) float sm[];
+  float* V = sm + kCT * g.PP;
+  float* wsm = V + kCT * g.VPP;                // [kCT][10]: 9 taps + bias
+  const int L = g.L, W = g.W, H = g.H, RP = g.RP;
+  const int ngrp = (g.D + kCT - 1) / kCT;
+  const int b = blockIdx.x / ngrp, c0 = (blockIdx.x - b * ngrp) * kCT;
+  for (int i = threadIdx.x; i < kCT * g.PP / 4; i += kEdgeThreads) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  load_taps<kCT>(wsm, cw, cb, c0, g.D);
   __syncthreads();
-  load_planes<kCT>(sm, x + (int64_t)b * L * ld + c0, ld, c0, D, L, W, RP, PP);
+  load_planes<kCT>(sm, x + (int64_t)b * L * ld + c0, ld, c0, g);
   __syncthreads();
-  const int nvalid = (D - c0 < kCT ? D - c0 : kCT) * L;
-  // row-major orders (k = 0 and its reverse k = 2): lanes walk w
-  for (int i = threadIdx.x; i < nvalid; i += kEdgeThreads) {
-    const int c = i / L, p = i - c * L;
-    const int h = p / W, w = p - h * W;
-    const float a = conv9(sm + c * PP + h * RP + w, RP, wsm + c * 10, wsm[c * 10 + 9]);
-    const float v = a * sigmoid_acc(a);
-    float* o = xs + ((int64_t)b * 4 * D + c0 + c) * pitch;
-    o[p] = v;
-    o[2 * D * pitch + (L - 1 - p)] = v;
+  const int nc = g.D - c0 < kCT ? g.D - c0 : kCT;
+  const int H2 = (H + 1) / 2;
+  // conv + SiLU once, two rows per thread (12 shared loads for 2 outputs); row-major orders k = 0 / 2 leave from registers
+  for (int i = threadIdx.x; i < nc * H2 * W; i += kEdgeThreads) {
+    const int r = fdiv(i, g.dW), w = i - r * W;
+    const int c = fdiv(r, g.dH2), h = (r - c * H2) * 2;
+    const float* q = sm + c * g.PP + h * RP + w;
+    const float* t = wsm + c * 10;
+    float a0 = t[9], a1 = t[9];
+    float r0[3], r1[3], r2[3], r3[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      r0[s] = q[s];
+      r1[s] = q[RP + s];
+      r2[s] = q[2 * RP + s];
+      r3[s] = (h + 1 < H) ? q[3 * RP + s] : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      a0 = fmaf(t[s], r0[s], a0);
+      a0 = fmaf(t[3 + s], r1[s], a0);
+      a0 = fmaf(t[6 + s], r2[s], a0);
+      a1 = fmaf(t[s], r1[s], a1);
+      a1 = fmaf(t[3 + s], r2[s], a1);
+      a1 = fmaf(t[6 + s], r3[s], a1);
+    }
+    const float v0 = a0 * sigmoid_fast(a0), v1 = a1 * sigmoid_fast(a1);
+    float* o = xs + ((int64_t)b * 4 * g.D + c0 + c) * g.pitch;
+    float* o2 = o + 2 * g.D * g.pitch;
+    const int p = h * W + w;
+    o[p] = v0;
+    o2[L - 1 - p] = v0;
+    V[c * g.VPP + h * g.VP + w] = v0;
+    if (h + 1 < H) {
+      o[p + W] = v1;
+      o2[L - 1 - p - W] = v1;
+      V[c * g.VPP + (h + 1) * g.VP + w] = v1;
+    }
   }
-  // column-major orders (k = 1, k = 3): lanes walk h; the conv is simply evaluated again (9 FMAs) instead of parking it
-  for (int i = threadIdx.x; i < nvalid; i += kEdgeThreads) {
-    const int c = i / L, p = i - c * L;
-    const int w = p / H, h = p - w * H;
-    const float a = conv9(sm + c * PP + h * RP + w, RP, wsm + c * 10, wsm[c * 10 + 9]);
-    const float v = a * sigmoid_acc(a);
-    float* o = xs + (((int64_t)b * 4 + 1) * D + c0 + c) * pitch;
+  __syncthreads();
+  // column-major orders k = 1 / 3: lanes walk h
+  for (int i = threadIdx.x; i < nc * L; i += kEdgeThreads) {
+    const int c = fdiv(i, g.dL), p = i - c * L;
+    const int w = fdiv(p, g.dH), h = p - w * H;
+    const float v = V[c * g.VPP + h * g.VP + w];
+    float* o = xs + (((int64_t)b * 4 + 1) * g.D + c0 + c) * g.pitch;
     o[p] = v;
-    o[2 * D * pitch + (L - 1 - p)] = v;
+    o[2 * g.D * g.pitch + (L - 1 - p)] = v;
   }
 }
 
 template <int kCT>
 __global__ void __launch_bounds__(kEdgeThreads)
 ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, int64_t ld, const float* __restrict__ cw,
-                   const float* __restrict__ cb, float* __restrict__ dx, int64_t dld, float* __restrict__ wpart, int D, int H,
-                   int W, int RP, int PP, int64_t pitch) {
+                   const float* __restrict__ cb, float* __restrict__ dx, int64_t dld, float* __restrict__ wpart, InGeom g) {
   extern __shared__ __align__(16) float sm[];
   float* X = sm;
-  float* G = sm + kCT * PP;
-  float* wsm = G + kCT * PP;                   // [kCT][10]
-  float* red = wsm + kCT * 10;                 // [nwarps][10]
-  constexpr int kWarps = kEdgeThreads / 32;
-  constexpr int kWarpsPerC = kWarps / kCT;     // 1 (kCT = 8) or 2 (kCT = 4)
-  const int L = H * W;
+  float* G = sm + kCT * g.PP;
+  float* wsm = G + kCT * g.PP;                 // [kCT][10]
+  float* red = wsm + kCT * 10;                 // [warps][10]
+  constexpr int kWarpsPerC = kEdgeWarps / kCT;     // 1 (kCT = 8) or 2 (kCT = 4)
+  const int L = g.L, W = g.W, H = g.H, RP = g.RP, PP = g.PP, D = g.D;
   const int ngrp = (D + kCT - 1) / kCT;
   const int b = blockIdx.x / ngrp, c0 = (blockIdx.x - b * ngrp) * kCT;
   for (int i = threadIdx.x; i < 2 * kCT * PP / 4; i += kEdgeThreads) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (threadIdx.x < kCT * 10) {
-    const int c = threadIdx.x / 10, j = threadIdx.x - c * 10;
-    float v = 0.f;
-    if (c0 + c < D) v = j < 9 ? __ldg(cw + (int64_t)(c0 + c) * 9 + j) : (cb ? __ldg(cb + c0 + c) : 0.f);
-    wsm[threadIdx.x] = v;
-  }
+  load_taps<kCT>(wsm, cw, cb, c0, D);
   __syncthreads();
-  load_planes<kCT>(X, x + (int64_t)b * L * ld + c0, ld, c0, D, L, W, RP, PP);
+  load_planes<kCT>(X, x + (int64_t)b * L * ld + c0, ld, c0, g);
   const int nvalid = (D - c0 < kCT ? D - c0 : kCT) * L;
-  for (int i = threadIdx.x; i < nvalid; i += kEdgeThreads) {          // CrossScan backward, row-major pair
-    const int c = i / L, p = i - c * L;
-    const int h = p / W, w = p - h * W;
-    const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * pitch;
-    G[c * PP + (h + 1) * RP + (w + 1)] = __ldg(g0 + p) + __ldg(g0 + 2 * D * pitch + (L - 1 - p));
+  const int64_t dir2 = 2 * (int64_t)D * g.pitch;
+  for (int i0 = threadIdx.x; i0 < nvalid; i0 += kEdgeThreads * 4) {   // CrossScan backward, row-major pair
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kEdgeThreads;
+      if (i < nvalid) {
+        const int c = fdiv(i, g.dL), p = i - c * L;
+        const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
+        v[u] = __ldg(g0 + p) + __ldg(g0 + dir2 + (L - 1 - p));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kEdgeThreads;
+      if (i < nvalid) {
+        const int c = fdiv(i, g.dL), p = i - c * L;
+        const int h = fdiv(p, g.dW), w = p - h * W;
+        G[c * PP + (h + 1) * RP + (w + 1)] = v[u];
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nvalid; i += kEdgeThreads) {          // column-major pair
-    const int c = i / L, p = i - c * L;
-    const int w = p / H, h = p - w * H;
-    const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * pitch;
-    G[c * PP + (h + 1) * RP + (w + 1)] += __ldg(g1 + p) + __ldg(g1 + 2 * D * pitch + (L - 1 - p));
+  for (int i0 = threadIdx.x; i0 < nvalid; i0 += kEdgeThreads * 4) {   // column-major pair
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kEdgeThreads;
+      if (i < nvalid) {
+        const int c = fdiv(i, g.dL), p = i - c * L;
+        const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
+        v[u] = __ldg(g1 + p) + __ldg(g1 + dir2 + (L - 1 - p));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kEdgeThreads;
+      if (i < nvalid) {
+        const int c = fdiv(i, g.dL), p = i - c * L;
+        const int w = fdiv(p, g.dH), h = p - w * H;
+        G[c * PP + (h + 1) * RP + (w + 1)] += v[u];
+      }
+    }
   }
   __syncthreads();
   {  // d(pre-activation) in place, conv weight / bias partial sums; a warp stays on one channel
@@ -155,7 +261,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
     if (c0 + c < D) {
       const float* wc = wsm + c * 10;
       for (int p = sub * 32 + lane; p < L; p += kWarpsPerC * 32) {
-        const int h = p / W, w = p - h * W;
+        const int h = fdiv(p, g.dW), w = p - h * W;
         const float* q = X + c * PP + h * RP + w;
         float xv[9];
 #pragma unroll
@@ -165,7 +271,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
         float a = wc[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) a = fmaf(wc[j], xv[j], a);
-        const float sg = sigmoid_acc(a);
+        const float sg = sigmoid_fast(a);
         float* gp = G + c * PP + (h + 1) * RP + (w + 1);
         const float dp = *gp * (sg * (1.f + a * (1.f - sg)));
         *gp = dp;
@@ -189,19 +295,42 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
     for (int k = 0; k < kWarpsPerC; ++k) s += red[(c * kWarpsPerC + k) * 10 + j];
     if (c0 + c < D) wpart[((int64_t)b * D + c0 + c) * 10 + j] = s;
   }
+  // transposed conv, channels-fastest store.  padded coords: dpre[h' - r + 1][w' - s + 1] = q[(2 - r) * RP + (2 - s)]
   float* dxb = dx + (int64_t)b * L * dld + c0;
-  for (int i = threadIdx.x; i < L * kCT; i += kEdgeThreads) {         // transposed conv, channels-fastest store
-    const int c = i % kCT, p = i / kCT;
-    if (c0 + c >= D) continue;
-    const int h = p / W, w = p - h * W;
-    const float* q = G + c * PP + h * RP + w;     // padded coords: dpre[h' - i + 1][w' - j + 1] = q[(2 - i) * RP + (2 - j)]
-    const float* wc = wsm + c * 10;
-    float a = 0.f;
+  constexpr int kParts = kCT / 4;
+  const bool vec = g.vec && c0 + kCT <= D && (dld % 4 == 0) && ((reinterpret_cast<uintptr_t>(dxb) & 15) == 0);
+  if (vec) {
+    for (int i = threadIdx.x; i < L * kParts; i += kEdgeThreads) {
+      const int p = i / kParts, cq = (i % kParts) * 4;
+      const int h = fdiv(p, g.dW), w = p - h * W;
+      float o[4];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 4; ++k) {
+        const float* q = G + (cq + k) * PP + h * RP + w;
+        const float* wc = wsm + (cq + k) * 10;
+        float a = 0.f;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) a = fmaf(wc[r * 3 + s], q[(2 - r) * RP + (2 - s)], a);
-    dxb[(int64_t)p * dld + c] = a;
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) a = fmaf(wc[r * 3 + s], q[(2 - r) * RP + (2 - s)], a);
+        o[k] = a;
+      }
+      *reinterpret_cast<float4*>(dxb + (int64_t)p * dld + cq) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < L * kCT; i += kEdgeThreads) {
+      const int c = i % kCT, p = i / kCT;
+      if (c0 + c >= D) continue;
+      const int h = fdiv(p, g.dW), w = p - h * W;
+      const float* q = G + c * PP + h * RP + w;
+      const float* wc = wsm + c * 10;
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) a = fmaf(wc[r * 3 + s], q[(2 - r) * RP + (2 - s)], a);
+      dxb[(int64_t)p * dld + c] = a;
+    }
   }
 }
 
@@ -209,35 +338,49 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
 // epilogue
 // ------------------------------------------------------------------------------------------------------------------
 struct OutGeom {
-  int D, H, W, L, TH, TW, tiles_h, tiles_w, DP;
+  int D, H, W, L, tiles_h, tiles_w, DP;
   int64_t pitch;
 };
 
 // Walk every (channel, run) of the tile for one pair of scan orders.  kCol = false: runs along w (orders 0 / 2);
 // kCol = true: runs along h (orders 1 / 3).  A warp instruction covers R consecutive run elements x 32 / R channels;
 // the channel pattern is chosen so that the accesses to the [position][channel] tile (pitch DP == 1 mod 32) spread
-// over all banks.  f(d, gpos, tpos) gets the channel, the position in THIS order's sequence, and the tile slot.
-template <bool kCol, typename F>
-__device__ __forceinline__ void for_each_run(const OutGeom& g, int h0, int w0, F f) {
-  const int R = kCol ? g.TH : g.TW;            // run length (power of two <= 8)
-  const int O = kCol ? g.TW : g.TH;            // runs per channel
-  const int DS = 32 / R;
+// over all banks.  Four steps are decoded at once: load(d, gpos) for all four, then store(slot, value), so that
+// 8 global loads per thread are in flight.
+template <int TH, int TW, bool kCol, typename FL, typename FS>
+__device__ __forceinline__ void for_each_run(const OutGeom& g, int h0, int w0, FL load, FS store) {
+  constexpr int R = kCol ? TH : TW;            // run length
+  constexpr int O = kCol ? TW : TH;            // runs per channel
+  constexpr int DS = 32 / R;
+  constexpr int U = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = lane % R, dsub = lane / R;
   const int dblocks = (g.D + 31) / 32;
-  const int dlo_n = kCol ? R : R;              // d = dblk * 32 + (row-runs: dsub * R + dlo | column-runs: dlo * DS + dsub)
-  const int total = dlo_n * dblocks * O;
-  for (int m = warp; m < total; m += kEdgeThreads / 32) {
-    const int dlo = m % dlo_n;
-    const int r = m / dlo_n;
-    const int dblk = r % dblocks, o = r / dblocks;
-    const int d = dblk * 32 + (kCol ? dlo * DS + dsub : dsub * R + dlo);
-    const int hh = kCol ? i : o, ww = kCol ? o : i;
-    const int h = h0 + hh, w = w0 + ww;
-    if (d < g.D && h < g.H && w < g.W) f(d, kCol ? w * g.H + h : h * g.W + w, hh * g.TW + ww);
+  const int total = R * dblocks * O;           // steps: (dlo, dblk, o); d = dblk*32 + (rows: dsub*R + dlo | columns: dlo*DS + dsub)
+  for (int m0 = warp; m0 < total; m0 += kEdgeWarps * U) {
+    float v[U];
+    int slot[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int m = m0 + u * kEdgeWarps;
+      const int dlo = m % R, r = m / R;
+      const int dblk = r % dblocks, o = r / dblocks;
+      const int d = dblk * 32 + (kCol ? dlo * DS + dsub : dsub * R + dlo);
+      const int hh = kCol ? i : o, ww = kCol ? o : i;
+      const int h = h0 + hh, w = w0 + ww;
+      slot[u] = -1;
+      if (m < total && d < g.D && h < g.H && w < g.W) {
+        slot[u] = (hh * TW + ww) * g.DP + d;
+        v[u] = load(d, kCol ? w * g.H + h : h * g.W + w, slot[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (slot[u] >= 0) store(slot[u], v[u]);
   }
 }
 
+template <int TH, int TW>
 __global__ void __launch_bounds__(kEdgeThreads)
 ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, int64_t zld, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, float* __restrict__ out, float* __restrict__ xhat,
@@ -245,89 +388,115 @@ ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, i
   extern __shared__ __align__(16) float T[];
   const int tiles = g.tiles_h * g.tiles_w;
   const int b = blockIdx.x / tiles, t = blockIdx.x - b * tiles;
-  const int h0 = (t / g.tiles_w) * g.TH, w0 = (t % g.tiles_w) * g.TW;
+  const int h0 = (t / g.tiles_w) * TH, w0 = (t % g.tiles_w) * TW;
   const float* yb = ys + (int64_t)b * 4 * g.D * g.pitch;
   const int64_t dir = (int64_t)g.D * g.pitch;
-  const int L = g.L;
-  for_each_run<false>(g, h0, w0, [&](int d, int gp, int tp) {
-    const float* r = yb + (int64_t)d * g.pitch;
-    T[tp * g.DP + d] = __ldg(r + gp) + __ldg(r + 2 * dir + (L - 1 - gp));
-  });
+  const int L = g.L, D = g.D;
+  for_each_run<TH, TW, false>(
+      g, h0, w0,
+      [&](int d, int gp, int) {
+        const float* r = yb + (int64_t)d * g.pitch;
+        return __ldg(r + gp) + __ldg(r + 2 * dir + (L - 1 - gp));
+      },
+      [&](int slot, float v) { T[slot] = v; });
   __syncthreads();
-  for_each_run<true>(g, h0, w0, [&](int d, int gp, int tp) {
-    const float* r = yb + dir + (int64_t)d * g.pitch;
-    T[tp * g.DP + d] += __ldg(r + gp) + __ldg(r + 2 * dir + (L - 1 - gp));
-  });
+  for_each_run<TH, TW, true>(
+      g, h0, w0,
+      [&](int d, int gp, int) {
+        const float* r = yb + dir + (int64_t)d * g.pitch;
+        return __ldg(r + gp) + __ldg(r + 2 * dir + (L - 1 - gp));
+      },
+      [&](int slot, float v) { T[slot] += v; });
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float inv_d = 1.f / (float)g.D;
-  for (int tp = warp; tp < g.TH * g.TW; tp += kEdgeThreads / 32) {
-    const int h = h0 + tp / g.TW, w = w0 + tp % g.TW;
+  const float inv_d = 1.f / (float)D;
+  for (int tp = warp; tp < TH * TW; tp += kEdgeWarps) {
+    const int h = h0 + tp / TW, w = w0 + tp % TW;
     if (h >= g.H || w >= g.W) continue;
     const float* row = T + tp * g.DP;
+    const int64_t pos = (int64_t)b * L + h * g.W + w;
     float s = 0.f;
-    for (int d = lane; d < g.D; d += 32) s += row[d];
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) s += row[d];
     const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
-    for (int d = lane; d < g.D; d += 32) {
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) {
       const float c = row[d] - mean;
       q = fmaf(c, c, q);
     }
     const float rs = rsqrtf(warp_sum(q) * inv_d + eps);
-    const int64_t pos = (int64_t)b * L + h * g.W + w;
     if (rstd_out != nullptr && lane == 0) rstd_out[pos] = rs;
-    for (int d = lane; d < g.D; d += 32) {
-      const float xh = (row[d] - mean) * rs;
-      float v = fmaf(xh, __ldg(gamma + d), __ldg(beta + d));
-      if (z != nullptr) {
-        const float zz = __ldg(z + pos * zld + d);
-        v *= zz * sigmoid_acc(zz);
+    if (z != nullptr) {
+      const float* zr = z + pos * zld;
+#pragma unroll 4
+      for (int d = lane; d < D; d += 32) {
+        const float zz = __ldg(zr + d);
+        const float xh = (row[d] - mean) * rs;
+        out[pos * D + d] = fmaf(xh, __ldg(gamma + d), __ldg(beta + d)) * (zz * sigmoid_fast(zz));
+        if (xhat != nullptr) xhat[pos * D + d] = xh;
       }
-      out[pos * g.D + d] = v;
-      if (xhat != nullptr) xhat[pos * g.D + d] = xh;
+    } else {
+#pragma unroll 4
+      for (int d = lane; d < D; d += 32) {
+        const float xh = (row[d] - mean) * rs;
+        out[pos * D + d] = fmaf(xh, __ldg(gamma + d), __ldg(beta + d));
+        if (xhat != nullptr) xhat[pos * D + d] = xh;
+      }
     }
   }
 }
 
+template <int TH, int TW>
 __global__ void __launch_bounds__(kEdgeThreads)
 ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z, int64_t zld, const float* __restrict__ xhat,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ dz, int64_t dzld, float* __restrict__ dys, float* __restrict__ part, OutGeom g) {
   extern __shared__ __align__(16) float T[];
-  const int P = g.TH * g.TW;
+  constexpr int P = TH * TW;
   float* m1 = T + P * g.DP;                    // [P] mean_d(dln * gamma)
   float* m2 = m1 + P;                          // [P] mean_d(dln * gamma * xhat)
   const int tiles = g.tiles_h * g.tiles_w;
   const int b = blockIdx.x / tiles, t = blockIdx.x - b * tiles;
-  const int h0 = (t / g.tiles_w) * g.TH, w0 = (t % g.tiles_w) * g.TW;
-  const int L = g.L;
+  const int h0 = (t / g.tiles_w) * TH, w0 = (t % g.tiles_w) * TW;
+  const int L = g.L, D = g.D;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float inv_d = 1.f / (float)g.D;
-  for (int tp = warp; tp < P; tp += kEdgeThreads / 32) {           // gate backward, LayerNorm row moments
-    const int h = h0 + tp / g.TW, w = w0 + tp % g.TW;
+  const float inv_d = 1.f / (float)D;
+  for (int tp = warp; tp < P; tp += kEdgeWarps) {                  // gate backward, LayerNorm row moments
+    const int h = h0 + tp / TW, w = w0 + tp % TW;
     float* row = T + tp * g.DP;
     if (h >= g.H || w >= g.W) {
-      for (int d = lane; d < g.D; d += 32) row[d] = 0.f;
+      for (int d = lane; d < D; d += 32) row[d] = 0.f;
       continue;
     }
     const int64_t pos = (int64_t)b * L + h * g.W + w;
+    const float* gr = gout + pos * D;
+    const float* xr = xhat + pos * D;
     float a1 = 0.f, a2 = 0.f;
-    for (int d = lane; d < g.D; d += 32) {
-      const float go = __ldg(gout + pos * g.D + d);
-      const float xh = __ldg(xhat + pos * g.D + d);
-      const float gm = __ldg(gamma + d);
-      float dln = go;
-      if (z != nullptr) {
-        const float zz = __ldg(z + pos * zld + d);
-        const float sg = sigmoid_acc(zz);
-        const float lnout = fmaf(xh, gm, __ldg(beta + d));
-        dz[pos * dzld + d] = go * lnout * (sg * (1.f + zz * (1.f - sg)));
-        dln = go * (zz * sg);
+    if (z != nullptr) {
+      const float* zr = z + pos * zld;
+      float* dzr = dz + pos * dzld;
+#pragma unroll 4
+      for (int d = lane; d < D; d += 32) {
+        const float go = __ldg(gr + d), xh = __ldg(xr + d), zz = __ldg(zr + d);
+        const float gm = __ldg(gamma + d);
+        const float sg = sigmoid_fast(zz);
+        dzr[d] = go * fmaf(xh, gm, __ldg(beta + d)) * (sg * (1.f + zz * (1.f - sg)));
+        const float dln = go * (zz * sg);
+        row[d] = dln;
+        const float dy = dln * gm;
+        a1 += dy;
+        a2 = fmaf(dy, xh, a2);
       }
-      row[d] = dln;
-      const float dy = dln * gm;
-      a1 += dy;
-      a2 = fmaf(dy, xh, a2);
+    } else {
+#pragma unroll 4
+      for (int d = lane; d < D; d += 32) {
+        const float dln = __ldg(gr + d), xh = __ldg(xr + d);
+        row[d] = dln;
+        const float dy = dln * __ldg(gamma + d);
+        a1 += dy;
+        a2 = fmaf(dy, xh, a2);
+      }
     }
     a1 = warp_sum(a1);
     a2 = warp_sum(a2);
@@ -337,82 +506,110 @@ ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z,
     }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < g.D; d += kEdgeThreads) {         // per-CTA gamma / beta partials (summed by the host)
+  for (int d = threadIdx.x; d < D; d += kEdgeThreads) {            // per-CTA gamma / beta partials (summed by the host)
     float sg = 0.f, sb = 0.f;
+#pragma unroll 8
     for (int tp = 0; tp < P; ++tp) {
-      const int h = h0 + tp / g.TW, w = w0 + tp % g.TW;
-      if (h >= g.H || w >= g.W) continue;
-      const float dln = T[tp * g.DP + d];
-      sb += dln;
-      sg = fmaf(dln, __ldg(xhat + ((int64_t)b * L + h * g.W + w) * g.D + d), sg);
+      const int h = h0 + tp / TW, w = w0 + tp % TW;
+      if (h < g.H && w < g.W) {
+        const float dln = T[tp * g.DP + d];
+        sb += dln;
+        sg = fmaf(dln, __ldg(xhat + ((int64_t)b * L + h * g.W + w) * D + d), sg);
+      }
     }
-    part[(int64_t)blockIdx.x * 2 * g.D + d] = sg;
-    part[(int64_t)blockIdx.x * 2 * g.D + g.D + d] = sb;
+    part[(int64_t)blockIdx.x * 2 * D + d] = sg;
+    part[(int64_t)blockIdx.x * 2 * D + D + d] = sb;
   }
   __syncthreads();
-  for (int tp = warp; tp < P; tp += kEdgeThreads / 32) {           // LayerNorm input gradient, in place
-    const int h = h0 + tp / g.TW, w = w0 + tp % g.TW;
+  for (int tp = warp; tp < P; tp += kEdgeWarps) {                  // LayerNorm input gradient, in place
+    const int h = h0 + tp / TW, w = w0 + tp % TW;
     if (h >= g.H || w >= g.W) continue;
     const int64_t pos = (int64_t)b * L + h * g.W + w;
     const float rs = __ldg(rstd + pos), c1 = m1[tp], c2 = m2[tp];
     float* row = T + tp * g.DP;
-    for (int d = lane; d < g.D; d += 32) {
-      const float xh = __ldg(xhat + pos * g.D + d);
-      row[d] = rs * (fmaf(row[d], __ldg(gamma + d), -c1) - xh * c2);
-    }
+    const float* xr = xhat + pos * D;
+#pragma unroll 4
+    for (int d = lane; d < D; d += 32) row[d] = rs * (fmaf(row[d], __ldg(gamma + d), -c1) - __ldg(xr + d) * c2);
   }
   __syncthreads();
-  float* db = dys + (int64_t)b * 4 * g.D * g.pitch;
-  const int64_t dir = (int64_t)g.D * g.pitch;
-  for_each_run<false>(g, h0, w0, [&](int d, int gp, int tp) {      // CrossMerge backward: every order gets the same value
-    const float v = T[tp * g.DP + d];
-    float* r = db + (int64_t)d * g.pitch;
-    r[gp] = v;
-    r[2 * dir + (L - 1 - gp)] = v;
-  });
-  for_each_run<true>(g, h0, w0, [&](int d, int gp, int tp) {
-    const float v = T[tp * g.DP + d];
-    float* r = db + dir + (int64_t)d * g.pitch;
-    r[gp] = v;
-    r[2 * dir + (L - 1 - gp)] = v;
-  });
+  float* db = dys + (int64_t)b * 4 * D * g.pitch;
+  const int64_t dir = (int64_t)D * g.pitch;
+  // CrossMerge backward: every order receives the same value
+  // (the global stores are issued from the first functor: they need d and gp, not just the slot)
+  for_each_run<TH, TW, false>(
+      g, h0, w0,
+      [&](int d, int gp, int slot) {
+        const float v = T[slot];
+        float* r = db + (int64_t)d * g.pitch;
+        r[gp] = v;
+        r[2 * dir + (L - 1 - gp)] = v;
+        return 0.f;
+      },
+      [&](int, float) {});
+  for_each_run<TH, TW, true>(
+      g, h0, w0,
+      [&](int d, int gp, int slot) {
+        const float v = T[slot];
+        float* r = db + dir + (int64_t)d * g.pitch;
+        r[gp] = v;
+        r[2 * dir + (L - 1 - gp)] = v;
+        return 0.f;
+      },
+      [&](int, float) {});
 }
 
 struct InPlan {
-  int ct, RP, PP;
+  int ct;
   size_t smem;
+  InGeom g;
 };
 
-// planes per CTA: 8 channels when `nplanes` padded planes of 8 channels leave room for two CTAs per SM, else 4
-InPlan plan_in(int H, int W, int nplanes) {
+// channels per CTA: 8 when the planes of 8 channels leave room for two CTAs per SM, else 4.
+// planes: forward = padded X + plain V, backward = padded X + padded G
+InPlan plan_in(int D, int H, int W, int64_t pitch, bool bwd) {
   InPlan p;
-  p.RP = (W + 2) | 1;
+  InGeom& g = p.g;
+  g.D = D; g.H = H; g.W = W; g.L = H * W; g.pitch = pitch;
+  g.RP = (W + 2) | 1;
+  g.VP = W | 1;
+  g.VPP = H * g.VP;
+  g.dW = make_fastdiv(W); g.dH = make_fastdiv(H); g.dL = make_fastdiv(H * W); g.dH2 = make_fastdiv((H + 1) / 2);
+  g.vec = 0;
   for (p.ct = 8;; p.ct = 4) {
     const int want = 32 / p.ct;
-    int pp = (H + 2) * p.RP;
+    int pp = (H + 2) * g.RP;
     pp += ((want - pp % 32) % 32 + 32) % 32;
-    p.PP = pp;
-    p.smem = ((size_t)nplanes * p.ct * pp + p.ct * 10 + 10 * (kEdgeThreads / 32)) * sizeof(float);
+    g.PP = pp;
+    const size_t planes = bwd ? 2 * (size_t)p.ct * pp : (size_t)p.ct * (pp + g.VPP);
+    p.smem = (planes + p.ct * 10 + 10 * kEdgeWarps) * sizeof(float);
     if (p.ct == 4 || p.smem <= 112 * 1024) break;
   }
   return p;
 }
 
-bool plan_out(int D, int H, int W, int64_t pitch, OutGeom* g, size_t* smem) {
+template <int TH, int TW>
+bool out_fits(int DP, size_t* smem) {
+  *smem = ((size_t)TH * TW * DP + 2 * TH * TW) * sizeof(float);
+  return *smem <= 100 * 1024;
+}
+
+// tile shape index: 0 = 8x8, 1 = 8x4, 2 = 4x4, 3 = 2x2, 4 = 1x1 (any D up to ~55K)
+int plan_out(int D, int H, int W, int64_t pitch, OutGeom* g, size_t* smem) {
   g->D = D; g->H = H; g->W = W; g->L = H * W; g->pitch = pitch;
   g->DP = D + ((1 - D % 32) + 32) % 32;
-  static const int shapes[][2] = {{8, 8}, {8, 4}, {4, 4}, {4, 2}, {2, 2}, {2, 1}, {1, 1}};
-  for (const auto& s : shapes) {
-    const size_t need = ((size_t)s[0] * s[1] * g->DP + 2 * s[0] * s[1]) * sizeof(float);
-    if (need <= 100 * 1024 || (s[0] == 1 && s[1] == 1 && need <= 220 * 1024)) {
-      g->TH = s[0]; g->TW = s[1];
-      g->tiles_h = (H + g->TH - 1) / g->TH;
-      g->tiles_w = (W + g->TW - 1) / g->TW;
-      *smem = need;
-      return true;
-    }
+  int shape, th, tw;
+  if (out_fits<8, 8>(g->DP, smem)) { shape = 0; th = 8; tw = 8; }
+  else if (out_fits<8, 4>(g->DP, smem)) { shape = 1; th = 8; tw = 4; }
+  else if (out_fits<4, 4>(g->DP, smem)) { shape = 2; th = 4; tw = 4; }
+  else if (out_fits<2, 2>(g->DP, smem)) { shape = 3; th = 2; tw = 2; }
+  else {
+    *smem = ((size_t)g->DP + 2) * sizeof(float);
+    if (*smem > 220 * 1024) return -1;
+    shape = 4; th = 1; tw = 1;
   }
-  return false;
+  g->tiles_h = (H + th - 1) / th;
+  g->tiles_w = (W + tw - 1) / tw;
+  return shape;
 }
 
 template <typename K>
@@ -421,22 +618,28 @@ cudaError_t allow_smem(K kernel, size_t smem) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 }  // namespace
 
-bool ss2d_in_supported(int H, int W) { return plan_in(H, W, 2).smem <= 220 * 1024; }
+bool ss2d_in_supported(int H, int W) {
+  return plan_in(8, H, W, (int64_t)H * W, true).smem <= 220 * 1024 && plan_in(8, H, W, (int64_t)H * W, false).smem <= 220 * 1024 &&
+         (int64_t)H * W * 8 < (1 << 24);
+}
 
 cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, const float* cb, float* xs, int B, int D, int H, int W,
                                int64_t pitch, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
-  const InPlan p = plan_in(H, W, 1);
+  InPlan p = plan_in(D, H, W, pitch, false);
+  p.g.vec = al16(x) && ld % 4 == 0;
   const unsigned grid = (unsigned)((int64_t)B * ((D + p.ct - 1) / p.ct));
   cudaError_t e;
   if (p.ct == 8) {
     if ((e = allow_smem(ss2d_in_fwd_kernel<8>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_fwd_kernel<8><<<grid, kEdgeThreads, p.smem, stream>>>(x, ld, cw, cb, xs, D, H, W, p.RP, p.PP, pitch);
+    ss2d_in_fwd_kernel<8><<<grid, kEdgeThreads, p.smem, stream>>>(x, ld, cw, cb, xs, p.g);
   } else {
     if ((e = allow_smem(ss2d_in_fwd_kernel<4>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_fwd_kernel<4><<<grid, kEdgeThreads, p.smem, stream>>>(x, ld, cw, cb, xs, D, H, W, p.RP, p.PP, pitch);
+    ss2d_in_fwd_kernel<4><<<grid, kEdgeThreads, p.smem, stream>>>(x, ld, cw, cb, xs, p.g);
   }
   return cudaGetLastError();
 }
@@ -444,15 +647,16 @@ cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, cons
 cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, const float* cw, const float* cb, float* dx, int64_t dld,
                                float* wpart, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
-  const InPlan p = plan_in(H, W, 2);
+  InPlan p = plan_in(D, H, W, pitch, true);
+  p.g.vec = al16(x) && ld % 4 == 0;
   const unsigned grid = (unsigned)((int64_t)B * ((D + p.ct - 1) / p.ct));
   cudaError_t e;
   if (p.ct == 8) {
     if ((e = allow_smem(ss2d_in_bwd_kernel<8>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_bwd_kernel<8><<<grid, kEdgeThreads, p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, D, H, W, p.RP, p.PP, pitch);
+    ss2d_in_bwd_kernel<8><<<grid, kEdgeThreads, p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, p.g);
   } else {
     if ((e = allow_smem(ss2d_in_bwd_kernel<4>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_bwd_kernel<4><<<grid, kEdgeThreads, p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, D, H, W, p.RP, p.PP, pitch);
+    ss2d_in_bwd_kernel<4><<<grid, kEdgeThreads, p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, p.g);
   }
   return cudaGetLastError();
 }
@@ -460,27 +664,36 @@ cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, con
 bool ss2d_out_supported(int D) {
   OutGeom g;
   size_t smem;
-  return plan_out(D, 8, 8, 64, &g, &smem);
+  return D > 0 && plan_out(D, 8, 8, 64, &g, &smem) >= 0;
 }
 
 int64_t ss2d_out_ctas(int B, int D, int H, int W) {
   OutGeom g;
   size_t smem;
-  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || !plan_out(D, H, W, (int64_t)H * W, &g, &smem)) return 0;
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || plan_out(D, H, W, (int64_t)H * W, &g, &smem) < 0) return 0;
   return (int64_t)B * g.tiles_h * g.tiles_w;
 }
+
+#define SS2D_OUT_DISPATCH(KERNEL, ...)                                                         \
+  switch (shape) {                                                                             \
+    case 0: if ((e = allow_smem(KERNEL<8, 8>, smem)) == cudaSuccess) KERNEL<8, 8><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
+    case 1: if ((e = allow_smem(KERNEL<8, 4>, smem)) == cudaSuccess) KERNEL<8, 4><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
+    case 2: if ((e = allow_smem(KERNEL<4, 4>, smem)) == cudaSuccess) KERNEL<4, 4><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
+    case 3: if ((e = allow_smem(KERNEL<2, 2>, smem)) == cudaSuccess) KERNEL<2, 2><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
+    default: if ((e = allow_smem(KERNEL<1, 1>, smem)) == cudaSuccess) KERNEL<1, 1><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
+  }
 
 cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, int64_t zld, const float* gamma, const float* beta,
                                 float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   OutGeom g;
   size_t smem;
-  if (!plan_out(D, H, W, pitch, &g, &smem)) return cudaErrorInvalidValue;
-  cudaError_t e = allow_smem(ss2d_out_fwd_kernel, smem);
-  if (e != cudaSuccess) return e;
+  const int shape = plan_out(D, H, W, pitch, &g, &smem);
+  if (shape < 0) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((int64_t)B * g.tiles_h * g.tiles_w);
-  ss2d_out_fwd_kernel<<<grid, kEdgeThreads, smem, stream>>>(ys, z, zld, gamma, beta, eps, out, xhat, rstd, g);
-  return cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  SS2D_OUT_DISPATCH(ss2d_out_fwd_kernel, ys, z, zld, gamma, beta, eps, out, xhat, rstd, g)
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, const float* xhat, const float* rstd,
@@ -489,12 +702,12 @@ cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, 
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   OutGeom g;
   size_t smem;
-  if (!plan_out(D, H, W, pitch, &g, &smem)) return cudaErrorInvalidValue;
-  cudaError_t e = allow_smem(ss2d_out_bwd_kernel, smem);
-  if (e != cudaSuccess) return e;
+  const int shape = plan_out(D, H, W, pitch, &g, &smem);
+  if (shape < 0) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((int64_t)B * g.tiles_h * g.tiles_w);
-  ss2d_out_bwd_kernel<<<grid, kEdgeThreads, smem, stream>>>(gout, z, zld, xhat, rstd, gamma, beta, dz, dzld, dys, part, g);
-  return cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  SS2D_OUT_DISPATCH(ss2d_out_bwd_kernel, gout, z, zld, xhat, rstd, gamma, beta, dz, dzld, dys, part, g)
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace selscan

@@ -29,6 +29,8 @@ namespace {
 
 constexpr int kEdgeThreads = 256;
 constexpr int kEdgeWarps = kEdgeThreads / 32;
+constexpr int kInThreads = 512;                // prologue kernels: two big-plane CTAs per SM, so more threads per CTA
+constexpr int kInWarps = kInThreads / 32;
 
 // division by a runtime constant as one IMAD.HI (exact while p * d < 2^32); m == 0 encodes d == 1
 struct FastDiv {
@@ -68,18 +70,19 @@ struct InGeom {
 template <int kCT>
 __device__ __forceinline__ void load_planes(float* sm, const float* __restrict__ xb, int64_t ld, int c0, const InGeom& g) {
   constexpr int kParts = kCT / 4;
+  const int nthr = blockDim.x;
   if (g.vec && c0 + kCT <= g.D) {
     const int n = g.L * kParts;
-    for (int i0 = threadIdx.x; i0 < n; i0 += kEdgeThreads * 4) {
+    for (int i0 = threadIdx.x; i0 < n; i0 += nthr * 4) {
       float4 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kEdgeThreads;
+        const int i = i0 + u * nthr;
         if (i < n) v[u] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)(i / kParts) * ld + (i % kParts) * 4));
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * kEdgeThreads;
+        const int i = i0 + u * nthr;
         if (i < n) {
           const int p = i / kParts, c = (i % kParts) * 4;
           const int h = fdiv(p, g.dW), w = p - h * g.W;
@@ -94,16 +97,16 @@ __device__ __forceinline__ void load_planes(float* sm, const float* __restrict__
     return;
   }
   const int n = g.L * kCT;
-  for (int i0 = threadIdx.x; i0 < n; i0 += kEdgeThreads * 4) {
+  for (int i0 = threadIdx.x; i0 < n; i0 += nthr * 4) {
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kEdgeThreads;
+      const int i = i0 + u * nthr;
       v[u] = (i < n && c0 + i % kCT < g.D) ? __ldg(xb + (int64_t)(i / kCT) * ld + i % kCT) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kEdgeThreads;
+      const int i = i0 + u * nthr;
       if (i < n) {
         const int p = i / kCT, c = i % kCT;
         const int h = fdiv(p, g.dW), w = p - h * g.W;
@@ -124,16 +127,17 @@ __device__ __forceinline__ void load_taps(float* wsm, const float* __restrict__ 
 }
 
 template <int kCT>
-__global__ void __launch_bounds__(kEdgeThreads)
+__global__ void __launch_bounds__(kInThreads, 2)
 ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restrict__ cw, const float* __restrict__ cb,
                    float* __restrict__ xs, InGeom g) {
   extern __shared__ __align__(16) float sm[];
   float* V = sm + kCT * g.PP;
   float* wsm = V + kCT * g.VPP;                // [kCT][10]: 9 taps + bias
   const int L = g.L, W = g.W, H = g.H, RP = g.RP;
+  const int nthr = blockDim.x;
   const int ngrp = (g.D + kCT - 1) / kCT;
   const int b = blockIdx.x / ngrp, c0 = (blockIdx.x - b * ngrp) * kCT;
-  for (int i = threadIdx.x; i < kCT * g.PP / 4; i += kEdgeThreads) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < kCT * g.PP / 4; i += nthr) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   load_taps<kCT>(wsm, cw, cb, c0, g.D);
   __syncthreads();
   load_planes<kCT>(sm, x + (int64_t)b * L * ld + c0, ld, c0, g);
@@ -141,7 +145,7 @@ ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restr
   const int nc = g.D - c0 < kCT ? g.D - c0 : kCT;
   const int H2 = (H + 1) / 2;
   // conv + SiLU once, two rows per thread (12 shared loads for 2 outputs); row-major orders k = 0 / 2 leave from registers
-  for (int i = threadIdx.x; i < nc * H2 * W; i += kEdgeThreads) {
+  for (int i = threadIdx.x; i < nc * H2 * W; i += nthr) {
     const int r = fdiv(i, g.dW), w = i - r * W;
     const int c = fdiv(r, g.dH2), h = (r - c * H2) * 2;
     const float* q = sm + c * g.PP + h * RP + w;
@@ -179,7 +183,7 @@ ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restr
   }
   __syncthreads();
   // column-major orders k = 1 / 3: lanes walk h
-  for (int i = threadIdx.x; i < nc * L; i += kEdgeThreads) {
+  for (int i = threadIdx.x; i < nc * L; i += nthr) {
     const int c = fdiv(i, g.dL), p = i - c * L;
     const int w = fdiv(p, g.dH), h = p - w * H;
     const float v = V[c * g.VPP + h * g.VP + w];
@@ -190,7 +194,7 @@ ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restr
 }
 
 template <int kCT>
-__global__ void __launch_bounds__(kEdgeThreads)
+__global__ void __launch_bounds__(kInThreads, 2)
 ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, int64_t ld, const float* __restrict__ cw,
                    const float* __restrict__ cb, float* __restrict__ dx, int64_t dld, float* __restrict__ wpart, InGeom g) {
   extern __shared__ __align__(16) float sm[];
@@ -198,21 +202,23 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
   float* G = sm + kCT * g.PP;
   float* wsm = G + kCT * g.PP;                 // [kCT][10]
   float* red = wsm + kCT * 10;                 // [warps][10]
-  constexpr int kWarpsPerC = kEdgeWarps / kCT;     // 1 (kCT = 8) or 2 (kCT = 4)
   const int L = g.L, W = g.W, H = g.H, RP = g.RP, PP = g.PP, D = g.D;
+  const int nthr = blockDim.x, nwarps = nthr >> 5;
+  const int wpc = nwarps > kCT ? nwarps / kCT : 1;      // warps per channel in the d(pre-activation) pass
+  const int cslots = nwarps / wpc;                       // channels in flight (divides kCT: powers of two)
   const int ngrp = (D + kCT - 1) / kCT;
   const int b = blockIdx.x / ngrp, c0 = (blockIdx.x - b * ngrp) * kCT;
-  for (int i = threadIdx.x; i < 2 * kCT * PP / 4; i += kEdgeThreads) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < 2 * kCT * PP / 4; i += nthr) reinterpret_cast<float4*>(sm)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   load_taps<kCT>(wsm, cw, cb, c0, D);
   __syncthreads();
   load_planes<kCT>(X, x + (int64_t)b * L * ld + c0, ld, c0, g);
   const int nvalid = (D - c0 < kCT ? D - c0 : kCT) * L;
   const int64_t dir2 = 2 * (int64_t)D * g.pitch;
-  for (int i0 = threadIdx.x; i0 < nvalid; i0 += kEdgeThreads * 4) {   // CrossScan backward, row-major pair
+  for (int i0 = threadIdx.x; i0 < nvalid; i0 += nthr * 4) {   // CrossScan backward, row-major pair
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kEdgeThreads;
+      const int i = i0 + u * nthr;
       if (i < nvalid) {
         const int c = fdiv(i, g.dL), p = i - c * L;
         const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
@@ -221,7 +227,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kEdgeThreads;
+      const int i = i0 + u * nthr;
       if (i < nvalid) {
         const int c = fdiv(i, g.dL), p = i - c * L;
         const int h = fdiv(p, g.dW), w = p - h * W;
@@ -230,11 +236,11 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
     }
   }
   __syncthreads();
-  for (int i0 = threadIdx.x; i0 < nvalid; i0 += kEdgeThreads * 4) {   // column-major pair
+  for (int i0 = threadIdx.x; i0 < nvalid; i0 += nthr * 4) {   // column-major pair
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kEdgeThreads;
+      const int i = i0 + u * nthr;
       if (i < nvalid) {
         const int c = fdiv(i, g.dL), p = i - c * L;
         const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
@@ -243,7 +249,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kEdgeThreads;
+      const int i = i0 + u * nthr;
       if (i < nvalid) {
         const int c = fdiv(i, g.dL), p = i - c * L;
         const int w = fdiv(p, g.dH), h = p - w * H;
@@ -252,47 +258,48 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
     }
   }
   __syncthreads();
-  {  // d(pre-activation) in place, conv weight / bias partial sums; a warp stays on one channel
+  {  // d(pre-activation) in place, conv weight / bias partial sums; a warp stays on one channel at a time
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = warp / kWarpsPerC, sub = warp - c * kWarpsPerC;
-    float acc[10];
+    const int sub = warp % wpc;
+    for (int c = warp / wpc; c < kCT; c += cslots) {
+      float acc[10];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) acc[j] = 0.f;
-    if (c0 + c < D) {
-      const float* wc = wsm + c * 10;
-      for (int p = sub * 32 + lane; p < L; p += kWarpsPerC * 32) {
-        const int h = fdiv(p, g.dW), w = p - h * W;
-        const float* q = X + c * PP + h * RP + w;
-        float xv[9];
+      for (int j = 0; j < 10; ++j) acc[j] = 0.f;
+      if (c0 + c < D) {
+        const float* wc = wsm + c * 10;
+        for (int p = sub * 32 + lane; p < L; p += wpc * 32) {
+          const int h = fdiv(p, g.dW), w = p - h * W;
+          const float* q = X + c * PP + h * RP + w;
+          float xv[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) xv[r * 3 + s] = q[r * RP + s];
-        float a = wc[9];
+            for (int s = 0; s < 3; ++s) xv[r * 3 + s] = q[r * RP + s];
+          float a = wc[9];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) a = fmaf(wc[j], xv[j], a);
-        const float sg = sigmoid_fast(a);
-        float* gp = G + c * PP + (h + 1) * RP + (w + 1);
-        const float dp = *gp * (sg * (1.f + a * (1.f - sg)));
-        *gp = dp;
+          for (int j = 0; j < 9; ++j) a = fmaf(wc[j], xv[j], a);
+          const float sg = sigmoid_fast(a);
+          float* gp = G + c * PP + (h + 1) * RP + (w + 1);
+          const float dp = *gp * (sg * (1.f + a * (1.f - sg)));
+          *gp = dp;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) acc[j] = fmaf(dp, xv[j], acc[j]);
-        acc[9] += dp;
+          for (int j = 0; j < 9; ++j) acc[j] = fmaf(dp, xv[j], acc[j]);
+          acc[9] += dp;
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 10; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
+      for (int j = 0; j < 10; ++j) acc[j] = warp_sum(acc[j]);
+      if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 10; ++j) red[warp * 10 + j] = acc[j];
+        for (int j = 0; j < 10; ++j) red[(c * wpc + sub) * 10 + j] = acc[j];
+      }
     }
   }
   __syncthreads();
   if (threadIdx.x < kCT * 10) {
     const int c = threadIdx.x / 10, j = threadIdx.x - c * 10;
     float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < kWarpsPerC; ++k) s += red[(c * kWarpsPerC + k) * 10 + j];
+    for (int k = 0; k < wpc; ++k) s += red[(c * wpc + k) * 10 + j];
     if (c0 + c < D) wpart[((int64_t)b * D + c0 + c) * 10 + j] = s;
   }
   // transposed conv, channels-fastest store.  padded coords: dpre[h' - r + 1][w' - s + 1] = q[(2 - r) * RP + (2 - s)]
@@ -300,7 +307,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
   constexpr int kParts = kCT / 4;
   const bool vec = g.vec && c0 + kCT <= D && (dld % 4 == 0) && ((reinterpret_cast<uintptr_t>(dxb) & 15) == 0);
   if (vec) {
-    for (int i = threadIdx.x; i < L * kParts; i += kEdgeThreads) {
+    for (int i = threadIdx.x; i < L * kParts; i += nthr) {
       const int p = i / kParts, cq = (i % kParts) * 4;
       const int h = fdiv(p, g.dW), w = p - h * W;
       float o[4];
@@ -318,7 +325,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
       *reinterpret_cast<float4*>(dxb + (int64_t)p * dld + cq) = make_float4(o[0], o[1], o[2], o[3]);
     }
   } else {
-    for (int i = threadIdx.x; i < L * kCT; i += kEdgeThreads) {
+    for (int i = threadIdx.x; i < L * kCT; i += nthr) {
       const int c = i % kCT, p = i / kCT;
       if (c0 + c >= D) continue;
       const int h = fdiv(p, g.dW), w = p - h * W;
@@ -339,49 +346,91 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
 // ------------------------------------------------------------------------------------------------------------------
 struct OutGeom {
   int D, H, W, L, tiles_h, tiles_w, DP;
+  FastDiv dDb;                   // by the number of 32-channel blocks
   int64_t pitch;
 };
 
 // Walk every (channel, run) of the tile for one pair of scan orders.  kCol = false: runs along w (orders 0 / 2);
-// kCol = true: runs along h (orders 1 / 3).  A warp instruction covers R consecutive run elements x 32 / R channels;
-// the channel pattern is chosen so that the accesses to the [position][channel] tile (pitch DP == 1 mod 32) spread
-// over all banks.  Four steps are decoded at once: load(d, gpos) for all four, then store(slot, value), so that
-// 8 global loads per thread are in flight.
-template <int TH, int TW, bool kCol, typename FL, typename FS>
-__device__ __forceinline__ void for_each_run(const OutGeom& g, int h0, int w0, FL load, FS store) {
+// kCol = true: runs along h (orders 1 / 3).  A lane moves VEC consecutive run elements (float2 when the plane sides are
+// even), a warp instruction covers one run x 32 / (R / VEC) channels; the channel pattern keeps the accesses to the
+// [position][channel] tile (pitch DP == 1 mod 32) at most 2-way bank conflicted.  Four steps are decoded at once:
+// body(d, gpos, slot0, slot_step) issues its global loads for all four before `finish` consumes them.
+template <int VEC>
+struct Run {
+  float a[VEC];
+};
+
+template <int VEC>
+__device__ __forceinline__ Run<VEC> ld_run(const float* p) {          // elements p[0 .. VEC)
+  Run<VEC> r;
+  if constexpr (VEC == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.a[0] = t.x;
+    r.a[1] = t.y;
+  } else {
+    r.a[0] = __ldg(p);
+  }
+  return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ Run<VEC> ld_run_rev(const float* base, int L, int gp) {   // elements base[L-1-gp], base[L-2-gp]
+  Run<VEC> r;
+  if constexpr (VEC == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(base + (L - 2 - gp)));
+    r.a[0] = t.y;
+    r.a[1] = t.x;
+  } else {
+    r.a[0] = __ldg(base + (L - 1 - gp));
+  }
+  return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_run(float* p, const Run<VEC>& r) {
+  if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(r.a[0], r.a[1]);
+  else *p = r.a[0];
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_run_rev(float* base, int L, int gp, const Run<VEC>& r) {
+  if constexpr (VEC == 2) *reinterpret_cast<float2*>(base + (L - 2 - gp)) = make_float2(r.a[1], r.a[0]);
+  else base[L - 1 - gp] = r.a[0];
+}
+
+template <int TH, int TW, bool kCol, int VEC, typename FL, typename FS>
+__device__ __forceinline__ void for_each_run(const OutGeom& g, int h0, int w0, FL load, FS finish) {
   constexpr int R = kCol ? TH : TW;            // run length
   constexpr int O = kCol ? TW : TH;            // runs per channel
-  constexpr int DS = 32 / R;
-  constexpr int U = 4;
+  constexpr int RL = R / VEC;                  // lanes per run
+  constexpr int DS = 32 / RL;                  // channels per warp instruction
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = lane % R, dsub = lane / R;
-  const int dblocks = (g.D + 31) / 32;
-  const int total = R * dblocks * O;           // steps: (dlo, dblk, o); d = dblk*32 + (rows: dsub*R + dlo | columns: dlo*DS + dsub)
-  for (int m0 = warp; m0 < total; m0 += kEdgeWarps * U) {
-    float v[U];
-    int slot[U];
+  const int i = (lane % RL) * VEC, dsub = lane / RL;
+  const int dblocks = g.dDb.d;
+  const int step = (kCol ? TW : 1) * g.DP;     // tile distance of two consecutive run elements
+  for (int q = warp; q < O * dblocks; q += kEdgeWarps) {          // (run o, block of 32 channels)
+    const int o = fdiv(q, g.dDb), dblk = q - o * dblocks;
+    const int hh = kCol ? i : o, ww = kCol ? o : i;
+    const int h = h0 + hh, w = w0 + ww;
+    const bool inside = h < g.H && w < g.W;                       // VEC = 2 only with even H and W: both elements are inside
+    const int gp = kCol ? w * g.H + h : h * g.W + w;
+    const int slot0 = (hh * TW + ww) * g.DP + dblk * 32;
+    Run<VEC> v[RL];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int m = m0 + u * kEdgeWarps;
-      const int dlo = m % R, r = m / R;
-      const int dblk = r % dblocks, o = r / dblocks;
-      const int d = dblk * 32 + (kCol ? dlo * DS + dsub : dsub * R + dlo);
-      const int hh = kCol ? i : o, ww = kCol ? o : i;
-      const int h = h0 + hh, w = w0 + ww;
-      slot[u] = -1;
-      if (m < total && d < g.D && h < g.H && w < g.W) {
-        slot[u] = (hh * TW + ww) * g.DP + d;
-        v[u] = load(d, kCol ? w * g.H + h : h * g.W + w, slot[u]);
-      }
+    for (int dlo = 0; dlo < RL; ++dlo) {                          // the RL x 2 global loads of a step are issued back to back
+      const int dd = kCol ? dlo * DS + dsub : dsub * RL + dlo;
+      if (inside && dblk * 32 + dd < g.D) v[dlo] = load(dblk * 32 + dd, gp, slot0 + dd, step);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (slot[u] >= 0) store(slot[u], v[u]);
+    for (int dlo = 0; dlo < RL; ++dlo) {
+      const int dd = kCol ? dlo * DS + dsub : dsub * RL + dlo;
+      if (inside && dblk * 32 + dd < g.D) finish(slot0 + dd, step, v[dlo]);
+    }
   }
 }
 
-template <int TH, int TW>
-__global__ void __launch_bounds__(kEdgeThreads)
+template <int TH, int TW, int VEC>
+__global__ void __launch_bounds__(kEdgeThreads, 4)
 ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, int64_t zld, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float eps, float* __restrict__ out, float* __restrict__ xhat,
                     float* __restrict__ rstd_out, OutGeom g) {
@@ -392,21 +441,35 @@ ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, i
   const float* yb = ys + (int64_t)b * 4 * g.D * g.pitch;
   const int64_t dir = (int64_t)g.D * g.pitch;
   const int L = g.L, D = g.D;
-  for_each_run<TH, TW, false>(
+  for_each_run<TH, TW, false, VEC>(
       g, h0, w0,
-      [&](int d, int gp, int) {
+      [&](int d, int gp, int, int) {
         const float* r = yb + (int64_t)d * g.pitch;
-        return __ldg(r + gp) + __ldg(r + 2 * dir + (L - 1 - gp));
+        Run<VEC> a = ld_run<VEC>(r + gp);
+        const Run<VEC> c = ld_run_rev<VEC>(r + 2 * dir, L, gp);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a.a[k] += c.a[k];
+        return a;
       },
-      [&](int slot, float v) { T[slot] = v; });
+      [&](int slot, int step, const Run<VEC>& v) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) T[slot + k * step] = v.a[k];
+      });
   __syncthreads();
-  for_each_run<TH, TW, true>(
+  for_each_run<TH, TW, true, VEC>(
       g, h0, w0,
-      [&](int d, int gp, int) {
+      [&](int d, int gp, int, int) {
         const float* r = yb + dir + (int64_t)d * g.pitch;
-        return __ldg(r + gp) + __ldg(r + 2 * dir + (L - 1 - gp));
+        Run<VEC> a = ld_run<VEC>(r + gp);
+        const Run<VEC> c = ld_run_rev<VEC>(r + 2 * dir, L, gp);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a.a[k] += c.a[k];
+        return a;
       },
-      [&](int slot, float v) { T[slot] += v; });
+      [&](int slot, int step, const Run<VEC>& v) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) T[slot + k * step] += v.a[k];
+      });
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float inv_d = 1.f / (float)D;
@@ -447,8 +510,8 @@ ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, i
   }
 }
 
-template <int TH, int TW>
-__global__ void __launch_bounds__(kEdgeThreads)
+template <int TH, int TW, int VEC>
+__global__ void __launch_bounds__(kEdgeThreads, 4)
 ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z, int64_t zld, const float* __restrict__ xhat,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ dz, int64_t dzld, float* __restrict__ dys, float* __restrict__ part, OutGeom g) {
@@ -534,28 +597,31 @@ ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z,
   __syncthreads();
   float* db = dys + (int64_t)b * 4 * D * g.pitch;
   const int64_t dir = (int64_t)D * g.pitch;
-  // CrossMerge backward: every order receives the same value
-  // (the global stores are issued from the first functor: they need d and gp, not just the slot)
-  for_each_run<TH, TW, false>(
+  // CrossMerge backward: every order receives the same value (the global stores need d and gp, so they sit in the first functor)
+  for_each_run<TH, TW, false, VEC>(
       g, h0, w0,
-      [&](int d, int gp, int slot) {
-        const float v = T[slot];
+      [&](int d, int gp, int slot, int step) {
+        Run<VEC> v;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v.a[k] = T[slot + k * step];
         float* r = db + (int64_t)d * g.pitch;
-        r[gp] = v;
-        r[2 * dir + (L - 1 - gp)] = v;
-        return 0.f;
+        st_run<VEC>(r + gp, v);
+        st_run_rev<VEC>(r + 2 * dir, L, gp, v);
+        return v;
       },
-      [&](int, float) {});
-  for_each_run<TH, TW, true>(
+      [&](int, int, const Run<VEC>&) {});
+  for_each_run<TH, TW, true, VEC>(
       g, h0, w0,
-      [&](int d, int gp, int slot) {
-        const float v = T[slot];
+      [&](int d, int gp, int slot, int step) {
+        Run<VEC> v;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v.a[k] = T[slot + k * step];
         float* r = db + dir + (int64_t)d * g.pitch;
-        r[gp] = v;
-        r[2 * dir + (L - 1 - gp)] = v;
-        return 0.f;
+        st_run<VEC>(r + gp, v);
+        st_run_rev<VEC>(r + 2 * dir, L, gp, v);
+        return v;
       },
-      [&](int, float) {});
+      [&](int, int, const Run<VEC>&) {});
 }
 
 struct InPlan {
@@ -581,7 +647,7 @@ InPlan plan_in(int D, int H, int W, int64_t pitch, bool bwd) {
     pp += ((want - pp % 32) % 32 + 32) % 32;
     g.PP = pp;
     const size_t planes = bwd ? 2 * (size_t)p.ct * pp : (size_t)p.ct * (pp + g.VPP);
-    p.smem = (planes + p.ct * 10 + 10 * kEdgeWarps) * sizeof(float);
+    p.smem = (planes + p.ct * 10 + 10 * kInWarps) * sizeof(float);
     if (p.ct == 4 || p.smem <= 112 * 1024) break;
   }
   return p;
@@ -590,26 +656,34 @@ InPlan plan_in(int D, int H, int W, int64_t pitch, bool bwd) {
 template <int TH, int TW>
 bool out_fits(int DP, size_t* smem) {
   *smem = ((size_t)TH * TW * DP + 2 * TH * TW) * sizeof(float);
-  return *smem <= 100 * 1024;
+  return *smem <= 52 * 1024;                    // four CTAs per SM
 }
 
-// tile shape index: 0 = 8x8, 1 = 8x4, 2 = 4x4, 3 = 2x2, 4 = 1x1 (any D up to ~55K)
+// tile shape index: 0 = 8x8, 1 = 8x4, 2 = 4x4, 3 = 4x2, 4 = 2x2, 5 = 1x1 (any D up to ~55K)
 int plan_out(int D, int H, int W, int64_t pitch, OutGeom* g, size_t* smem) {
   g->D = D; g->H = H; g->W = W; g->L = H * W; g->pitch = pitch;
   g->DP = D + ((1 - D % 32) + 32) % 32;
+  g->dDb = make_fastdiv((D + 31) / 32);
   int shape, th, tw;
   if (out_fits<8, 8>(g->DP, smem)) { shape = 0; th = 8; tw = 8; }
   else if (out_fits<8, 4>(g->DP, smem)) { shape = 1; th = 8; tw = 4; }
   else if (out_fits<4, 4>(g->DP, smem)) { shape = 2; th = 4; tw = 4; }
-  else if (out_fits<2, 2>(g->DP, smem)) { shape = 3; th = 2; tw = 2; }
+  else if (out_fits<4, 2>(g->DP, smem)) { shape = 3; th = 4; tw = 2; }
+  else if (out_fits<2, 2>(g->DP, smem)) { shape = 4; th = 2; tw = 2; }
   else {
     *smem = ((size_t)g->DP + 2) * sizeof(float);
     if (*smem > 220 * 1024) return -1;
-    shape = 4; th = 1; tw = 1;
+    shape = 5; th = 1; tw = 1;
   }
   g->tiles_h = (H + th - 1) / th;
   g->tiles_w = (W + tw - 1) / tw;
   return shape;
+}
+
+// threads per prologue CTA: about 8 elements per thread, 128 .. 512 (>= 80 threads are needed to stage the taps)
+int in_threads(int ct, int L) {
+  const int want = (ct * L / 8 + 31) / 32 * 32;
+  return want < 128 ? 128 : (want > kInThreads ? kInThreads : want);
 }
 
 template <typename K>
@@ -636,10 +710,10 @@ cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, cons
   cudaError_t e;
   if (p.ct == 8) {
     if ((e = allow_smem(ss2d_in_fwd_kernel<8>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_fwd_kernel<8><<<grid, kEdgeThreads, p.smem, stream>>>(x, ld, cw, cb, xs, p.g);
+    ss2d_in_fwd_kernel<8><<<grid, in_threads(p.ct, H * W), p.smem, stream>>>(x, ld, cw, cb, xs, p.g);
   } else {
     if ((e = allow_smem(ss2d_in_fwd_kernel<4>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_fwd_kernel<4><<<grid, kEdgeThreads, p.smem, stream>>>(x, ld, cw, cb, xs, p.g);
+    ss2d_in_fwd_kernel<4><<<grid, in_threads(p.ct, H * W), p.smem, stream>>>(x, ld, cw, cb, xs, p.g);
   }
   return cudaGetLastError();
 }
@@ -653,10 +727,10 @@ cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, con
   cudaError_t e;
   if (p.ct == 8) {
     if ((e = allow_smem(ss2d_in_bwd_kernel<8>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_bwd_kernel<8><<<grid, kEdgeThreads, p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, p.g);
+    ss2d_in_bwd_kernel<8><<<grid, in_threads(p.ct, H * W), p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, p.g);
   } else {
     if ((e = allow_smem(ss2d_in_bwd_kernel<4>, p.smem)) != cudaSuccess) return e;
-    ss2d_in_bwd_kernel<4><<<grid, kEdgeThreads, p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, p.g);
+    ss2d_in_bwd_kernel<4><<<grid, in_threads(p.ct, H * W), p.smem, stream>>>(dxs, x, ld, cw, cb, dx, dld, wpart, p.g);
   }
   return cudaGetLastError();
 }
@@ -674,14 +748,30 @@ int64_t ss2d_out_ctas(int B, int D, int H, int W) {
   return (int64_t)B * g.tiles_h * g.tiles_w;
 }
 
-#define SS2D_OUT_DISPATCH(KERNEL, ...)                                                         \
-  switch (shape) {                                                                             \
-    case 0: if ((e = allow_smem(KERNEL<8, 8>, smem)) == cudaSuccess) KERNEL<8, 8><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
-    case 1: if ((e = allow_smem(KERNEL<8, 4>, smem)) == cudaSuccess) KERNEL<8, 4><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
-    case 2: if ((e = allow_smem(KERNEL<4, 4>, smem)) == cudaSuccess) KERNEL<4, 4><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
-    case 3: if ((e = allow_smem(KERNEL<2, 2>, smem)) == cudaSuccess) KERNEL<2, 2><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
-    default: if ((e = allow_smem(KERNEL<1, 1>, smem)) == cudaSuccess) KERNEL<1, 1><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); break; \
+#define SS2D_OUT_CASE(KERNEL, TH, TW, ...)                                                                        \
+  if (vec2) {                                                                                                      \
+    if ((e = allow_smem(KERNEL<TH, TW, 2>, smem)) == cudaSuccess) KERNEL<TH, TW, 2><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); \
+  } else {                                                                                                         \
+    if ((e = allow_smem(KERNEL<TH, TW, 1>, smem)) == cudaSuccess) KERNEL<TH, TW, 1><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); \
+  }                                                                                                                \
+  break;
+
+#define SS2D_OUT_DISPATCH(KERNEL, ...)                                                                             \
+  switch (shape) {                                                                                                 \
+    case 0: SS2D_OUT_CASE(KERNEL, 8, 8, __VA_ARGS__)                                                               \
+    case 1: SS2D_OUT_CASE(KERNEL, 8, 4, __VA_ARGS__)                                                               \
+    case 2: SS2D_OUT_CASE(KERNEL, 4, 4, __VA_ARGS__)                                                               \
+    case 3: SS2D_OUT_CASE(KERNEL, 4, 2, __VA_ARGS__)                                                               \
+    case 4: SS2D_OUT_CASE(KERNEL, 2, 2, __VA_ARGS__)                                                               \
+    default:                                                                                                       \
+      if ((e = allow_smem(KERNEL<1, 1, 1>, smem)) == cudaSuccess) KERNEL<1, 1, 1><<<grid, kEdgeThreads, smem, stream>>>(__VA_ARGS__); \
+      break;                                                                                                       \
   }
+
+// float2 runs: even plane sides and row pitch, 8-byte aligned base
+bool out_vec2(const float* p, int H, int W, int64_t pitch) {
+  return H % 2 == 0 && W % 2 == 0 && pitch % 2 == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0;
+}
 
 cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, int64_t zld, const float* gamma, const float* beta,
                                 float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, cudaStream_t stream) {
@@ -692,6 +782,7 @@ cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, 
   if (shape < 0) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((int64_t)B * g.tiles_h * g.tiles_w);
   cudaError_t e = cudaSuccess;
+  const bool vec2 = out_vec2(ys, H, W, pitch);
   SS2D_OUT_DISPATCH(ss2d_out_fwd_kernel, ys, z, zld, gamma, beta, eps, out, xhat, rstd, g)
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -706,6 +797,7 @@ cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, 
   if (shape < 0) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((int64_t)B * g.tiles_h * g.tiles_w);
   cudaError_t e = cudaSuccess;
+  const bool vec2 = out_vec2(dys, H, W, pitch);
   SS2D_OUT_DISPATCH(ss2d_out_bwd_kernel, gout, z, zld, xhat, rstd, gamma, beta, dz, dzld, dys, part, g)
   return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -154,6 +154,19 @@ int selscan_b200_ss2d_out_bwd(const float* dout, const float* z, int64_t z_pos_s
                               const float* ln_weight, const float* ln_bias, float* dz, int64_t dz_pos_stride, float* dys,
                               int64_t row_pitch, float* dln_part, int32_t batch, int32_t dim, int32_t H, int32_t W, void* stream);
 
+/* LayerNorm over the last dimension of a contiguous (rows, dim) fp32 tensor: the op on the caller side of every SS2D block
+ * (VSSBlock.ln_1, code/networks/mamba_sys.py:552,559; PatchMerging2D.norm :205; PatchExpand.norm :242; VSSM.norm / norm_up).
+ * Biased variance, y = (x - mean) * rsqrt(var + eps) * weight + bias, as torch.nn.LayerNorm.  dim <= 1536
+ * (selscan_b200_layernorm_supported).  mean / rstd (rows each) are saved for the backward when non-NULL.
+ * bwd: dx fully written; dwb_part = selscan_b200_layernorm_partial_elems() floats = (n_ctas, 2, dim) partial sums of
+ * d weight and d bias, summed over n_ctas by the caller. */
+int selscan_b200_layernorm_supported(int32_t dim);
+int64_t selscan_b200_layernorm_partial_elems(int64_t rows, int32_t dim);
+int selscan_b200_layernorm_fwd(const float* x, const float* weight, const float* bias, float eps, float* y, float* mean, float* rstd,
+                               int64_t rows, int32_t dim, void* stream);
+int selscan_b200_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* weight, float* dx,
+                               float* dwb_part, int64_t rows, int32_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

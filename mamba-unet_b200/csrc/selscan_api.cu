@@ -223,4 +223,30 @@ SELSCAN_EXPORT int selscan_b200_ss2d_out_bwd(const float* dout, const float* z, 
                                                      row_pitch, dln_part, batch, dim, H, W, static_cast<cudaStream_t>(stream)));
 }
 
+SELSCAN_EXPORT int selscan_b200_layernorm_supported(int32_t dim) { return dim > 0 && selscan::ln_nv(dim) != 0; }
+
+SELSCAN_EXPORT int64_t selscan_b200_layernorm_partial_elems(int64_t rows, int32_t dim) {
+  return dim > 0 ? selscan::ln_bwd_ctas(rows, dim) * 2 * (int64_t)dim : 0;
+}
+
+SELSCAN_EXPORT int selscan_b200_layernorm_fwd(const float* x, const float* weight, const float* bias, float eps, float* y, float* mean,
+                                              float* rstd, int64_t rows, int32_t dim, void* stream) {
+  const char* who = "selscan_b200_layernorm_fwd";
+  if (!x || !weight || !bias || !y) return fail("%s: x, weight, bias, y must not be NULL", who);
+  if ((mean == nullptr) != (rstd == nullptr)) return fail("%s: mean and rstd are saved together (both or neither)", who);
+  if (rows < 0 || dim <= 0) return fail("%s: bad sizes rows=%lld dim=%d", who, (long long)rows, dim);
+  if (selscan::ln_nv(dim) == 0) return fail("%s: dim=%d is larger than the kernels are instantiated for (1536)", who, dim);
+  return edge_done(who, selscan::launch_ln_fwd(x, weight, bias, eps, y, mean, rstd, rows, dim, static_cast<cudaStream_t>(stream)));
+}
+
+SELSCAN_EXPORT int selscan_b200_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* weight,
+                                              float* dx, float* dwb_part, int64_t rows, int32_t dim, void* stream) {
+  const char* who = "selscan_b200_layernorm_bwd";
+  if (!dy || !x || !mean || !rstd || !weight || !dx || !dwb_part)
+    return fail("%s: dy, x, mean, rstd, weight, dx, dwb_part must not be NULL", who);
+  if (rows < 0 || dim <= 0) return fail("%s: bad sizes rows=%lld dim=%d", who, (long long)rows, dim);
+  if (selscan::ln_nv(dim) == 0) return fail("%s: dim=%d is larger than the kernels are instantiated for (1536)", who, dim);
+  return edge_done(who, selscan::launch_ln_bwd(dy, x, mean, rstd, weight, dx, dwb_part, rows, dim, static_cast<cudaStream_t>(stream)));
+}
+
 }  // extern "C"

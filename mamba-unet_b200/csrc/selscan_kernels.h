@@ -59,4 +59,12 @@ cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, 
                                 const float* gamma, const float* beta, float* dz, int64_t dzld, float* dys, int64_t pitch,
                                 float* part, int B, int D, int H, int W, cudaStream_t stream);
 
+// LayerNorm over short rows (selscan_ln.cu): ln_nv(dim) == 0 means the row length is not instantiated
+int ln_nv(int D);
+int64_t ln_bwd_ctas(int64_t rows, int D);
+cudaError_t launch_ln_fwd(const float* x, const float* w, const float* b, float eps, float* y, float* mean, float* rstd, int64_t rows,
+                          int D, cudaStream_t stream);
+cudaError_t launch_ln_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, float* dx, float* part,
+                          int64_t rows, int D, cudaStream_t stream);
+
 }  // namespace selscan

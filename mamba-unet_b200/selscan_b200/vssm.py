@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .layernorm import LayerNorm
 from .ss2d import forward_b200, forward_core_b200
 
 
@@ -49,7 +50,7 @@ class SS2D(nn.Module):
         self.dt_projs_bias = nn.Parameter(torch.empty(K, D))
         self.A_logs = nn.Parameter(torch.empty(K * D, N))
         self.Ds = nn.Parameter(torch.ones(K * D))
-        self.out_norm = nn.LayerNorm(D)
+        self.out_norm = LayerNorm(D)
         self.out_proj = nn.Linear(D, d_model, bias=False)
         self.A_logs._no_weight_decay = True
         self.Ds._no_weight_decay = True
@@ -77,7 +78,7 @@ class SS2D(nn.Module):
 class VSSBlock(nn.Module):
     def __init__(self, hidden_dim, drop_path=0.0, d_state=16):
         super().__init__()
-        self.ln_1 = nn.LayerNorm(hidden_dim)
+        self.ln_1 = LayerNorm(hidden_dim)
         self.self_attention = SS2D(hidden_dim, d_state=d_state)
         self.drop_path = DropPath(drop_path)
 
@@ -89,7 +90,7 @@ class PatchMerging2D(nn.Module):
     def __init__(self, dim):
         super().__init__()
         self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
-        self.norm = nn.LayerNorm(4 * dim)
+        self.norm = LayerNorm(4 * dim)
 
     def forward(self, x):                                   # (B, H, W, C) -> (B, H/2, W/2, 2C)
         x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], dim=-1)
@@ -103,7 +104,7 @@ class PatchExpand(nn.Module):
         super().__init__()
         self.scale, self.out_dim = scale, out_dim
         self.expand = nn.Linear(dim, scale * scale * out_dim, bias=False)
-        self.norm = nn.LayerNorm(out_dim)
+        self.norm = LayerNorm(out_dim)
 
     def forward(self, x):
         B, H, W, _ = x.shape
@@ -138,7 +139,7 @@ class VSSM(nn.Module):
         d0 = dims[0]
         self.patch_embed = nn.Module()
         self.patch_embed.proj = nn.Conv2d(in_chans, d0, kernel_size=patch_size, stride=patch_size)
-        self.patch_embed.norm = nn.LayerNorm(d0)
+        self.patch_embed.norm = LayerNorm(d0)
         dpr = torch.linspace(0, drop_path_rate, sum(depths)).tolist()
         sl = lambda i: dpr[sum(depths[:i]):sum(depths[:i + 1])]
         self.layers = nn.ModuleList([VSSLayer(d0 * 2 ** i, depths[i], sl(i), d_state, downsample=(i < n - 1)) for i in range(n)])
@@ -152,8 +153,8 @@ class VSSM(nn.Module):
             else:
                 self.layers_up.append(VSSLayer(dim, depths[n - 1 - i], sl(n - 1 - i), d_state, upsample=(i < n - 1)))
                 self.concat_back_dim.append(nn.Linear(2 * dim, dim))
-        self.norm = nn.LayerNorm(d0 * 2 ** (n - 1))
-        self.norm_up = nn.LayerNorm(d0)
+        self.norm = LayerNorm(d0 * 2 ** (n - 1))
+        self.norm_up = LayerNorm(d0)
         self.up = PatchExpand(d0, 4, d0)
         self.output = nn.Conv2d(d0, num_classes, kernel_size=1, bias=False)
         self.apply(self._init)

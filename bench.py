@@ -218,11 +218,28 @@ def model_leg(world, rank, dev, steps):
     with torch.no_grad():
         ms = timed(lambda: model(x24), n)
     res["infer_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
+    if world == 1:   # the same forward replayed as one CUDA graph (host launch overhead removed)
+        try:
+            with torch.no_grad():
+                g = wl.GraphedStep(lambda x: model(x), x24)
+                ms = timed(lambda: g(x24), n)
+            res["infer_bs24_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
+            del g
+        except Exception as e:  # noqa: BLE001 -- reported, not hidden
+            res["infer_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
     model.train()
     net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if world > 1 else model
     opt = wl.make_sgd(net)
     ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
     res["train_supervised_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
+    if world == 1:
+        try:
+            g = wl.GraphedStep(lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24)
+            ms = timed(lambda: g(x24, y24), n)
+            res["train_supervised_bs24_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
+            del g
+        except Exception as e:  # noqa: BLE001
+            res["train_supervised_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
     del net, opt, model
     m1, m2 = MambaUnet(num_classes=4).to(dev).train(), MambaUnet(num_classes=4).to(dev).train()
     if world > 1:

@@ -56,8 +56,33 @@ def semi_step(model1, model2, opt1, opt2, dice, x, y, labeled_bs, cw):
     return loss
 
 
+class GraphedStep:
+    """A whole static-shape step (forward, loss, backward, optimizer) captured once as a CUDA graph and replayed: at batch 24 a
+    MambaUnet step is ~2600 kernel launches, and the host can no longer issue them as fast as a B200 retires them (SURVEY.md
+    section 8f row 4).  `fn(*tensors)` must be sync-free; inputs are copied into the captured buffers before every replay."""
+
+    def __init__(self, fn, *inputs, warmup=3):
+        self.inputs = [t.clone() for t in inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # eager warm-up on a side stream: lazy optimizer state, kernel attributes, autotuning
+            for _ in range(warmup):
+                fn(*self.inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(*self.inputs)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def make_sgd(model, lr=0.01):
     return torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4)
 
 
-__all__ = ["supervised_step", "semi_step", "make_sgd", "consistency_weight", "constra_loss", "DiceLoss"]
+__all__ = ["supervised_step", "semi_step", "make_sgd", "GraphedStep", "consistency_weight", "constra_loss", "DiceLoss"]

@@ -119,6 +119,25 @@ def test_fused_ss2d_block_matches_separate_kernels(B, d_model, H, W):
         _close(blk(x), res[1][0], 1e-4, 1e-5, "inference out")
 
 
+def test_large_plane_takes_the_separate_kernels():
+    """A plane too large for the edge kernels' shared memory (80 x 80) still runs on the GPU through CrossScan / CrossMerge and
+    torch's conv / LayerNorm; same result as the reference chain of a smaller-plane-capable block."""
+    from selscan_b200 import ss2d
+    from selscan_b200.vssm import SS2D
+
+    _fp32()
+    torch.manual_seed(3)
+    blk = SS2D(16).cuda()
+    assert not ss2d.fused_supported(blk, 80, 80) and ss2d.fused_supported(blk, 56, 56)
+    x = torch.randn(1, 80, 80, 16, device="cuda", requires_grad=True)
+    out = blk(x)
+    blk.fused = False
+    ref = blk(x)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    out.sum().backward()
+    assert torch.isfinite(x.grad).all()
+
+
 def test_patch_ss2d_installs_forward():
     from selscan_b200.ss2d import forward_b200, forward_core_b200, patch_ss2d
 

@@ -418,7 +418,7 @@ def main():
     if not args.no_e2e:
         from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
 
-        e_steps = max(1, min(args.steps, 2))
+        e_steps = max(1, min(args.steps, 3))
         host = {}
         h2d = d2h = 0
         for name, d_inner, L, calls in stages:
@@ -435,12 +435,24 @@ def main():
         h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         call_list = [name for name, _, _, calls in stages for _ in range(calls)]
 
+        # device-side input staging: two reusable buffer sets per stage shape (no allocator traffic inside the timed region)
+        ring = {name: [{k: torch.empty_like(bufs[name][k]) for k in ("u", "delta", "B", "C", "dout")} for _ in range(2)]
+                for name, _, _, _ in stages}
+        ring_done = {name: [None, None] for name, _, _, _ in stages}
+        ring_next = {name: 0 for name, _, _, _ in stages}
+
         def upload(name):
+            slot = ring_next[name]
+            ring_next[name] = slot ^ 1
             with torch.cuda.stream(h2d_s):
-                dv = {k: v.to(dev, non_blocking=True) for k, v in host[name][0].items()}
+                if ring_done[name][slot] is not None:
+                    h2d_s.wait_event(ring_done[name][slot])      # the call that last computed from this set has finished
+                dv = ring[name][slot]
+                for k, v in host[name][0].items():
+                    dv[k].copy_(v, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(h2d_s)
-            return dv, ev
+            return dv, ev, slot
 
         def e2e_step():
             h2d_s.wait_stream(main)
@@ -448,13 +460,11 @@ def main():
             for i, name in enumerate(call_list):
                 t = bufs[name]
                 hout = host[name][1]
-                dv, ev = nxt
+                dv, ev, slot = nxt
                 if i + 1 < len(call_list):
                     nxt = upload(call_list[i + 1])
                 main.wait_event(ev)
-                for v in dv.values():
-                    v.record_stream(main)
-                u, dl, Bm, Cm = (dv[k].requires_grad_() for k in ("u", "delta", "B", "C"))
+                u, dl, Bm, Cm = (dv[k].detach().requires_grad_() for k in ("u", "delta", "B", "C"))
                 A, Dp, bias = (t[k].detach().clone().requires_grad_() for k in ("A", "D", "bias"))
                 out = selective_scan_fn(u, dl, A, Bm, Cm, Dp, z=None, delta_bias=bias, delta_softplus=True,
                                         return_last_state=False)
@@ -464,6 +474,7 @@ def main():
                         dist.all_reduce(p.grad)
                 done = torch.cuda.Event()
                 done.record(main)
+                ring_done[name][slot] = done
                 d2h_s.wait_event(done)
                 with torch.cuda.stream(d2h_s):
                     for k, src in (("out", out.detach()), ("du", u.grad), ("ddelta", dl.grad), ("dB", Bm.grad), ("dC", Cm.grad),
@@ -472,6 +483,7 @@ def main():
                         src.record_stream(d2h_s)
             main.wait_stream(d2h_s)   # the step ends when its last result is on the host
 
+        e2e_step()
         e2e_step()
         barrier()
         t0 = time.perf_counter()

@@ -62,9 +62,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // hit distinct banks).
 struct InGeom {
   int D, H, W, L, RP, PP, VP, VPP;
-  FastDiv dW, dH, dL, dH2;       // dH2: by ceil(H / 2)
+  FastDiv dW, dH, dL, dH2, dLq;  // dH2: by ceil(H / 2); dLq: by L / 4
   int64_t pitch;
   int vec;                        // channels-last rows can be moved as float4
+  int vec4;                       // scan-order rows can be moved as float4 (H, W, pitch multiples of 4, aligned base)
 };
 
 template <int kCT>
@@ -214,50 +215,109 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
   load_planes<kCT>(X, x + (int64_t)b * L * ld + c0, ld, c0, g);
   const int nvalid = (D - c0 < kCT ? D - c0 : kCT) * L;
   const int64_t dir2 = 2 * (int64_t)D * g.pitch;
-  for (int i0 = threadIdx.x; i0 < nvalid; i0 += nthr * 4) {   // CrossScan backward, row-major pair
-    float v[4];
+  if (g.vec4) {
+    // CrossScan backward with 16-byte loads: a thread takes 4 consecutive positions of an order and of its reverse
+    const int Lq = L >> 2, nq = nvalid >> 2;
+    for (int q0 = threadIdx.x; q0 < nq; q0 += nthr * 2) {         // row-major pair
+      float4 a[2], r[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * nthr;
-      if (i < nvalid) {
-        const int c = fdiv(i, g.dL), p = i - c * L;
-        const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
-        v[u] = __ldg(g0 + p) + __ldg(g0 + dir2 + (L - 1 - p));
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + u * nthr;
+        if (q < nq) {
+          const int c = fdiv(q, g.dLq), p = (q - c * Lq) << 2;
+          const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
+          a[u] = __ldg(reinterpret_cast<const float4*>(g0 + p));
+          r[u] = __ldg(reinterpret_cast<const float4*>(g0 + dir2 + (L - 4 - p)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + u * nthr;
+        if (q < nq) {
+          const int c = fdiv(q, g.dLq), p = (q - c * Lq) << 2;
+          const int h = fdiv(p, g.dW), w = p - h * W;
+          float* d = G + c * PP + (h + 1) * RP + (w + 1);
+          d[0] = a[u].x + r[u].w;
+          d[1] = a[u].y + r[u].z;
+          d[2] = a[u].z + r[u].y;
+          d[3] = a[u].w + r[u].x;
+        }
       }
     }
+    __syncthreads();
+    for (int q0 = threadIdx.x; q0 < nq; q0 += nthr * 2) {         // column-major pair: 4 consecutive rows of one column
+      float4 a[2], r[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * nthr;
-      if (i < nvalid) {
-        const int c = fdiv(i, g.dL), p = i - c * L;
-        const int h = fdiv(p, g.dW), w = p - h * W;
-        G[c * PP + (h + 1) * RP + (w + 1)] = v[u];
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + u * nthr;
+        if (q < nq) {
+          const int c = fdiv(q, g.dLq), p = (q - c * Lq) << 2;
+          const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
+          a[u] = __ldg(reinterpret_cast<const float4*>(g1 + p));
+          r[u] = __ldg(reinterpret_cast<const float4*>(g1 + dir2 + (L - 4 - p)));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = q0 + u * nthr;
+        if (q < nq) {
+          const int c = fdiv(q, g.dLq), p = (q - c * Lq) << 2;
+          const int w = fdiv(p, g.dH), h = p - w * H;
+          float* d = G + c * PP + (h + 1) * RP + (w + 1);
+          d[0] += a[u].x + r[u].w;
+          d[RP] += a[u].y + r[u].z;
+          d[2 * RP] += a[u].z + r[u].y;
+          d[3 * RP] += a[u].w + r[u].x;
+        }
       }
     }
+    __syncthreads();
+  } else {
+    for (int i0 = threadIdx.x; i0 < nvalid; i0 += nthr * 4) {   // CrossScan backward, row-major pair
+      float v[4];
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        if (i < nvalid) {
+          const int c = fdiv(i, g.dL), p = i - c * L;
+          const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
+          v[u] = __ldg(g0 + p) + __ldg(g0 + dir2 + (L - 1 - p));
+        }
+      }
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        if (i < nvalid) {
+          const int c = fdiv(i, g.dL), p = i - c * L;
+          const int h = fdiv(p, g.dW), w = p - h * W;
+          G[c * PP + (h + 1) * RP + (w + 1)] = v[u];
+        }
+      }
+    }
+    __syncthreads();
+    for (int i0 = threadIdx.x; i0 < nvalid; i0 += nthr * 4) {   // column-major pair
+      float v[4];
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        if (i < nvalid) {
+          const int c = fdiv(i, g.dL), p = i - c * L;
+          const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
+          v[u] = __ldg(g1 + p) + __ldg(g1 + dir2 + (L - 1 - p));
+        }
+      }
+  #pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        if (i < nvalid) {
+          const int c = fdiv(i, g.dL), p = i - c * L;
+          const int w = fdiv(p, g.dH), h = p - w * H;
+          G[c * PP + (h + 1) * RP + (w + 1)] += v[u];
+        }
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i0 = threadIdx.x; i0 < nvalid; i0 += nthr * 4) {   // column-major pair
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * nthr;
-      if (i < nvalid) {
-        const int c = fdiv(i, g.dL), p = i - c * L;
-        const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
-        v[u] = __ldg(g1 + p) + __ldg(g1 + dir2 + (L - 1 - p));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * nthr;
-      if (i < nvalid) {
-        const int c = fdiv(i, g.dL), p = i - c * L;
-        const int w = fdiv(p, g.dH), h = p - w * H;
-        G[c * PP + (h + 1) * RP + (w + 1)] += v[u];
-      }
-    }
-  }
-  __syncthreads();
   {  // d(pre-activation) in place, conv weight / bias partial sums; a warp stays on one channel at a time
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = warp % wpc;
@@ -640,7 +700,9 @@ InPlan plan_in(int D, int H, int W, int64_t pitch, bool bwd) {
   g.VP = W | 1;
   g.VPP = H * g.VP;
   g.dW = make_fastdiv(W); g.dH = make_fastdiv(H); g.dL = make_fastdiv(H * W); g.dH2 = make_fastdiv((H + 1) / 2);
+  g.dLq = make_fastdiv(H * W / 4 > 0 ? H * W / 4 : 1);
   g.vec = 0;
+  g.vec4 = 0;
   for (p.ct = 8;; p.ct = 4) {
     const int want = 32 / p.ct;
     int pp = (H + 2) * g.RP;
@@ -723,6 +785,7 @@ cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, con
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   InPlan p = plan_in(D, H, W, pitch, true);
   p.g.vec = al16(x) && ld % 4 == 0;
+  p.g.vec4 = al16(dxs) && H % 4 == 0 && W % 4 == 0 && pitch % 4 == 0;
   const unsigned grid = (unsigned)((int64_t)B * ((D + p.ct - 1) / p.ct));
   cudaError_t e;
   if (p.ct == 8) {

@@ -57,6 +57,30 @@ def test_mambaunet_train_step_runs_and_is_finite():
     assert sum(p.grad is not None for p in model.parameters()) == len(list(model.parameters()))
 
 
+def test_training_step_captured_as_cuda_graph_matches_eager():
+    """workloads.GraphedStep: every kernel of the step (TMA descriptors included) must be capturable, and the replayed
+    step must produce the same losses as the eager step on an identical copy of the model."""
+    import copy
+
+    from selscan_b200 import workloads as wl
+    from selscan_b200.vssm import DiceLoss, MambaUnet
+
+    torch.manual_seed(0)
+    m1 = MambaUnet(num_classes=4, depths=(1, 1, 1, 1), dims=(32, 64, 128, 256), drop_path_rate=0.0).cuda().train()
+    m2 = copy.deepcopy(m1)
+    o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
+    dice = DiceLoss(4)
+    x = torch.rand(2, 1, 64, 64, device="cuda")
+    y = torch.randint(0, 4, (2, 64, 64), device="cuda")
+    g = wl.GraphedStep(lambda a, b: wl.supervised_step(m1, o1, dice, a, b), x, y, warmup=2)
+    for _ in range(2):
+        wl.supervised_step(m2, o2, dice, x, y)
+    for _ in range(3):
+        lg = float(g(x, y).detach())
+        le = float(wl.supervised_step(m2, o2, dice, x, y).detach())
+        assert abs(lg - le) <= 1e-5 * max(1.0, abs(le)), (lg, le)
+
+
 @pytest.mark.parametrize("B,D,H,W", [(2, 5, 7, 7), (1, 3, 4, 9), (2, 8, 56, 56), (3, 4, 14, 14)])
 def test_cross_scan_merge_kernels(B, D, H, W):
     """The plane kernels against the plain-torch statement of CrossScan / CrossMerge, forward and backward (bit-exact:

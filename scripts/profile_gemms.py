@@ -8,6 +8,9 @@ from selscan_b200 import workloads as wl
 from selscan_b200.vssm import DiceLoss, MambaUnet
 
 dev = torch.device("cuda")
+if os.environ.get("BLAS"):
+    torch.backends.cuda.preferred_blas_library(os.environ["BLAS"])
+    print("blas:", torch.backends.cuda.preferred_blas_library())
 torch.manual_seed(0)
 model = MambaUnet(num_classes=4).to(dev).train()
 opt = wl.make_sgd(model)

@@ -167,6 +167,17 @@ int selscan_b200_layernorm_fwd(const float* x, const float* weight, const float*
 int selscan_b200_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* weight, float* dx,
                                float* dwb_part, int64_t rows, int32_t dim, void* stream);
 
+/* fp32 GEMM on the tcgen05 tensor cores with the 3xTF32 split (a = a_hi + a_lo in TF32; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with
+ * fp32 accumulation): agrees with an fp32 SIMT GEMM to ~1e-6 relative.  OPT-IN replacement for the cuBLAS fp32 GEMMs around the
+ * scan (SS2D.in_proj / out_proj / x_proj, code/networks/mamba_sys.py:299,336,406) and their dgrad / wgrad forms.
+ *   C[b] (M x N, row stride ldc) (+)= A[b] (M x K) * B[b] (N x K)^T          b = 0 .. batch-1, strides strideA/B/C floats
+ *   A: a_mn_major = 0: stored [M][K] (row stride lda, K contiguous); 1: stored [K][M] (row stride lda, M contiguous)
+ *   B: b_mn_major = 0: stored [N][K];                                1: stored [K][N]
+ *   accumulate = 1: C += ...   A, B 16-byte aligned, lda / ldb / batch strides multiples of 4 floats (TMA). */
+int selscan_b200_gemm_3xtf32(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb, int32_t b_mn_major,
+                             float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t batch, int64_t strideA,
+                             int64_t strideB, int64_t strideC, int32_t accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,289 @@
+// fp32 GEMM on the 5th-generation tensor cores (tcgen05 / TMEM / TMA, sm_100a) with the 3xTF32 split:
+//   C (M x N) (+)= A (M x K) * B (N x K)^T,   a = a_hi + a_lo,  a_hi = tf32(a),  a_lo = a - a_hi (exact),
+//   a * b ~= a_lo * b_hi + a_hi * b_lo + a_hi * b_hi   (the dropped a_lo * b_lo term is 2^-22 relative), fp32 accumulation in TMEM.
+// This is the arithmetic cuBLAS does NOT offer for fp32 (its tensor-core mode is a single TF32 product, 2^-11 relative): the
+// result agrees with an fp32 SIMT GEMM to ~1e-6 relative, at several times its speed.  Used, opt-in, for the GEMMs around the
+// scan (SS2D.in_proj / out_proj / x_proj: code/networks/mamba_sys.py:299,336,406) and their dgrad / wgrad forms.
+//
+// Both operands may be stored K-major (row = M or N index, K contiguous) or MN-major (row = K index, M or N contiguous), so
+// that y = x W^T, dx = dy W and dW = dy^T x all run without a transpose pass.
+//
+// CTA = one 128 x BN tile of C (BN <= 128, multiple of 16), 6 warps:
+//   warp 0      TMA producer: 128-byte-swizzled boxes of 32 k per stage into a 3-stage ring (OOB rows / k are zero fill)
+//   warps 2-5   split a stage in place into hi (tf32-exact) and lo tiles (generic proxy -> fence.proxy.async), later the epilogue
+//   warp 1      one lane issues 12 tcgen05.mma.kind::tf32 per stage (4 k-steps x 3 products), commits to the stage's empty barrier
+//   epilogue    tcgen05.ld 32 lanes x 16 columns per warp and instruction -> global stores (or atomics for split-K)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "selscan_kernels.h"
+#include "selscan_ptx.cuh"
+#include "selscan_tma_host.h"
+
+namespace selscan {
+
+namespace {
+
+constexpr int kBM = 128;                 // UMMA M
+constexpr int kBK = 32;                  // k per stage: 128 bytes of fp32 = one swizzle row
+constexpr int kBNMax = 128;
+constexpr int kTcStages = 3;
+constexpr int kTcThreads = 192;
+constexpr int kTileBytes = kBM * kBK * 4;     // 16 KB: the A tile, and the largest B tile
+
+struct TcParams {
+  int M, N, K, BN;
+  int a_mn, b_mn;                         // operand storage: 0 = K-major, 1 = MN-major
+  int kb_total, kb_per_split, splits;     // k-blocks of kBK
+  int mode;                               // 0: C = , 1: C += (this CTA owns the tile), 2: atomicAdd (split-K)
+  float* C;
+  int64_t ldc, strideC;
+  uint32_t idesc;
+};
+
+struct TcSmem {
+  float a_hi[kTcStages][kBM * kBK];
+  float a_lo[kTcStages][kBM * kBK];
+  float b_hi[kTcStages][kBNMax * kBK];
+  float b_lo[kTcStages][kBNMax * kBK];
+  u64 full[kTcStages], split[kTcStages], empty[kTcStages], accum;
+  uint32_t tmem_base;
+};
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), Blackwell version bits.
+// layout 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only layout tcgen05 accepts for MN-major tf32 operands)
+__device__ __forceinline__ u64 smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (u64)((addr & 0x3FFFF) >> 4) | ((u64)(lbo_bytes >> 4) << 16) | ((u64)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((u64)layout << 61);
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, u64 da, u64 db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * p.BN;
+  const int bz = blockIdx.z / p.splits, split = blockIdx.z - bz * p.splits;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+  const int n_kb = kb_end - kb_begin;
+  const int b_chunks = (p.BN + 31) / 32;
+  const uint32_t b_bytes = p.b_mn ? (uint32_t)b_chunks * 4096u : (uint32_t)p.BN * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(smem_u32(&sm.full[s]), 1);
+      mbar_init(smem_u32(&sm.split[s]), 4);     // lane 0 of each of the four split warps
+      mbar_init(smem_u32(&sm.empty[s]), 1);     // tcgen05.commit
+    }
+    mbar_init(smem_u32(&sm.accum), 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {                                // TMEM: 128 lanes x 128 fp32 columns for the accumulator tile
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(kBNMax) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % kTcStages, k = i / kTcStages;
+        if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
+        const uint32_t full = smem_u32(&sm.full[s]);
+        const int k0 = (kb_begin + i) * kBK;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)kTileBytes + b_bytes) : "memory");
+        if (p.a_mn) {
+#pragma unroll
+          for (int c = 0; c < kBM / 32; ++c) tma_load_3d(smem_u32(sm.a_hi[s]) + c * 4096, &map_a, m0 + 32 * c, k0, bz, full);
+        } else {
+          tma_load_3d(smem_u32(sm.a_hi[s]), &map_a, k0, m0, bz, full);
+        }
+        if (p.b_mn) {
+          for (int c = 0; c < b_chunks; ++c) tma_load_3d(smem_u32(sm.b_hi[s]) + c * 4096, &map_b, n0 + 32 * c, k0, bz, full);
+        } else {
+          tma_load_3d(smem_u32(sm.b_hi[s]), &map_b, k0, n0, bz, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % kTcStages, k = i / kTcStages;
+      mbar_wait(smem_u32(&sm.split[s]), k & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        // K-major (128B swizzle): atoms of 8 rows x 128 B (SBO 1024); a k-step of 8 is 32 B inside the swizzled row.
+        // MN-major (128B swizzle on a 32 B base): [chunk of 32 mn][k][32 mn], atoms of 4 k x 128 B: LBO 4096 between
+        // chunks, SBO 512 between groups of 4 k; a k-step of 8 is 1024 B.
+        const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
+        const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+        const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
+        const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
+#pragma unroll
+        for (int ks = 0; ks < kBK / 8; ++ks) {
+          const u64 ah = smem_desc(smem_u32(sm.a_hi[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
+          const u64 al = smem_desc(smem_u32(sm.a_lo[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
+          const u64 bh = smem_desc(smem_u32(sm.b_hi[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
+          const u64 bl = smem_desc(smem_u32(sm.b_lo[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
+          tc_mma(tmem, al, bh, p.idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          tc_mma(tmem, ah, bl, p.idesc, 1u);
+          tc_mma(tmem, ah, bh, p.idesc, 1u);
+        }
+        tc_commit(smem_u32(&sm.empty[s]));        // the stage may be refilled once these MMAs have read it
+        if (i + 1 == n_kb) tc_commit(smem_u32(&sm.accum));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ split warps, then epilogue ---------------------------------
+    const int t = threadIdx.x - 64;               // 0..127
+    const int b_vec = (int)(b_bytes >> 4);
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % kTcStages, k = i / kTcStages;
+      mbar_wait(smem_u32(&sm.full[s]), k & 1);
+      float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
+      float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
+      float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
+      float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
+      auto split4 = [](float4* hi, float4* lo, int j) {       // hi = tf32(x) round-to-nearest, lo = tf32(x - hi): both exact operands
+        float4 v = hi[j], h, l;
+        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+        hi[j] = h;
+        lo[j] = l;
+      };
+#pragma unroll
+      for (int j = 0; j < kTileBytes / 16 / 128; ++j) split4(ah, al, t + 128 * j);
+      for (int j = t; j < b_vec; j += 128) split4(bh, bl, j);
+      fence_proxy_async_smem();                   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.split[s]));
+    }
+    // epilogue: TMEM lane = tile row; a warp may only touch lanes 32 * (warp % 4) .. + 31
+    mbar_wait(smem_u32(&sm.accum), 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane, m = m0 + row;
+    float* crow = p.C + (int64_t)bz * p.strideC + (int64_t)m * p.ldc + n0;
+    const bool vec_ok = (p.ldc % 4 == 0) && (n0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.strideC % 4 == 0);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < p.M) {
+        if (p.mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < p.N) atomicAdd(crow + c0 + j, __uint_as_float(r[j]));
+        } else if (vec_ok && n0 + c0 + 16 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
+            if (p.mode == 1) {
+              const float4 o = *dst;
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *dst = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < p.N) crow[c0 + j] = (p.mode == 1 ? crow[c0 + j] : 0.f) + __uint_as_float(r[j]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kBNMax) : "memory");
+  }
+}
+
+}  // namespace
+
+bool tcgemm_operand_ok(const float* p, int64_t ld, int64_t batch_stride, int batch) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ld % 4 == 0 && ld > 0 && (batch <= 1 || batch_stride % 4 == 0);
+}
+
+// C (M x N) (+)= A (M x K) * B (N x K)^T; see selscan_b200_gemm_3xtf32 in include/selscan_b200.h
+cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* C, int64_t ldc, int M,
+                          int N, int K, int batch, int64_t strideA, int64_t strideB, int64_t strideC, int accumulate,
+                          cudaStream_t stream) {
+  if (M == 0 || N == 0 || batch == 0) return cudaSuccess;
+  TcParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  p.C = C; p.ldc = ldc; p.strideC = strideC;
+  // tile width: the smallest multiple of 16 that covers N in the fewest tiles of at most 128
+  const int n_tiles = (N + kBNMax - 1) / kBNMax;
+  p.BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  const int m_tiles = (M + kBM - 1) / kBM;
+  p.kb_total = (K + kBK - 1) / kBK;
+  if (p.kb_total == 0) p.kb_total = 1;
+  // split K when the tiles alone cannot fill the GPU and the reduction is long (weight gradients: K = batch * L)
+  int splits = 1;
+  const int64_t ctas = (int64_t)m_tiles * n_tiles * batch;
+  if (ctas < 148 && p.kb_total >= 16) {
+    splits = (int)((2 * 148 + ctas - 1) / ctas);
+    if (splits > p.kb_total / 4) splits = p.kb_total / 4;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.mode = p.splits > 1 ? 2 : (accumulate ? 1 : 0);
+  p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
+            ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  CUtensorMap ma, mb;
+  // K-major: rows = M (or N), inner = K; MN-major: rows = K, inner = M (or N).  Boxes are 32 floats (128 B, swizzled) wide.
+  const bool ok_a = a_mn ? make_row_map_sw(&ma, A, M, K, batch, lda, strideA, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                         : make_row_map_sw(&ma, A, K, M, batch, lda, strideA, 32, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  const bool ok_b = b_mn ? make_row_map_sw(&mb, B, N, K, batch, ldb, strideB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                         : make_row_map_sw(&mb, B, K, N, batch, ldb, strideB, 32, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!ok_a || !ok_b) return cudaErrorInvalidValue;
+  if (p.mode == 2 && !accumulate) {               // split-K accumulates with atomics: start from zero
+    for (int b = 0; b < batch; ++b) {
+      const cudaError_t e = cudaMemset2DAsync(C + (int64_t)b * strideC, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tcgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)(batch * p.splits));
+  tcgemm_3xtf32_kernel<<<grid, kTcThreads, smem, stream>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+}  // namespace selscan

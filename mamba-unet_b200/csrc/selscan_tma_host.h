@@ -36,6 +36,19 @@ inline bool make_row_map(CUtensorMap* map, const float* base, int seqlen, int di
   return r == CUDA_SUCCESS;
 }
 
+// same, with an explicit swizzle mode
+inline bool make_row_map_sw(CUtensorMap* map, const float* base, int inner, int rows, int batch, int64_t row_stride, int64_t batch_stride,
+                            int box_inner, int box_rows, CUtensorMapSwizzle sw) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+  const cuuint64_t gstr[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)(batch > 1 ? batch_stride : (int64_t)rows * row_stride) * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline bool tma_row_ok(const void* base, int64_t d_stride, int64_t batch_stride) {
   return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (d_stride & 3) == 0 && (batch_stride & 3) == 0 && d_stride > 0;
 }

@@ -255,8 +255,9 @@ SELSCAN_EXPORT int selscan_b200_gemm_3xtf32(const float* A, int64_t lda, int32_t
   const char* who = "selscan_b200_gemm_3xtf32";
   if (!A || !B || !C) return fail("%s: A, B, C must not be NULL", who);
   if (M < 0 || N < 0 || K < 0 || batch < 0) return fail("%s: bad sizes M=%d N=%d K=%d batch=%d", who, M, N, K, batch);
-  if (!selscan::tcgemm_operand_ok(A, lda, strideA, batch) || !selscan::tcgemm_operand_ok(B, ldb, strideB, batch))
-    return fail("%s: A and B must be 16-byte aligned with row / batch strides that are multiples of 4 floats", who);
+  if (!selscan::tcgemm_operand_ok(A, lda, strideA, batch) || !selscan::tcgemm_operand_ok(B, ldb, strideB, batch) ||
+      !selscan::tcgemm_operand_ok(C, ldc, strideC, batch))
+    return fail("%s: A, B and C must be 16-byte aligned with row / batch strides that are multiples of 4 floats", who);
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
     return fail("%s: a leading dimension is smaller than the row it strides over", who);
   return edge_done(who, selscan::launch_tcgemm(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, batch, strideA, strideB, strideC,

@@ -8,11 +8,13 @@
 // Both operands may be stored K-major (row = M or N index, K contiguous) or MN-major (row = K index, M or N contiguous), so
 // that y = x W^T, dx = dy W and dW = dy^T x all run without a transpose pass.
 //
-// CTA = one 128 x BN tile of C (BN <= 128, multiple of 16), 6 warps:
+// Persistent CTAs (one per SM) walk the 128 x BN tiles of C (BN <= 128); 10 warps, every hand-over is an mbarrier:
 //   warp 0      TMA producer: 128-byte-swizzled boxes of 32 k per stage into a 3-stage ring (OOB rows / k are zero fill)
-//   warps 2-5   split a stage in place into hi (tf32-exact) and lo tiles (generic proxy -> fence.proxy.async), later the epilogue
-//   warp 1      one lane issues 12 tcgen05.mma.kind::tf32 per stage (4 k-steps x 3 products), commits to the stage's empty barrier
-//   epilogue    tcgen05.ld 32 lanes x 16 columns per warp and instruction -> global stores (or atomics for split-K)
+//   warps 2-5   split a stage in place into hi (tf32-exact) and lo tiles (generic proxy -> fence.proxy.async)
+//   warp 1      one lane issues 12 tcgen05.mma.kind::tf32 per stage (4 k-steps x 3 products) into one of TWO TMEM
+//               accumulators, commits to the stage's empty barrier and, after a tile's last k-block, to acc_full
+//   warps 6-9   epilogue of tile j while tile j+1 is being multiplied: tcgen05.ld 32 lanes x 32 columns -> swizzled staging
+//               tile -> TMA store, or TMA reduce-add for C += and for split-K (weight gradients: K = batch * L)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,16 +30,15 @@ constexpr int kBM = 128;                 // UMMA M
 constexpr int kBK = 32;                  // k per stage: 128 bytes of fp32 = one swizzle row
 constexpr int kBNMax = 128;
 constexpr int kTcStages = 3;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 constexpr int kTileBytes = kBM * kBK * 4;     // 16 KB: the A tile, and the largest B tile
 
 struct TcParams {
   int M, N, K, BN;
   int a_mn, b_mn;                         // operand storage: 0 = K-major, 1 = MN-major
+  int m_tiles, n_tiles, batch;
   int kb_total, kb_per_split, splits;     // k-blocks of kBK
-  int mode;                               // 0: C = , 1: C += (this CTA owns the tile), 2: atomicAdd (split-K)
-  float* C;
-  int64_t ldc, strideC;
+  int reduce;                             // 0: C = tile (TMA store), 1: C += tile (TMA reduce-add: accumulate and / or split-K)
   uint32_t idesc;
 };
 
@@ -46,7 +47,8 @@ struct TcSmem {
   float a_lo[kTcStages][kBM * kBK];
   float b_hi[kTcStages][kBNMax * kBK];
   float b_lo[kTcStages][kBNMax * kBK];
-  u64 full[kTcStages], split[kTcStages], empty[kTcStages], accum;
+  float out[4][2][32 * 32];               // per epilogue warp: two 32 x 32 staging tiles for the TMA stores
+  u64 full[kTcStages], split[kTcStages], empty[kTcStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
@@ -74,33 +76,59 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// work item w (n tile fastest, so that CTAs running side by side share the A tile in L2) -> tile coordinates
+struct TcTile {
+  int m0, n0, bz, kb_begin, n_kb;
+};
+__device__ __forceinline__ TcTile tc_tile(const TcParams& p, int w) {
+  TcTile t;
+  const int nt = w % p.n_tiles;
+  w /= p.n_tiles;
+  const int split = w % p.splits;
+  w /= p.splits;
+  const int mt = w % p.m_tiles;
+  t.bz = w / p.m_tiles;
+  t.m0 = mt * kBM;
+  t.n0 = nt * p.BN;
+  t.kb_begin = split * p.kb_per_split;
+  t.n_kb = min(p.kb_total, t.kb_begin + p.kb_per_split) - t.kb_begin;
+  return t;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * p.BN;
-  const int bz = blockIdx.z / p.splits, split = blockIdx.z - bz * p.splits;
-  const int kb_begin = split * p.kb_per_split;
-  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
-  const int n_kb = kb_end - kb_begin;
+  const int n_work = p.m_tiles * p.n_tiles * p.batch * p.splits;
   const int b_chunks = (p.BN + 31) / 32;
   const uint32_t b_bytes = p.b_mn ? (uint32_t)b_chunks * 4096u : (uint32_t)p.BN * 128u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(smem_u32(&sm.full[s]), 1);
-      mbar_init(smem_u32(&sm.split[s]), 4);     // lane 0 of each of the four split warps
-      mbar_init(smem_u32(&sm.empty[s]), 1);     // tcgen05.commit
+      mbar_init(smem_u32(&sm.split[s]), 4);       // lane 0 of each of the four split warps
+      mbar_init(smem_u32(&sm.empty[s]), 1);       // tcgen05.commit
     }
-    mbar_init(smem_u32(&sm.accum), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&sm.acc_full[a]), 1);    // tcgen05.commit after a tile's last k-block
+      mbar_init(smem_u32(&sm.acc_empty[a]), 4);   // lane 0 of each epilogue warp once its TMEM reads are done
+    }
     mbar_fence_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_c);
   }
-  if (warp == 1) {                                // TMEM: 128 lanes x 128 fp32 columns for the accumulator tile
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(kBNMax) : "memory");
+  if (warp == 1) {                                // TMEM: two accumulator tiles of 128 lanes x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(2 * kBNMax) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -111,123 +139,145 @@ tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
     if (lane == 0) {
-      for (int i = 0; i < n_kb; ++i) {
-        const int s = i % kTcStages, k = i / kTcStages;
-        if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
-        const uint32_t full = smem_u32(&sm.full[s]);
-        const int k0 = (kb_begin + i) * kBK;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)kTileBytes + b_bytes) : "memory");
-        if (p.a_mn) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const TcTile t = tc_tile(p, w);
+        for (int i = 0; i < t.n_kb; ++i, ++it) {
+          const int s = it % kTcStages, k = it / kTcStages;
+          if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
+          const uint32_t full = smem_u32(&sm.full[s]);
+          const int k0 = (t.kb_begin + i) * kBK;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)kTileBytes + b_bytes) : "memory");
+          if (p.a_mn) {
 #pragma unroll
-          for (int c = 0; c < kBM / 32; ++c) tma_load_3d(smem_u32(sm.a_hi[s]) + c * 4096, &map_a, m0 + 32 * c, k0, bz, full);
-        } else {
-          tma_load_3d(smem_u32(sm.a_hi[s]), &map_a, k0, m0, bz, full);
-        }
-        if (p.b_mn) {
-          for (int c = 0; c < b_chunks; ++c) tma_load_3d(smem_u32(sm.b_hi[s]) + c * 4096, &map_b, n0 + 32 * c, k0, bz, full);
-        } else {
-          tma_load_3d(smem_u32(sm.b_hi[s]), &map_b, k0, n0, bz, full);
+            for (int c = 0; c < kBM / 32; ++c) tma_load_3d(smem_u32(sm.a_hi[s]) + c * 4096, &map_a, t.m0 + 32 * c, k0, t.bz, full);
+          } else {
+            tma_load_3d(smem_u32(sm.a_hi[s]), &map_a, k0, t.m0, t.bz, full);
+          }
+          if (p.b_mn) {
+            for (int c = 0; c < b_chunks; ++c) tma_load_3d(smem_u32(sm.b_hi[s]) + c * 4096, &map_b, t.n0 + 32 * c, k0, t.bz, full);
+          } else {
+            tma_load_3d(smem_u32(sm.b_hi[s]), &map_b, k0, t.n0, t.bz, full);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
-    for (int i = 0; i < n_kb; ++i) {
-      const int s = i % kTcStages, k = i / kTcStages;
-      mbar_wait(smem_u32(&sm.split[s]), k & 1);
+    // K-major (128B swizzle): atoms of 8 rows x 128 B (SBO 1024); a k-step of 8 is 32 B inside the swizzled row.
+    // MN-major (128B swizzle on a 32 B base): [chunk of 32 mn][k][32 mn], atoms of 4 k x 128 B: LBO 4096 between
+    // chunks, SBO 512 between groups of 4 k; a k-step of 8 is 1024 B.
+    const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
+    const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
+    const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
+    const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
+    int it = 0, j = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++j) {
+      const TcTile t = tc_tile(p, w);
+      const int ab = j & 1, use = j >> 1;
+      if (use > 0) mbar_wait(smem_u32(&sm.acc_empty[ab]), (use - 1) & 1);   // the epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        // K-major (128B swizzle): atoms of 8 rows x 128 B (SBO 1024); a k-step of 8 is 32 B inside the swizzled row.
-        // MN-major (128B swizzle on a 32 B base): [chunk of 32 mn][k][32 mn], atoms of 4 k x 128 B: LBO 4096 between
-        // chunks, SBO 512 between groups of 4 k; a k-step of 8 is 1024 B.
-        const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
-        const uint32_t a_lbo = p.a_mn ? 4096u : 16u, b_lbo = p.b_mn ? 4096u : 16u;
-        const uint32_t a_sbo = p.a_mn ? 512u : 1024u, b_sbo = p.b_mn ? 512u : 1024u;
-        const uint32_t a_lt = p.a_mn ? 1u : 2u, b_lt = p.b_mn ? 1u : 2u;
+      const uint32_t acc = tmem + (uint32_t)ab * kBNMax;
+      for (int i = 0; i < t.n_kb; ++i, ++it) {
+        const int s = it % kTcStages, k = it / kTcStages;
+        mbar_wait(smem_u32(&sm.split[s]), k & 1);
+        tc_fence_after();
+        if (lane == 0) {
 #pragma unroll
-        for (int ks = 0; ks < kBK / 8; ++ks) {
-          const u64 ah = smem_desc(smem_u32(sm.a_hi[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
-          const u64 al = smem_desc(smem_u32(sm.a_lo[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
-          const u64 bh = smem_desc(smem_u32(sm.b_hi[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
-          const u64 bl = smem_desc(smem_u32(sm.b_lo[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
-          tc_mma(tmem, al, bh, p.idesc, (i > 0 || ks > 0) ? 1u : 0u);
-          tc_mma(tmem, ah, bl, p.idesc, 1u);
-          tc_mma(tmem, ah, bh, p.idesc, 1u);
+          for (int ks = 0; ks < kBK / 8; ++ks) {
+            const u64 ah = smem_desc(smem_u32(sm.a_hi[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
+            const u64 al = smem_desc(smem_u32(sm.a_lo[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
+            const u64 bh = smem_desc(smem_u32(sm.b_hi[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
+            const u64 bl = smem_desc(smem_u32(sm.b_lo[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
+            tc_mma(acc, al, bh, p.idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            tc_mma(acc, ah, bl, p.idesc, 1u);
+            tc_mma(acc, ah, bh, p.idesc, 1u);
+          }
+          tc_commit(smem_u32(&sm.empty[s]));      // the stage may be refilled once these MMAs have read it
+          if (i + 1 == t.n_kb) tc_commit(smem_u32(&sm.acc_full[ab]));
         }
-        tc_commit(smem_u32(&sm.empty[s]));        // the stage may be refilled once these MMAs have read it
-        if (i + 1 == n_kb) tc_commit(smem_u32(&sm.accum));
+        __syncwarp();
       }
-      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------ split warps -------------------------------------------------
+    const int tix = threadIdx.x - 64;             // 0..127
+    const int b_vec = (int)(b_bytes >> 4);
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const TcTile t = tc_tile(p, w);
+      for (int i = 0; i < t.n_kb; ++i, ++it) {
+        const int s = it % kTcStages, k = it / kTcStages;
+        mbar_wait(smem_u32(&sm.full[s]), k & 1);
+        float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
+        float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
+        float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
+        float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
+        auto split4 = [](float4* hi, float4* lo, int q) {   // hi = tf32(x) round-to-nearest, lo = tf32(x - hi): both exact operands
+          float4 v = hi[q], h, l;
+          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+          hi[q] = h;
+          lo[q] = l;
+        };
+#pragma unroll
+        for (int q = 0; q < kTileBytes / 16 / 128; ++q) split4(ah, al, tix + 128 * q);
+        for (int q = tix; q < b_vec; q += 128) split4(bh, bl, q);
+        fence_proxy_async_smem();                 // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.split[s]));
+      }
     }
   } else {
-    // ------------------------------------------------ split warps, then epilogue ---------------------------------
-    const int t = threadIdx.x - 64;               // 0..127
-    const int b_vec = (int)(b_bytes >> 4);
-    for (int i = 0; i < n_kb; ++i) {
-      const int s = i % kTcStages, k = i / kTcStages;
-      mbar_wait(smem_u32(&sm.full[s]), k & 1);
-      float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
-      float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
-      float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
-      float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
-      auto split4 = [](float4* hi, float4* lo, int j) {       // hi = tf32(x) round-to-nearest, lo = tf32(x - hi): both exact operands
-        float4 v = hi[j], h, l;
-        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-        l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-        hi[j] = h;
-        lo[j] = l;
-      };
-#pragma unroll
-      for (int j = 0; j < kTileBytes / 16 / 128; ++j) split4(ah, al, t + 128 * j);
-      for (int j = t; j < b_vec; j += 128) split4(bh, bl, j);
-      fence_proxy_async_smem();                   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sm.split[s]));
-    }
-    // epilogue: TMEM lane = tile row; a warp may only touch lanes 32 * (warp % 4) .. + 31
-    mbar_wait(smem_u32(&sm.accum), 0);
-    tc_fence_after();
+    // ------------------------------------------------ epilogue warps ----------------------------------------------
+    // TMEM lane = tile row; a warp may only touch lanes 32 * (warp % 4) .. + 31.  32 x 32 chunks go through a swizzled
+    // staging tile and leave as TMA stores (or reduce-adds), clipped at the edges of C by the tensor map.
     const int q = warp & 3;
-    const int row = q * 32 + lane, m = m0 + row;
-    float* crow = p.C + (int64_t)bz * p.strideC + (int64_t)m * p.ldc + n0;
-    const bool vec_ok = (p.ldc % 4 == 0) && (n0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.strideC % 4 == 0);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < p.M) {
-        if (p.mode == 2) {
+    int j = 0, n_store = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++j) {
+      const TcTile t = tc_tile(p, w);
+      const int ab = j & 1, use = j >> 1;
+      mbar_wait(smem_u32(&sm.acc_full[ab]), use & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem + (uint32_t)ab * kBNMax + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 32, ++n_store) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+            "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(acc + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (lane == 0) tma_store_wait_read<1>();  // the staging tile used two stores ago has been read
+        __syncwarp();
+        const uint32_t stage = smem_u32(sm.out[q][n_store & 1]);
+        const uint32_t rowp = stage + (uint32_t)lane * 128;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < p.N) atomicAdd(crow + c0 + j, __uint_as_float(r[j]));
-        } else if (vec_ok && n0 + c0 + 16 <= p.N) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
-            if (p.mode == 1) {
-              const float4 o = *dst;
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            *dst = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < p.N) crow[c0 + j] = (p.mode == 1 ? crow[c0 + j] : 0.f) + __uint_as_float(r[j]);
+        for (int c = 0; c < 8; ++c)               // 128-byte swizzle of the C tensor map: 16-byte chunk c of row r sits at c ^ (r & 7)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (uint32_t)((c ^ (lane & 7)) << 4)), "r"(r[4 * c]),
+                       "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.reduce) tma_reduce_add_3d(&map_c, stage, t.n0 + c0, t.m0 + q * 32, t.bz);
+          else tma_store_3d(&map_c, stage, t.n0 + c0, t.m0 + q * 32, t.bz);
+          tma_store_commit();
         }
       }
+      tc_fence_before();                          // this warp's TMEM reads of the tile are complete
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.acc_empty[ab]));
     }
-    tc_fence_before();
+    if (lane == 0) tma_store_wait_all<0>();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kBNMax) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * kBNMax) : "memory");
   }
 }
 
@@ -245,34 +295,38 @@ cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B,
   TcParams p;
   p.M = M; p.N = N; p.K = K;
   p.a_mn = a_mn; p.b_mn = b_mn;
-  p.C = C; p.ldc = ldc; p.strideC = strideC;
-  // tile width: the smallest multiple of 16 that covers N in the fewest tiles of at most 128
-  const int n_tiles = (N + kBNMax - 1) / kBNMax;
-  p.BN = (((N + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
-  const int m_tiles = (M + kBM - 1) / kBM;
+  p.batch = batch;
+  // tile width: as few tiles of at most 128 columns as cover N; several tiles are multiples of 32 wide (their 32-column
+  // stores must not spill into the next tile), a single tile only needs the UMMA granularity of 16
+  p.n_tiles = (N + kBNMax - 1) / kBNMax;
+  const int gran = p.n_tiles > 1 ? 32 : 16;
+  p.BN = (((N + p.n_tiles - 1) / p.n_tiles) + gran - 1) / gran * gran;
+  p.n_tiles = (N + p.BN - 1) / p.BN;
+  p.m_tiles = (M + kBM - 1) / kBM;
   p.kb_total = (K + kBK - 1) / kBK;
   if (p.kb_total == 0) p.kb_total = 1;
   // split K when the tiles alone cannot fill the GPU and the reduction is long (weight gradients: K = batch * L)
   int splits = 1;
-  const int64_t ctas = (int64_t)m_tiles * n_tiles * batch;
-  if (ctas < 148 && p.kb_total >= 16) {
-    splits = (int)((2 * 148 + ctas - 1) / ctas);
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles * batch;
+  if (tiles < 148 && p.kb_total >= 16) {
+    splits = (int)((2 * 148 + tiles - 1) / tiles);
     if (splits > p.kb_total / 4) splits = p.kb_total / 4;
     if (splits < 1) splits = 1;
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.mode = p.splits > 1 ? 2 : (accumulate ? 1 : 0);
+  p.reduce = (p.splits > 1 || accumulate) ? 1 : 0;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
   // K-major: rows = M (or N), inner = K; MN-major: rows = K, inner = M (or N).  Boxes are 32 floats (128 B, swizzled) wide.
   const bool ok_a = a_mn ? make_row_map_sw(&ma, A, M, K, batch, lda, strideA, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
                          : make_row_map_sw(&ma, A, K, M, batch, lda, strideA, 32, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
   const bool ok_b = b_mn ? make_row_map_sw(&mb, B, N, K, batch, ldb, strideB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
                          : make_row_map_sw(&mb, B, K, N, batch, ldb, strideB, 32, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (!ok_a || !ok_b) return cudaErrorInvalidValue;
-  if (p.mode == 2 && !accumulate) {               // split-K accumulates with atomics: start from zero
+  const bool ok_c = make_row_map_sw(&mc, C, N, M, batch, ldc, strideC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!ok_a || !ok_b || !ok_c) return cudaErrorInvalidValue;
+  if (p.splits > 1 && !accumulate) {              // split-K accumulates with reduce-adds: start from zero
     for (int b = 0; b < batch; ++b) {
       const cudaError_t e = cudaMemset2DAsync(C + (int64_t)b * strideC, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
       if (e != cudaSuccess) return e;
@@ -281,8 +335,9 @@ cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B,
   const int smem = (int)sizeof(TcSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(tcgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)(batch * p.splits));
-  tcgemm_3xtf32_kernel<<<grid, kTcThreads, smem, stream>>>(ma, mb, p);
+  const int64_t n_work = tiles * p.splits;
+  const unsigned grid = (unsigned)(n_work < 148 ? n_work : 148);
+  tcgemm_3xtf32_kernel<<<grid, kTcThreads, smem, stream>>>(ma, mb, mc, p);
   return cudaGetLastError();
 }
 

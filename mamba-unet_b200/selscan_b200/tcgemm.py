@@ -25,8 +25,12 @@ def gemm(a, b, a_mn=False, b_mn=False, out=None, accumulate=False):
         raise RuntimeError(f"gemm: reduction sizes differ ({K} vs {K2})")
     if not (_ok(a) and _ok(b)):
         a, b = a.contiguous(), b.contiguous()
-    if out is None:
-        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    if out is None:          # rows of C leave through TMA stores: 16-byte aligned rows
+        n4 = (N + 3) // 4 * 4
+        out = torch.empty((M, n4), device=a.device, dtype=torch.float32)
+        out = out if n4 == N else out[:, :N]
+    elif not _ok(out):
+        raise RuntimeError("gemm: `out` must have unit inner stride and 16-byte aligned rows")
     with torch.cuda.device(a.device):
         _lib.check(lib.selscan_b200_gemm_3xtf32(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
                                                 out.data_ptr(), out.stride(0), M, N, K, 1, 0, 0, 0, int(accumulate),

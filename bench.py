@@ -240,10 +240,12 @@ def model_leg(world, rank, dev, steps):
             del g
         except Exception as e:  # noqa: BLE001
             res["train_supervised_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
+    from selscan_b200 import ss2d
     if world == 1:   # opt-in: the Linear layers on the tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy, not cuBLAS)
         try:
-            from selscan_b200 import tcgemm
+            from selscan_b200 import ss2d, tcgemm
             tcgemm.patch_linears(model)
+            ss2d.TC_PROJ = True                    # x_proj / dt_proj too
             ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
             res["train_supervised_bs24_3xtf32_linears"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
             g = wl.GraphedStep(lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24)
@@ -252,6 +254,8 @@ def model_leg(world, rank, dev, steps):
             del g
         except Exception as e:  # noqa: BLE001
             res["train_supervised_bs24_3xtf32_linears"] = {"unavailable": repr(e)[:200]}
+        finally:
+            ss2d.TC_PROJ = False
     del net, opt, model
     m1, m2 = MambaUnet(num_classes=4).to(dev).train(), MambaUnet(num_classes=4).to(dev).train()
     if world > 1:

@@ -173,10 +173,13 @@ int selscan_b200_layernorm_bwd(const float* dy, const float* x, const float* mea
  *   C[b] (M x N, row stride ldc) (+)= A[b] (M x K) * B[b] (N x K)^T          b = 0 .. batch-1, strides strideA/B/C floats
  *   A: a_mn_major = 0: stored [M][K] (row stride lda, K contiguous); 1: stored [K][M] (row stride lda, M contiguous)
  *   B: b_mn_major = 0: stored [N][K];                                1: stored [K][N]
- *   accumulate = 1: C += ...   A, B 16-byte aligned, lda / ldb / batch strides multiples of 4 floats (TMA). */
+ *   accumulate = 1: C += ...   A, B, C 16-byte aligned, lda / ldb / ldc / batch strides multiples of 4 floats (TMA).
+ *   x_batch_mod > 0: operand x uses batch entry (b % x_batch_mod) -- weights shared by all images of a batch (a/b), or one C
+ *   that sums over images (c: the weight gradients of x_proj / dt_proj); 0: entry b. */
 int selscan_b200_gemm_3xtf32(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb, int32_t b_mn_major,
                              float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t batch, int64_t strideA,
-                             int64_t strideB, int64_t strideC, int32_t accumulate, void* stream);
+                             int64_t strideB, int64_t strideC, int32_t accumulate, int32_t a_batch_mod, int32_t b_batch_mod,
+                             int32_t c_batch_mod, void* stream);
 
 #ifdef __cplusplus
 }

@@ -251,17 +251,20 @@ SELSCAN_EXPORT int selscan_b200_layernorm_bwd(const float* dy, const float* x, c
 
 SELSCAN_EXPORT int selscan_b200_gemm_3xtf32(const float* A, int64_t lda, int32_t a_mn_major, const float* B, int64_t ldb,
                                             int32_t b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t batch,
-                                            int64_t strideA, int64_t strideB, int64_t strideC, int32_t accumulate, void* stream) {
+                                            int64_t strideA, int64_t strideB, int64_t strideC, int32_t accumulate,
+                                            int32_t a_batch_mod, int32_t b_batch_mod, int32_t c_batch_mod, void* stream) {
   const char* who = "selscan_b200_gemm_3xtf32";
   if (!A || !B || !C) return fail("%s: A, B, C must not be NULL", who);
   if (M < 0 || N < 0 || K < 0 || batch < 0) return fail("%s: bad sizes M=%d N=%d K=%d batch=%d", who, M, N, K, batch);
-  if (!selscan::tcgemm_operand_ok(A, lda, strideA, batch) || !selscan::tcgemm_operand_ok(B, ldb, strideB, batch) ||
-      !selscan::tcgemm_operand_ok(C, ldc, strideC, batch))
+  if (a_batch_mod < 0 || b_batch_mod < 0 || c_batch_mod < 0) return fail("%s: batch moduli must be >= 0", who);
+  if (!selscan::tcgemm_operand_ok(A, lda, strideA, a_batch_mod ? a_batch_mod : batch) ||
+      !selscan::tcgemm_operand_ok(B, ldb, strideB, b_batch_mod ? b_batch_mod : batch) ||
+      !selscan::tcgemm_operand_ok(C, ldc, strideC, c_batch_mod ? c_batch_mod : batch))
     return fail("%s: A, B and C must be 16-byte aligned with row / batch strides that are multiples of 4 floats", who);
   if (lda < (a_mn_major ? M : K) || ldb < (b_mn_major ? N : K) || ldc < N)
     return fail("%s: a leading dimension is smaller than the row it strides over", who);
   return edge_done(who, selscan::launch_tcgemm(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, batch, strideA, strideB, strideC,
-                                               accumulate, static_cast<cudaStream_t>(stream)));
+                                               accumulate, a_batch_mod, b_batch_mod, c_batch_mod, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

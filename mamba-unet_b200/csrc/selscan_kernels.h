@@ -70,7 +70,7 @@ cudaError_t launch_ln_bwd(const float* dy, const float* x, const float* mean, co
 // fp32 GEMM with the 3xTF32 split on tcgen05 tensor cores (selscan_tcgemm.cu)
 bool tcgemm_operand_ok(const float* p, int64_t ld, int64_t batch_stride, int batch);
 cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* C, int64_t ldc, int M,
-                          int N, int K, int batch, int64_t strideA, int64_t strideB, int64_t strideC, int accumulate,
-                          cudaStream_t stream);
+                          int N, int K, int batch, int64_t strideA, int64_t strideB, int64_t strideC, int accumulate, int a_bmod,
+                          int b_bmod, int c_bmod, cudaStream_t stream);
 
 }  // namespace selscan

@@ -37,6 +37,7 @@ struct TcParams {
   int M, N, K, BN;
   int a_mn, b_mn;                         // operand storage: 0 = K-major, 1 = MN-major
   int m_tiles, n_tiles, batch;
+  int a_bmod, b_bmod, c_bmod;             // batch coordinate of an operand = bz % mod (0: bz): weights shared across images, sums over images
   int kb_total, kb_per_split, splits;     // k-blocks of kBK
   int reduce;                             // 0: C = tile (TMA store), 1: C += tile (TMA reduce-add: accumulate and / or split-K)
   uint32_t idesc;
@@ -148,16 +149,17 @@ tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const uint32_t full = smem_u32(&sm.full[s]);
           const int k0 = (t.kb_begin + i) * kBK;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)kTileBytes + b_bytes) : "memory");
+          const int za = p.a_bmod ? t.bz % p.a_bmod : t.bz, zb = p.b_bmod ? t.bz % p.b_bmod : t.bz;
           if (p.a_mn) {
 #pragma unroll
-            for (int c = 0; c < kBM / 32; ++c) tma_load_3d(smem_u32(sm.a_hi[s]) + c * 4096, &map_a, t.m0 + 32 * c, k0, t.bz, full);
+            for (int c = 0; c < kBM / 32; ++c) tma_load_3d(smem_u32(sm.a_hi[s]) + c * 4096, &map_a, t.m0 + 32 * c, k0, za, full);
           } else {
-            tma_load_3d(smem_u32(sm.a_hi[s]), &map_a, k0, t.m0, t.bz, full);
+            tma_load_3d(smem_u32(sm.a_hi[s]), &map_a, k0, t.m0, za, full);
           }
           if (p.b_mn) {
-            for (int c = 0; c < b_chunks; ++c) tma_load_3d(smem_u32(sm.b_hi[s]) + c * 4096, &map_b, t.n0 + 32 * c, k0, t.bz, full);
+            for (int c = 0; c < b_chunks; ++c) tma_load_3d(smem_u32(sm.b_hi[s]) + c * 4096, &map_b, t.n0 + 32 * c, k0, zb, full);
           } else {
-            tma_load_3d(smem_u32(sm.b_hi[s]), &map_b, k0, t.n0, t.bz, full);
+            tma_load_3d(smem_u32(sm.b_hi[s]), &map_b, k0, t.n0, zb, full);
           }
         }
       }
@@ -263,8 +265,9 @@ tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (p.reduce) tma_reduce_add_3d(&map_c, stage, t.n0 + c0, t.m0 + q * 32, t.bz);
-          else tma_store_3d(&map_c, stage, t.n0 + c0, t.m0 + q * 32, t.bz);
+          const int zc = p.c_bmod ? t.bz % p.c_bmod : t.bz;
+          if (p.reduce) tma_reduce_add_3d(&map_c, stage, t.n0 + c0, t.m0 + q * 32, zc);
+          else tma_store_3d(&map_c, stage, t.n0 + c0, t.m0 + q * 32, zc);
           tma_store_commit();
         }
       }
@@ -289,10 +292,11 @@ bool tcgemm_operand_ok(const float* p, int64_t ld, int64_t batch_stride, int bat
 
 // C (M x N) (+)= A (M x K) * B (N x K)^T; see selscan_b200_gemm_3xtf32 in include/selscan_b200.h
 cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn, float* C, int64_t ldc, int M,
-                          int N, int K, int batch, int64_t strideA, int64_t strideB, int64_t strideC, int accumulate,
-                          cudaStream_t stream) {
+                          int N, int K, int batch, int64_t strideA, int64_t strideB, int64_t strideC, int accumulate, int a_bmod,
+                          int b_bmod, int c_bmod, cudaStream_t stream) {
   if (M == 0 || N == 0 || batch == 0) return cudaSuccess;
   TcParams p;
+  p.a_bmod = a_bmod; p.b_bmod = b_bmod; p.c_bmod = c_bmod;
   p.M = M; p.N = N; p.K = K;
   p.a_mn = a_mn; p.b_mn = b_mn;
   p.batch = batch;
@@ -315,19 +319,21 @@ cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B,
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.reduce = (p.splits > 1 || accumulate) ? 1 : 0;
+  const bool shared_c = c_bmod > 0 && c_bmod < batch;     // several batch entries sum into one C
+  p.reduce = (p.splits > 1 || accumulate || shared_c) ? 1 : 0;
   p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) | ((uint32_t)(b_mn ? 1 : 0) << 16) |
             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
   CUtensorMap ma, mb, mc;
   // K-major: rows = M (or N), inner = K; MN-major: rows = K, inner = M (or N).  Boxes are 32 floats (128 B, swizzled) wide.
-  const bool ok_a = a_mn ? make_row_map_sw(&ma, A, M, K, batch, lda, strideA, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-                         : make_row_map_sw(&ma, A, K, M, batch, lda, strideA, 32, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
-  const bool ok_b = b_mn ? make_row_map_sw(&mb, B, N, K, batch, ldb, strideB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-                         : make_row_map_sw(&mb, B, K, N, batch, ldb, strideB, 32, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
-  const bool ok_c = make_row_map_sw(&mc, C, N, M, batch, ldc, strideC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int na = a_bmod ? a_bmod : batch, nb = b_bmod ? b_bmod : batch, nc = c_bmod ? c_bmod : batch;
+  const bool ok_a = a_mn ? make_row_map_sw(&ma, A, M, K, na, lda, strideA, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                         : make_row_map_sw(&ma, A, K, M, na, lda, strideA, 32, kBM, CU_TENSOR_MAP_SWIZZLE_128B);
+  const bool ok_b = b_mn ? make_row_map_sw(&mb, B, N, K, nb, ldb, strideB, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                         : make_row_map_sw(&mb, B, K, N, nb, ldb, strideB, 32, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  const bool ok_c = make_row_map_sw(&mc, C, N, M, nc, ldc, strideC, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   if (!ok_a || !ok_b || !ok_c) return cudaErrorInvalidValue;
-  if (p.splits > 1 && !accumulate) {              // split-K accumulates with reduce-adds: start from zero
-    for (int b = 0; b < batch; ++b) {
+  if (p.reduce && !accumulate) {                  // split-K / shared C accumulate with reduce-adds: start from zero
+    for (int b = 0; b < nc; ++b) {
       const cudaError_t e = cudaMemset2DAsync(C + (int64_t)b * strideC, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
       if (e != cudaSuccess) return e;
     }

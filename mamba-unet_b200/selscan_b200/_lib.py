@@ -104,7 +104,7 @@ def load():
         lib.selscan_b200_layernorm_bwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _ptr]
         lib.selscan_b200_gemm_3xtf32.restype = ctypes.c_int
         lib.selscan_b200_gemm_3xtf32.argtypes = [_ptr, _i64, _i32, _ptr, _i64, _i32, _ptr, _i64, _i32, _i32, _i32, _i32, _i64, _i64,
-                                                 _i64, _i32, _ptr]
+                                                 _i64, _i32, _i32, _i32, _i32, _ptr]
         if lib.selscan_b200_abi_version() != ABI_VERSION:
             raise RuntimeError("libselscan_b200.so ABI version mismatch: rebuild with mamba-unet_b200/build.py")
         _lib = lib

@@ -178,6 +178,25 @@ def edge_out_bwd(g, H, W, z, zld, xhat, rstd, ln_w, ln_b, dz, dzld):
     return d_ys, part[0], part[1]
 
 
+# Opt-in: x_proj / dt_proj and their gradients on the tcgen05 tensor cores (3xTF32 split, tcgemm.bgemm) instead of cuBLAS fp32.
+TC_PROJ = False
+
+
+def _tc_proj_ok(D, L, N, R):
+    return TC_PROJ and L % 4 == 0 and D % 4 == 0
+
+
+def _pad_dt_weight(dt_w):
+    """(K, D, R) -> (K, D, R4) zero padded so that its rows are 16-byte aligned for TMA."""
+    K, D, R = dt_w.shape
+    R4 = (R + 3) // 4 * 4
+    if R4 == R:
+        return dt_w.contiguous(), R4
+    w = dt_w.new_zeros((K, D, R4))
+    w[:, :, :R] = dt_w
+    return w, R4
+
+
 class SS2DFusedFn(torch.autograd.Function):
     """xz = in_proj(x) (B, H, W, 2*D)  ->  LayerNorm(merge(scan(...))) * silu(z)  (B, H, W, D)  (mamba_sys.py:530-537).
 
@@ -195,10 +214,21 @@ class SS2DFusedFn(torch.autograd.Function):
         conv_b = conv_b.contiguous() if conv_b is not None else None
         needs_grad = any(ctx.needs_input_grad)
         xs = edge_in_fwd(xz, D, conv_w, conv_b)                                          # (B, K, D, L)
-        x_dbl = torch.matmul(x_proj_w.unsqueeze(0), xs)                                  # (B, K, R+2N, L)   :406
-        dts = torch.matmul(dt_w.unsqueeze(0), x_dbl[:, :, :R])                           # (B, K, D, L)      :409
-        if L % 4:                                                                        # rows must stay 16-byte aligned
-            dts = _empty_dirs(xz, B, D, L).copy_(dts)
+        tc = _tc_proj_ok(D, L, N, R)
+        if tc:
+            from . import tcgemm
+            C = R + 2 * N
+            x_proj_w = x_proj_w.contiguous()
+            x_dbl = xz.new_empty((B, K, C, L))
+            tcgemm.bgemm(x_proj_w, xs.view(B * K, D, L), x_dbl.view(B * K, C, L), b_mn=True)          # W (C, D) x xs (D, L)
+            dtw_pad, R4 = _pad_dt_weight(dt_w)
+            dts = xz.new_empty((B, K, D, L))
+            tcgemm.bgemm(dtw_pad, x_dbl.view(B * K, C, L)[:, :R4], dts.view(B * K, D, L), b_mn=True)  # padded columns are zero
+        else:
+            x_dbl = torch.matmul(x_proj_w.unsqueeze(0), xs)                              # (B, K, R+2N, L)   :406
+            dts = torch.matmul(dt_w.unsqueeze(0), x_dbl[:, :, :R])                       # (B, K, D, L)      :409
+            if L % 4:                                                                    # rows must stay 16-byte aligned
+                dts = _empty_dirs(xz, B, D, L).copy_(dts)
         As = -torch.exp(A_logs.float()).view(K * D, N)                                   # :417
         Dsf, dtb = Ds.float().reshape(-1).contiguous(), dt_b.float().reshape(-1).contiguous()
         out_y = _empty_dirs(xz, B, D, L)
@@ -215,6 +245,7 @@ class SS2DFusedFn(torch.autograd.Function):
         if needs_grad:
             ctx.save_for_backward(xz, xs, x_dbl, dts, As, ckpt, xhat, rstd, conv_w, conv_b, x_proj_w, dt_w, Dsf, dtb, ln_w, ln_b)
             ctx.shape_A, ctx.shape_D, ctx.shape_dtb = A_logs.shape, Ds.shape, dt_b.shape
+            ctx.tc = tc
         return y
 
     @staticmethod
@@ -238,14 +269,26 @@ class SS2DFusedFn(torch.autograd.Function):
         ops.launch_bwd(xs.view(B, KD, L), dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], Dsf, None, dtb,
                        d_ys.view(B, KD, L), None, ckpt, True, du.view(B, KD, L), ddelta.view(B, KD, L), dA, dB, dC, dD,
                        None, dbias)
-        x_dt = x_dbl[:, :, :R]
-        d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                      # (K, D, R)
-        d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)                 # (B, K, R, L)
-        d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                       # (B, K, R+2N, L)
-        d_x_proj_w = torch.matmul(d_x_dbl, xs.transpose(-1, -2)).sum(0)                   # (K, R+2N, D)
-        wT = x_proj_w.transpose(-1, -2).unsqueeze(0).expand(B, K, D, R + 2 * N).reshape(B * K, D, R + 2 * N)
-        d_xs = du.view(B * K, D, L)
-        d_xs.baddbmm_(wT, d_x_dbl.view(B * K, R + 2 * N, L))                              # du + W^T d(x_dbl), no extra pass
+        if ctx.tc:
+            from . import tcgemm
+            C = R + 2 * N
+            dtw_pad, R4 = _pad_dt_weight(dt_w)
+            x3, dd3 = x_dbl.view(B * K, C, L), ddelta.view(B * K, D, L)
+            d_dt_w = tcgemm.bgemm(dd3, x3[:, :R4], xz.new_empty((K, D, R4)))[:, :, :R].contiguous()    # sum over images
+            d_dtr = tcgemm.bgemm(dtw_pad, dd3, xz.new_empty((B * K, R4, L)), a_mn=True, b_mn=True)     # W^T (R, D) x ddelta (D, L)
+            d_x_dbl = torch.cat([d_dtr.view(B, K, R4, L)[:, :, :R], dB, dC], dim=2)                    # (B, K, R+2N, L)
+            d3 = d_x_dbl.view(B * K, C, L)
+            d_x_proj_w = tcgemm.bgemm(d3, xs.view(B * K, D, L), xz.new_empty((K, C, D)))               # sum over images
+            tcgemm.bgemm(x_proj_w, d3, du.view(B * K, D, L), a_mn=True, b_mn=True, accumulate=True)    # du += W^T d(x_dbl)
+        else:
+            x_dt = x_dbl[:, :, :R]
+            d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                  # (K, D, R)
+            d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)             # (B, K, R, L)
+            d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                   # (B, K, R+2N, L)
+            d_x_proj_w = torch.matmul(d_x_dbl, xs.transpose(-1, -2)).sum(0)               # (K, R+2N, D)
+            wT = x_proj_w.transpose(-1, -2).unsqueeze(0).expand(B, K, D, R + 2 * N).reshape(B * K, D, R + 2 * N)
+            d_xs = du.view(B * K, D, L)
+            d_xs.baddbmm_(wT, d_x_dbl.view(B * K, R + 2 * N, L))                          # du + W^T d(x_dbl), no extra pass
         d_conv_w, d_conv_b = edge_in_bwd(du, xz, D, conv_w, conv_b, d_xz)
         d_A_logs = (dA * As).view(ctx.shape_A)
         return (d_xz, d_conv_w, d_conv_b if conv_b is not None else None, d_x_proj_w, d_dt_w, dbias.view(ctx.shape_dtb), d_A_logs,

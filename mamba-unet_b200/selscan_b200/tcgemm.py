@@ -33,7 +33,32 @@ def gemm(a, b, a_mn=False, b_mn=False, out=None, accumulate=False):
         raise RuntimeError("gemm: `out` must have unit inner stride and 16-byte aligned rows")
     with torch.cuda.device(a.device):
         _lib.check(lib.selscan_b200_gemm_3xtf32(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
-                                                out.data_ptr(), out.stride(0), M, N, K, 1, 0, 0, 0, int(accumulate),
+                                                out.data_ptr(), out.stride(0), M, N, K, 1, 0, 0, 0, int(accumulate), 0, 0, 0,
+                                                torch.cuda.current_stream(a.device).cuda_stream), "selscan_b200_gemm_3xtf32")
+    return out
+
+
+def bgemm_ok(*ts):
+    """Can these (batch, rows, cols) operands go through the TMA descriptors?"""
+    return all(t.is_cuda and t.dtype == torch.float32 and t.dim() == 3 and _ok(t) and (t.shape[0] == 1 or t.stride(0) % 4 == 0)
+               for t in ts)
+
+
+def bgemm(a, b, out, a_mn=False, b_mn=False, accumulate=False, batch=None):
+    """out[i % len(out)] (+)= A[i % len(a)] @ B[i % len(b)]^T for i < batch: 3-D (entries, rows, cols) fp32 tensors.
+    An operand with fewer entries than `batch` is shared cyclically (weights per direction); an `out` with fewer entries
+    receives the SUM over the batch entries that map to it (weight gradients)."""
+    lib = _lib.load()
+    M, K = (a.shape[2], a.shape[1]) if a_mn else a.shape[1:]
+    N, K2 = (b.shape[2], b.shape[1]) if b_mn else b.shape[1:]
+    if K != K2 or tuple(out.shape[1:]) != (M, N):
+        raise RuntimeError(f"bgemm: shapes do not match: A {tuple(a.shape)} B {tuple(b.shape)} out {tuple(out.shape)}")
+    batch = batch or max(a.shape[0], b.shape[0], out.shape[0])
+    mods = [0 if t.shape[0] == batch else t.shape[0] for t in (a, b, out)]
+    with torch.cuda.device(a.device):
+        _lib.check(lib.selscan_b200_gemm_3xtf32(a.data_ptr(), a.stride(1), int(a_mn), b.data_ptr(), b.stride(1), int(b_mn),
+                                                out.data_ptr(), out.stride(1), M, N, K, batch, a.stride(0), b.stride(0),
+                                                out.stride(0), int(accumulate), mods[0], mods[1], mods[2],
                                                 torch.cuda.current_stream(a.device).cuda_stream), "selscan_b200_gemm_3xtf32")
     return out
 

@@ -87,11 +87,15 @@ def test_epilogue_merge_layernorm_gate(B, D, H, W, gated):
         _close(d_xz[..., D:], grads[3], 1e-3, 1e-5, "dz")
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("B,d_model,H,W", [(2, 16, 8, 8), (1, 20, 7, 7), (2, 96, 56, 56), (2, 24, 5, 9), (3, 192, 14, 14)])
-def test_fused_ss2d_block_matches_separate_kernels(B, d_model, H, W):
-    """SS2D.forward through SS2DFusedFn (hand-written backward) == the same block through conv2d / CrossScan / autograd."""
+def test_fused_ss2d_block_matches_separate_kernels(B, d_model, H, W, tc, monkeypatch):
+    """SS2D.forward through SS2DFusedFn (hand-written backward) == the same block through conv2d / CrossScan / autograd;
+    tc: x_proj / dt_proj and their gradients through the 3xTF32 tensor-core GEMM instead of cuBLAS fp32."""
+    from selscan_b200 import ss2d
     from selscan_b200.vssm import SS2D
 
+    monkeypatch.setattr(ss2d, "TC_PROJ", tc)
     _fp32()
     torch.manual_seed(d_model + H)
     blk = SS2D(d_model).cuda()

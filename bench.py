@@ -241,19 +241,20 @@ def model_leg(world, rank, dev, steps):
         except Exception as e:  # noqa: BLE001
             res["train_supervised_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
     from selscan_b200 import ss2d
-    if world == 1:   # opt-in: the Linear layers on the tcgen05 tensor cores with the 3xTF32 split (fp32-level accuracy, not cuBLAS)
+    if world == 1:   # opt-in legs: Linear layers, x_proj, dt_proj and d(xs) on the tcgen05 tensor cores with the 3xTF32 split
+        # (fp32-level accuracy, ~2x the rounding error of cuBLAS fp32; NOT the reference's cuBLAS arithmetic, hence separate keys)
         try:
             from selscan_b200 import ss2d, tcgemm
             tcgemm.patch_linears(model)
             ss2d.TC_PROJ = True                    # x_proj / dt_proj too
             ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
-            res["train_supervised_bs24_3xtf32_linears"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
+            res["train_supervised_bs24_tc3xtf32"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
             g = wl.GraphedStep(lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24)
             ms = timed(lambda: g(x24, y24), n)
-            res["train_supervised_bs24_3xtf32_linears_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
+            res["train_supervised_bs24_tc3xtf32_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
             del g
         except Exception as e:  # noqa: BLE001
-            res["train_supervised_bs24_3xtf32_linears"] = {"unavailable": repr(e)[:200]}
+            res["train_supervised_bs24_tc3xtf32"] = {"unavailable": repr(e)[:200]}
         finally:
             ss2d.TC_PROJ = False
     del net, opt, model

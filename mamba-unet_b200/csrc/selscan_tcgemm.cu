@@ -29,7 +29,7 @@ namespace {
 constexpr int kBM = 128;                 // UMMA M
 constexpr int kBK = 32;                  // k per stage: 128 bytes of fp32 = one swizzle row
 constexpr int kBNMax = 128;
-constexpr int kTcStages = 3;
+constexpr int kTcMaxStages = 8;          // the ring is as deep as shared memory allows: 3 stages at BN = 128, 5 at BN = 16
 constexpr int kTcThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 constexpr int kTileBytes = kBM * kBK * 4;     // 16 KB: the A tile, and the largest B tile
 
@@ -39,19 +39,19 @@ struct TcParams {
   int m_tiles, n_tiles, batch;
   int a_bmod, b_bmod, c_bmod;             // batch coordinate of an operand = bz % mod (0: bz): weights shared across images, sums over images
   int kb_total, kb_per_split, splits;     // k-blocks of kBK
+  int stages;                             // depth of the operand ring
+  uint32_t stage_bytes, b_off;            // one stage: [a_hi 16K][a_lo 16K][b_hi][b_lo]; b_off = bytes between b_hi and b_lo
   int reduce;                             // 0: C = tile (TMA store), 1: C += tile (TMA reduce-add: accumulate and / or split-K)
   uint32_t idesc;
 };
 
-struct TcSmem {
-  float a_hi[kTcStages][kBM * kBK];
-  float a_lo[kTcStages][kBM * kBK];
-  float b_hi[kTcStages][kBNMax * kBK];
-  float b_lo[kTcStages][kBNMax * kBK];
+struct TcSmem {                           // followed by the operand ring (runtime depth)
   float out[4][2][32 * 32];               // per epilogue warp: two 32 x 32 staging tiles for the TMA stores
-  u64 full[kTcStages], split[kTcStages], empty[kTcStages], acc_full[2], acc_empty[2];
+  u64 full[kTcMaxStages], split[kTcMaxStages], empty[kTcMaxStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
+constexpr uint32_t kTcHeader = (sizeof(TcSmem) + 1023) / 1024 * 1024;
+constexpr uint32_t kTcSmemMax = 232448 - 1024;    // opt-in dynamic shared memory minus the alignment slack
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), Blackwell version bits.
 // layout 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only layout tcgen05 accepts for MN-major tf32 operands)
@@ -59,11 +59,9 @@ __device__ __forceinline__ u64 smem_desc(uint32_t addr, uint32_t lbo_bytes, uint
   return (u64)((addr & 0x3FFFF) >> 4) | ((u64)(lbo_bytes >> 4) << 16) | ((u64)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((u64)layout << 61);
 }
 
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round to the 10-bit TF32 mantissa (nearest, ties away) with two full-rate integer ops; cvt.rna.tf32.f32 runs on the
+// quarter-rate conversion pipe and made the split pass, not the tensor core, the bottleneck of a stage
+__device__ __forceinline__ float rna_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 __device__ __forceinline__ void tc_mma(uint32_t tmem_c, u64 da, u64 db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -107,14 +105,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
-  TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_al = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_al);
+  const uint32_t ring = smem_u32(smem_al) + kTcHeader;      // stage s: ring + s * stage_bytes
+  unsigned char* ring_ptr = smem_al + kTcHeader;
+  const int kTcStages = p.stages;
+  auto a_hi_addr = [&](int st) { return ring + (uint32_t)st * p.stage_bytes; };
+  auto a_lo_addr = [&](int st) { return ring + (uint32_t)st * p.stage_bytes + kTileBytes; };
+  auto b_hi_addr = [&](int st) { return ring + (uint32_t)st * p.stage_bytes + 2 * kTileBytes; };
+  auto b_lo_addr = [&](int st) { return ring + (uint32_t)st * p.stage_bytes + 2 * kTileBytes + p.b_off; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_work = p.m_tiles * p.n_tiles * p.batch * p.splits;
   const int b_chunks = (p.BN + 31) / 32;
   const uint32_t b_bytes = p.b_mn ? (uint32_t)b_chunks * 4096u : (uint32_t)p.BN * 128u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
+    for (int s = 0; s < kTcMaxStages; ++s) {
       mbar_init(smem_u32(&sm.full[s]), 1);
       mbar_init(smem_u32(&sm.split[s]), 4);       // lane 0 of each of the four split warps
       mbar_init(smem_u32(&sm.empty[s]), 1);       // tcgen05.commit
@@ -152,14 +158,14 @@ tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           const int za = p.a_bmod ? t.bz % p.a_bmod : t.bz, zb = p.b_bmod ? t.bz % p.b_bmod : t.bz;
           if (p.a_mn) {
 #pragma unroll
-            for (int c = 0; c < kBM / 32; ++c) tma_load_3d(smem_u32(sm.a_hi[s]) + c * 4096, &map_a, t.m0 + 32 * c, k0, za, full);
+            for (int c = 0; c < kBM / 32; ++c) tma_load_3d(a_hi_addr(s) + c * 4096, &map_a, t.m0 + 32 * c, k0, za, full);
           } else {
-            tma_load_3d(smem_u32(sm.a_hi[s]), &map_a, k0, t.m0, za, full);
+            tma_load_3d(a_hi_addr(s), &map_a, k0, t.m0, za, full);
           }
           if (p.b_mn) {
-            for (int c = 0; c < b_chunks; ++c) tma_load_3d(smem_u32(sm.b_hi[s]) + c * 4096, &map_b, t.n0 + 32 * c, k0, zb, full);
+            for (int c = 0; c < b_chunks; ++c) tma_load_3d(b_hi_addr(s) + c * 4096, &map_b, t.n0 + 32 * c, k0, zb, full);
           } else {
-            tma_load_3d(smem_u32(sm.b_hi[s]), &map_b, k0, t.n0, zb, full);
+            tma_load_3d(b_hi_addr(s), &map_b, k0, t.n0, zb, full);
           }
         }
       }
@@ -187,10 +193,10 @@ tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (lane == 0) {
 #pragma unroll
           for (int ks = 0; ks < kBK / 8; ++ks) {
-            const u64 ah = smem_desc(smem_u32(sm.a_hi[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
-            const u64 al = smem_desc(smem_u32(sm.a_lo[s]) + ks * a_step, a_lbo, a_sbo, a_lt);
-            const u64 bh = smem_desc(smem_u32(sm.b_hi[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
-            const u64 bl = smem_desc(smem_u32(sm.b_lo[s]) + ks * b_step, b_lbo, b_sbo, b_lt);
+            const u64 ah = smem_desc(a_hi_addr(s) + ks * a_step, a_lbo, a_sbo, a_lt);
+            const u64 al = smem_desc(a_lo_addr(s) + ks * a_step, a_lbo, a_sbo, a_lt);
+            const u64 bh = smem_desc(b_hi_addr(s) + ks * b_step, b_lbo, b_sbo, b_lt);
+            const u64 bl = smem_desc(b_lo_addr(s) + ks * b_step, b_lbo, b_sbo, b_lt);
             tc_mma(acc, al, bh, p.idesc, (i > 0 || ks > 0) ? 1u : 0u);
             tc_mma(acc, ah, bl, p.idesc, 1u);
             tc_mma(acc, ah, bh, p.idesc, 1u);
@@ -211,14 +217,15 @@ tcgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int i = 0; i < t.n_kb; ++i, ++it) {
         const int s = it % kTcStages, k = it / kTcStages;
         mbar_wait(smem_u32(&sm.full[s]), k & 1);
-        float4* ah = reinterpret_cast<float4*>(sm.a_hi[s]);
-        float4* al = reinterpret_cast<float4*>(sm.a_lo[s]);
-        float4* bh = reinterpret_cast<float4*>(sm.b_hi[s]);
-        float4* bl = reinterpret_cast<float4*>(sm.b_lo[s]);
-        auto split4 = [](float4* hi, float4* lo, int q) {   // hi = tf32(x) round-to-nearest, lo = tf32(x - hi): both exact operands
-          float4 v = hi[q], h, l;
+        unsigned char* st = ring_ptr + (size_t)s * p.stage_bytes;
+        float4* ah = reinterpret_cast<float4*>(st);
+        float4* al = reinterpret_cast<float4*>(st + kTileBytes);
+        float4* bh = reinterpret_cast<float4*>(st + 2 * kTileBytes);
+        float4* bl = reinterpret_cast<float4*>(st + 2 * kTileBytes + p.b_off);
+        auto split4 = [](float4* hi, float4* lo, int q) {   // hi = tf32(x) round-to-nearest (exact operand), lo = x - hi (exact
+          float4 v = hi[q], h, l;                             // difference; the tensor core drops its bits below 2^-21 |x|)
           h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-          l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
           hi[q] = h;
           lo[q] = l;
         };
@@ -338,7 +345,12 @@ cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B,
       if (e != cudaSuccess) return e;
     }
   }
-  const int smem = (int)sizeof(TcSmem) + 1024;
+  const uint32_t b_tile = b_mn ? (uint32_t)((p.BN + 31) / 32) * 4096u : (uint32_t)p.BN * 128u;
+  p.b_off = (b_tile + 1023u) / 1024u * 1024u;
+  p.stage_bytes = 2u * kTileBytes + 2u * p.b_off;
+  p.stages = (int)((kTcSmemMax - kTcHeader) / p.stage_bytes);
+  if (p.stages > kTcMaxStages) p.stages = kTcMaxStages;
+  const int smem = (int)(kTcHeader + (uint32_t)p.stages * p.stage_bytes + 1024u);
   cudaError_t e = cudaFuncSetAttribute(tcgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const int64_t n_work = tiles * p.splits;

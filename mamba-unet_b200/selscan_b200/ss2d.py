@@ -269,23 +269,18 @@ class SS2DFusedFn(torch.autograd.Function):
         ops.launch_bwd(xs.view(B, KD, L), dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], Dsf, None, dtb,
                        d_ys.view(B, KD, L), None, ckpt, True, du.view(B, KD, L), ddelta.view(B, KD, L), dA, dB, dC, dD,
                        None, dbias)
+        # The three small-output products (reductions over L with a 6..56-row result) stay on cuBLAS: a 128-row tensor-core
+        # tile is mostly padding there and the 3xTF32 operand split makes them shared-memory bound (scripts/bench_tcproj.py).
+        x_dt = x_dbl[:, :, :R]
+        d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                      # (K, D, R)
+        d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)                 # (B, K, R, L)
+        d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                       # (B, K, R+2N, L)
+        d_x_proj_w = torch.matmul(d_x_dbl, xs.transpose(-1, -2)).sum(0)                   # (K, R+2N, D)
         if ctx.tc:
             from . import tcgemm
-            C = R + 2 * N
-            dtw_pad, R4 = _pad_dt_weight(dt_w)
-            x3, dd3 = x_dbl.view(B * K, C, L), ddelta.view(B * K, D, L)
-            d_dt_w = tcgemm.bgemm(dd3, x3[:, :R4], xz.new_empty((K, D, R4)))[:, :, :R].contiguous()    # sum over images
-            d_dtr = tcgemm.bgemm(dtw_pad, dd3, xz.new_empty((B * K, R4, L)), a_mn=True, b_mn=True)     # W^T (R, D) x ddelta (D, L)
-            d_x_dbl = torch.cat([d_dtr.view(B, K, R4, L)[:, :, :R], dB, dC], dim=2)                    # (B, K, R+2N, L)
-            d3 = d_x_dbl.view(B * K, C, L)
-            d_x_proj_w = tcgemm.bgemm(d3, xs.view(B * K, D, L), xz.new_empty((K, C, D)))               # sum over images
-            tcgemm.bgemm(x_proj_w, d3, du.view(B * K, D, L), a_mn=True, b_mn=True, accumulate=True)    # du += W^T d(x_dbl)
+            tcgemm.bgemm(x_proj_w, d_x_dbl.view(B * K, R + 2 * N, L), du.view(B * K, D, L), a_mn=True, b_mn=True,
+                         accumulate=True)                                                 # du += W^T d(x_dbl), TMA reduce-add
         else:
-            x_dt = x_dbl[:, :, :R]
-            d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                  # (K, D, R)
-            d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)             # (B, K, R, L)
-            d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                   # (B, K, R+2N, L)
-            d_x_proj_w = torch.matmul(d_x_dbl, xs.transpose(-1, -2)).sum(0)               # (K, R+2N, D)
             wT = x_proj_w.transpose(-1, -2).unsqueeze(0).expand(B, K, D, R + 2 * N).reshape(B * K, D, R + 2 * N)
             d_xs = du.view(B * K, D, L)
             d_xs.baddbmm_(wT, d_x_dbl.view(B * K, R + 2 * N, L))                          # du + W^T d(x_dbl), no extra pass

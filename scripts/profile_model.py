@@ -10,6 +10,10 @@ from selscan_b200.vssm import DiceLoss, MambaUnet
 dev = torch.device("cuda")
 torch.manual_seed(0)
 model = MambaUnet(num_classes=4).to(dev).train()
+if os.environ.get("TC"):
+    from selscan_b200 import ss2d, tcgemm
+    tcgemm.patch_linears(model)
+    ss2d.TC_PROJ = True
 opt = wl.make_sgd(model)
 dice = DiceLoss(4)
 x = torch.rand(24, 1, 224, 224, device=dev)

@@ -55,3 +55,32 @@ def test_linear_autograd_matches_torch():
     hx, hw, hb = torch.autograd.grad(out, (x, lin.weight, lin.bias), g)
     for a, r, name in ((out, ref, "y"), (hx, gx, "dx"), (hw, gw, "dW"), (hb, gb, "db")):
         torch.testing.assert_close(a, r, rtol=1e-5, atol=2e-5 * float(r.abs().max()), msg=lambda m: f"{name}: {m}")
+
+
+def test_batched_gemm_with_shared_operands_and_summed_output():
+    """bgemm: per-direction weights shared cyclically across images (x_proj), MN-major operands, accumulate, and an output that
+    sums over the images that map to it (the weight-gradient form)."""
+    from selscan_b200 import tcgemm
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    Bt, K, C, D, L = 3, 4, 40, 64, 200
+    W = torch.randn(K, C, D, device="cuda")
+    xs = torch.randn(Bt * K, D, L, device="cuda")
+    ref = torch.matmul(W.repeat(Bt, 1, 1).double(), xs.double())                       # entry i uses W[i % K]
+    out = torch.empty(Bt * K, C, L, device="cuda")
+    tcgemm.bgemm(W, xs, out, b_mn=True)
+    e_blas = float((torch.matmul(W.repeat(Bt, 1, 1), xs).double() - ref).abs().max())
+    assert float((out.double() - ref).abs().max()) <= 4 * e_blas + 1e-6
+    # d(xs) += W^T g   (A MN-major, accumulate)
+    g = torch.randn(Bt * K, C, L, device="cuda")
+    base = torch.randn(Bt * K, D, L, device="cuda")
+    ref2 = base.double() + torch.matmul(W.repeat(Bt, 1, 1).double().transpose(1, 2), g.double())
+    acc = base.clone()
+    tcgemm.bgemm(W, g, acc, a_mn=True, b_mn=True, accumulate=True)
+    assert float((acc.double() - ref2).abs().max()) <= 1e-4
+    # d W[k] = sum_b g[b, k] xs[b, k]^T   (output shared by the images)
+    ref3 = torch.matmul(g.double(), xs.double().transpose(1, 2)).view(Bt, K, C, D).sum(0)
+    dW = torch.empty(K, C, D, device="cuda")
+    tcgemm.bgemm(g, xs, dW)
+    assert float((dW.double() - ref3).abs().max()) <= 2e-5 * float(ref3.abs().max())

@@ -444,6 +444,7 @@ bool bwd_tma_eligible(const BwdLaunch& p) {
 }
 
 cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream) {
+  if (bwd_ws_usable() && bwd_ws_eligible(p)) return launch_bwd_ws(p, stream);
   const selscan_bwd_args& a = p.a;
   CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
   if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, 4, kR) ||

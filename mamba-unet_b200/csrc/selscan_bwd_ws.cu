@@ -1,0 +1,527 @@
+// Backward selective scan, warp-specialised tiled path for sm_100a.  Replaces selective_scan_bwd_kernel
+// (/root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489) for the aligned shapes Mamba-UNet produces
+// (channels per group a multiple of 64, 16-byte aligned rows, no z); same arithmetic and the same saved-state scheme as
+// selscan_bwd_tma.cu, which it supersedes as the default (SELSCAN_B200_BWD=tma selects the older single-role kernel).
+//
+// Why two roles.  In the single-role kernel every thread ran ~1240 instructions per chunk of 8 positions, of which only ~600 were the
+// recurrences (FFMA2 / FMUL2 / MUFU.EX2); the rest -- softplus / sigmoid of delta, the B/C gather, TMA issue, the reduce-scatter and
+// finalisation of du / ddelta, the contraction of the dB / dC products over channels, atomics -- are latency-bound chains
+// (MUFU -> RCP -> polynomial, shared-memory round trips, shuffles) and with 254 registers per thread only 2 warps per SM
+// sub-partition were there to hide them: issue slots 45 % busy.  Here the CTA is two warpgroups with different register budgets
+// (setmaxnreg):
+//   warps 0-3  COMPUTE (200 registers): a thread owns 2 channels x 4 states; per chunk it restarts the forward recurrence from the
+//              saved state, runs the reverse recurrence in registers, and leaves (a) the channel-pair products for dB / dC in the
+//              swizzled P tile and (b) its 4-state partial sums of dx*B and dx*a*x*A per (channel, position) in the S12 tile.
+//              Nothing else: no transcendental besides the decays, no shuffles, no global memory.
+//   warps 4-7  HELPER (56 registers): thread (row, half chunk) discretises delta once per element (softplus, sigmoid) one chunk
+//              ahead and publishes delta and delta*u; gathers B/C (any strides) into the [position][B0..15 C0..15] tile; one lane
+//              issues the TMA loads two chunks ahead (u, delta, dout, saved state) into a 3-stage ring; after the compute warps
+//              finish a half chunk it sums P over the 32 channel pairs (one atomic per (state, position) per CTA -- the reference
+//              issues one per (channel, state, position), bwd_kernel.cuh:298-316), sums the S12 partials over the 4 lanes of a
+//              channel and finalises du, ddelta (through softplus'), dD, ddelta_bias; du / ddelta leave by TMA stores.
+// Hand-over is by mbarriers only (full/empty per stage and per half chunk); the two roles drift by up to a chunk.  All waits are
+// bounded (trap instead of hang).  16 warps per SM (2 CTAs): 8 dense compute warps + 8 helper warps that fill their stalls.
+#include <type_traits>
+
+#include "selscan_common.cuh"
+#include "selscan_kernels.h"
+#include "selscan_ptx.cuh"
+#include "selscan_tma_host.h"
+
+namespace selscan {
+
+namespace {
+
+constexpr int kR = 64;            // channels per CTA
+constexpr int kNP = kR / 2;       // channel pairs per CTA
+constexpr int kC = kCkptInterval; // positions per chunk (8)
+constexpr int kHP = kC / 2;       // positions per half chunk
+constexpr int kStg = 3;
+constexpr int kPitch = 36;        // B/C tile pitch (floats)
+constexpr int kGroupThr = 128;    // threads per role
+constexpr int kThr = 2 * kGroupThr;
+constexpr int kLS = kStatePad / 4;  // states per lane
+constexpr int kCompRegs = 184;    // 128 * (184 + 72) * 2 CTAs = the whole register file
+constexpr int kHelpRegs = 72;
+constexpr int kLaunchRegs = 128;  // what ptxas must report for the kernel (checked by the launcher: setmaxnreg.inc would block otherwise)
+
+constexpr int kPP = kHP * 32 + 16;   // floats per channel pair in a P half: 4 positions x 32 values + 64 bytes, so that the two pairs of
+                                     // a quarter-warp store to disjoint banks and readers need no swizzle
+constexpr int kS12P = 36;            // floats per row in an S12 half (32 + 16 bytes: conflict-free STS.128 by (row, lane), LDS.128 by row)
+
+struct WsSmem {
+  float CK[kStg][kR * kStatePad];   // [row][16 states]                                    (TMA)
+  float U[kStg][kR * kC];           // [row][8 positions] (one 64 x 8 box)                  (TMA)
+  float DT[kStg][kR * kC];          //   raw delta
+  float DY[kStg][kR * kC];
+  float BC[kStg][kC * kPitch];      // [position][B0..15 C0..15]                            (helper)
+  float SD[kStg][kR * kC];          // delta   [row][8]                                     (helper)
+  float SDU[kStg][kR * kC];         // delta*u
+  float P[2][kNP * kPP];            // per half chunk: [pair][position][dB 0..15 | dC 0..15]   (compute)
+  float S12[2][kR * kS12P];         // per half chunk: [row][lane 0..3][s1 x4 positions | s2 x4] (compute)
+  float DU[2][kR * kC];             // output tiles [half][row][4] (one 64 x 4 TMA store per half), double-buffered by chunk parity (helper)
+  float DDT[2][kR * kC];
+  u64 tma_full[kStg];               // TMA transaction bytes of a stage
+  u64 prep_done[kStg];              // helper warps: delta / delta*u / B/C tiles of a stage written
+  u64 stage_free[kStg];             // compute + helper warps: stage no longer read
+  u64 half_full[2];                 // compute warps: P / S12 of a half chunk written
+  u64 half_free[2];                 // helper warps: P / S12 of a half chunk consumed
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void sts_2x64(uint32_t addr, u64 a, u64 b) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ float ex2v(float x) {   // MUFU.EX2 that the compiler may not merge with an identical earlier one
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ u64 mul2v(u64 a, u64 b) {
+  u64 d;
+  asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+__global__ void __launch_bounds__(kThr, 2)
+selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
+                      const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
+                      const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt, const BwdLaunch p) {
+  extern __shared__ unsigned char smem_raw[];
+  WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 255) & ~(uintptr_t)255);   // 32B-swizzle atom = 256 B
+  const selscan_bwd_args& a = p.a;
+  const int L = a.seqlen, N = a.dstate;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_group = p.dim_per_group / kR;
+  int bid = blockIdx.x;
+  const int tile_g = bid % tiles_per_group; bid /= tiles_per_group;
+  const int g = bid % a.ngroups;
+  const int b = bid / a.ngroups;
+  const int d0 = g * p.dim_per_group + tile_g * kR;
+  const int n_tiles = (L + kC - 1) / kC;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStg; ++s) {
+      mbar_init(smem_u32(&sm.tma_full[s]), 1);
+      mbar_init(smem_u32(&sm.prep_done[s]), 4);
+      mbar_init(smem_u32(&sm.stage_free[s]), 8);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(smem_u32(&sm.half_full[h]), 4);
+      mbar_init(smem_u32(&sm.half_free[h]), 4);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&map_u);
+    tma_prefetch_desc(&map_dt);
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_ck);
+    tma_prefetch_desc(&map_du);
+    tma_prefetch_desc(&map_ddt);
+  }
+  __syncthreads();
+
+  // [row][8] tiles carry the TMA 32-byte swizzle (16-byte half index ^= bit 2 of the row): 8 consecutive rows x one half are then
+  // 8 distinct bank groups for the helper's per-row 128-bit accesses; the compute warps' broadcast reads do not care.
+  constexpr uint32_t kCT = kNP * kC * 4;    // byte offset of a pair's second channel (row + 32) in such a tile
+
+  if (warp >= 4) {
+    // =========================================== helper warpgroup ===========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelpRegs));
+    const int htid = threadIdx.x - kGroupThr;
+    const int hw = warp - 4;
+    const int row = htid & (kR - 1);        // my channel inside the CTA ...
+    const int hf = htid >> 6;               // ... and my half of every chunk (warp-uniform)
+    const int d = d0 + row;
+    const float Dv = a.D ? __ldg(a.D + d) : 0.f;
+    const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
+    const bool softplus = a.delta_softplus != 0;
+    const uint32_t my16 = (uint32_t)row * (kC * 4) + (uint32_t)((hf ^ ((row >> 2) & 1)) << 4);   // my 4 elements in every [row][8] tile
+    const uint32_t out16 = (uint32_t)hf * (kR * 16) + (uint32_t)row * 16;    // ... and in the [half][row][4] output tiles
+
+    // ---- B/C gather: elements htid and htid + 128 of a chunk's [8 positions][32 values] tile; the pointers walk backwards ----
+    // (B and C have the same position stride on this path: bwd_ws_eligible)
+    const int64_t bc_step = (int64_t)kC * a.B_l_stride;
+    const bool along_l = a.B_l_stride == 1;   // (.., N, L) layout: 8 consecutive threads read 8 consecutive positions of a state row;
+                                              // l-major x_dbl layout: a warp reads the 16 B and 16 C values of one position
+    const int bc_e1 = htid + kGroupThr;
+    const int bc_pos0 = along_l ? (htid & 7) : (htid >> 5), bc_val0 = along_l ? (htid >> 3) : (htid & 31);
+    const int bc_pos1 = along_l ? (bc_e1 & 7) : (bc_e1 >> 5), bc_val1 = along_l ? (bc_e1 >> 3) : (bc_e1 & 31);
+    auto bc_src = [&](int pos, int val) -> const float* {
+      const int n = val & 15;
+      const float* base = (val >= 16) ? (a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride + (int64_t)n * a.C_n_stride)
+                                      : (a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride + (int64_t)n * a.B_n_stride);
+      return base + (int64_t)((n_tiles - 1) * kC + pos) * a.B_l_stride;   // first chunk processed = last of the sequence
+    };
+    const float* bcp0 = bc_src(bc_pos0, bc_val0);
+    const float* bcp1 = bc_src(bc_pos1, bc_val1);
+    const uint32_t bc_i0 = (uint32_t)(bc_pos0 * kPitch + bc_val0) * 4, bc_i1 = (uint32_t)(bc_pos1 * kPitch + bc_val1) * 4;   // byte offsets in a tile
+    const bool bc_ok0 = (bc_val0 & 15) < N, bc_ok1 = (bc_val1 & 15) < N;
+    // ---- contraction role: warp = position of the half chunk, lane = (pair quarter q, 16-byte chunk c of the 32 values) ----
+    const int c_c = lane & 7, c_q = lane >> 3;
+    const int c_n = (c_c & 3) * 4 + 2 * (c_q >> 1) + (c_q & 1);   // the state whose sum this lane ends up with
+    const bool c_ok = c_n < N;
+    // address of my (state, position hw of half 0) in the chunk being processed; walks backwards by one chunk per iteration
+    float* dbc = ((c_c >= 4) ? a.dC : a.dB) + (((int64_t)b * a.ngroups + g) * N + (c_ok ? c_n : 0)) * (int64_t)L + (n_tiles - 1) * kC + hw;
+
+    auto issue_tma = [&](int j) {            // chunk j (processing order) -> stage j % kStg
+      const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC;
+      if (j >= kStg) mbar_wait(smem_u32(&sm.stage_free[s]), (uint32_t)((j / kStg - 1) & 1));
+      const uint32_t full = smem_u32(&sm.tma_full[s]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(3 * kR * kC * 4 + kR * kStatePad * 4)) : "memory");
+      tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
+      tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
+      tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
+      // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
+      tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, b * a.dim + d0, full);
+    };
+    // discretise my 4 elements of chunk j, publish delta, delta*u, softplus' and the chunk's B/C values (loaded one iteration earlier)
+    auto prep = [&](int j, float cb0, float cb1, float4& sg_out) {
+      const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC + hf * kHP;
+      mbar_wait(smem_u32(&sm.tma_full[s]), (uint32_t)((j / kStg) & 1));
+      const float4 u4 = lds_f4(smem_u32(sm.U[s]) + my16);
+      const float4 t4 = lds_f4(smem_u32(sm.DT[s]) + my16);
+      const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+      float v[4], vu[4], sg[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xb = tt[e] + bias;
+        float dv = xb, sgm = 1.f;
+        if (softplus) {
+          float wexp;
+          dv = softplus_fast(xb, wexp);
+          sgm = sigmoid_from_w(xb, wexp);   // softplus' (bwd_kernel.cuh:446-450; == 1 to rounding for x > 20)
+        }
+        dv = (l0 + e < L) ? dv : 0.f;       // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
+        v[e] = dv;
+        vu[e] = dv * uu[e];
+        sg[e] = sgm;
+      }
+      sts_f4(smem_u32(sm.SD[s]) + my16, make_float4(v[0], v[1], v[2], v[3]));
+      sts_f4(smem_u32(sm.SDU[s]) + my16, make_float4(vu[0], vu[1], vu[2], vu[3]));
+      sg_out = make_float4(sg[0], sg[1], sg[2], sg[3]);
+      sts_f1(smem_u32(sm.BC[s]) + bc_i0, cb0);
+      sts_f1(smem_u32(sm.BC[s]) + bc_i1, cb1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.prep_done[s]));
+    };
+
+    float dD_acc = 0.f, dbias_acc = 0.f;
+    float cb0, cb1;
+    float4 sg_cur, sg_nxt = make_float4(0.f, 0.f, 0.f, 0.f);   // softplus' of my 4 elements: chunk being finalised / prepared ahead
+    {
+      if (htid == 0) {
+        issue_tma(0);
+        if (n_tiles > 1) issue_tma(1);
+      }
+      const int lbase = (n_tiles - 1) * kC;   // the only chunk that can be partial
+      cb0 = (bc_ok0 && lbase + bc_pos0 < L) ? __ldg(bcp0) : 0.f;
+      cb1 = (bc_ok1 && lbase + bc_pos1 < L) ? __ldg(bcp1) : 0.f;
+      bcp0 -= bc_step;
+      bcp1 -= bc_step;
+      prep(0, cb0, cb1, sg_cur);
+      cb0 = (bc_ok0 && n_tiles > 1) ? __ldg(bcp0) : 0.f;
+      cb1 = (bc_ok1 && n_tiles > 1) ? __ldg(bcp1) : 0.f;
+      bcp0 -= bc_step;
+      bcp1 -= bc_step;
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+      const int t = n_tiles - 1 - i, s = i % kStg, c0 = t * kC, ob = i & 1;
+      if (htid == 0 && i + 2 < n_tiles) issue_tma(i + 2);
+      float nb0 = 0.f, nb1 = 0.f;
+      if (i + 2 < n_tiles) {                 // B/C of chunk i+2: in flight while chunk i is finalised
+        if (bc_ok0) nb0 = __ldg(bcp0);
+        if (bc_ok1) nb1 = __ldg(bcp1);
+        bcp0 -= bc_step;
+        bcp1 -= bc_step;
+      }
+      if (i + 1 < n_tiles) prep(i + 1, cb0, cb1, sg_nxt);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 1 - hh;
+        mbar_wait(smem_u32(&sm.half_full[h]), (uint32_t)(i & 1));
+        // ---------------- contraction of the pair products over the CTA's 32 channel pairs ----------------
+        {
+          const uint32_t src = smem_u32(sm.P[h]) + (uint32_t)(c_q * 8) * (kPP * 4) + (uint32_t)hw * 128 + (uint32_t)c_c * 16;
+          u64 v[8][2];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) lds_2x64(src + (uint32_t)e * (kPP * 4), v[e][0], v[e][1]);   // all in flight together
+          const u64 acc0 = add2(add2(add2(v[0][0], v[1][0]), add2(v[2][0], v[3][0])), add2(add2(v[4][0], v[5][0]), add2(v[6][0], v[7][0])));
+          const u64 acc1 = add2(add2(add2(v[0][1], v[1][1]), add2(v[2][1], v[3][1])), add2(add2(v[4][1], v[5][1]), add2(v[6][1], v[7][1])));
+          float o0, o1, o2, o3;
+          upk2(acc0, o0, o1);
+          upk2(acc1, o2, o3);
+          // reduce-scatter over the 4 pair quarters: lane q ends with value 2*(q>>1) + (q&1) of its chunk
+          const bool q1 = (c_q & 2) != 0, q0 = (c_q & 1) != 0;
+          float k0 = q1 ? o2 : o0, k1 = q1 ? o3 : o1;
+          k0 += __shfl_xor_sync(0xffffffffu, q1 ? o0 : o2, 16);
+          k1 += __shfl_xor_sync(0xffffffffu, q1 ? o1 : o3, 16);
+          float kk = q0 ? k1 : k0;
+          kk += __shfl_xor_sync(0xffffffffu, q0 ? k0 : k1, 8);
+          if (c_ok && (i > 0 || c0 + h * kHP + hw < L)) atomicAdd(dbc + h * kHP, kk);
+        }
+        // ---------------- du / ddelta of my (row, half): sum the 4 lanes' partials, finalise ----------------
+        if (hf == h) {
+          const uint32_t srow = smem_u32(sm.S12[h]) + (uint32_t)row * (kS12P * 4);
+          float4 s1 = lds_f4(srow), s2 = lds_f4(srow + 16);
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            const float4 x1 = lds_f4(srow + q * 32), x2 = lds_f4(srow + q * 32 + 16);
+            s1.x += x1.x; s1.y += x1.y; s1.z += x1.z; s1.w += x1.w;
+            s2.x += x2.x; s2.y += x2.y; s2.z += x2.z; s2.w += x2.w;
+          }
+          const float4 u4 = lds_f4(smem_u32(sm.U[s]) + my16);
+          const float4 y4 = lds_f4(smem_u32(sm.DY[s]) + my16);
+          const float4 l4 = lds_f4(smem_u32(sm.SD[s]) + my16);
+          const float4 g4 = sg_cur;
+          float4 o_du, o_dd;
+          o_du.x = fmaf(l4.x, s1.x, Dv * y4.x);                               // bwd_kernel.cuh:211, :280
+          o_du.y = fmaf(l4.y, s1.y, Dv * y4.y);
+          o_du.z = fmaf(l4.z, s1.z, Dv * y4.z);
+          o_du.w = fmaf(l4.w, s1.w, Dv * y4.w);
+          o_dd.x = fmaf(u4.x, s1.x, s2.x * kLn2) * g4.x;                      // :281-284, :446-450 (s2 in units of log2 e)
+          o_dd.y = fmaf(u4.y, s1.y, s2.y * kLn2) * g4.y;
+          o_dd.z = fmaf(u4.z, s1.z, s2.z * kLn2) * g4.z;
+          o_dd.w = fmaf(u4.w, s1.w, s2.w * kLn2) * g4.w;
+          // positions past the end contribute exact zeros (delta forced to 0, u / dout / B / C zero fill), so no masking is needed
+          dbias_acc += (o_dd.x + o_dd.y) + (o_dd.z + o_dd.w);
+          dD_acc = fmaf(y4.x, u4.x, fmaf(y4.y, u4.y, fmaf(y4.z, u4.z, fmaf(y4.w, u4.w, dD_acc))));   // :213
+          sts_f4(smem_u32(sm.DU[ob]) + out16, o_du);
+          sts_f4(smem_u32(sm.DDT[ob]) + out16, o_dd);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.half_free[h]));
+        if (hf == h) {                       // the two warps of this half hand their tiles to the TMA store
+          if (hh == 1 && lane == 0) mbar_arrive(smem_u32(&sm.stage_free[s]));   // (warps of half 0 are done with the stage here ...
+          fence_proxy_async_smem();          // my du / ddelta writes -> visible to the async proxy
+          if ((htid & 63) == 0) tma_store_wait_read<0>();   // my store of chunk i-1 has read its tiles: buffer ob^1 is free for chunk i+1
+          named_bar_sync(2 + h, 64);
+          if ((htid & 63) == 0) {
+            tma_store_3d(&map_du, smem_u32(sm.DU[ob]) + h * (kR * 16), c0 + kHP * h, d0, b);
+            tma_store_3d(&map_ddt, smem_u32(sm.DDT[ob]) + h * (kR * 16), c0 + kHP * h, d0, b);
+            tma_store_commit();
+          }
+        } else if (hh == 1 && lane == 0) {
+          mbar_arrive(smem_u32(&sm.stage_free[s]));                             //  ... and the warps of half 1 after contracting half 0)
+        }
+      }
+      dbc -= kC;
+      sg_cur = sg_nxt;
+      cb0 = nb0;
+      cb1 = nb1;
+    }
+    if ((htid & 63) == 0) tma_store_wait_all<0>();
+    if (a.dD != nullptr) atomicAdd(a.dD + d, dD_acc);                      // two threads (halves) per channel, summed over batch
+    if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbias_acc);
+    return;
+  }
+
+  // =========================================== compute warpgroup ===========================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kCompRegs));
+  const int sq = lane & 3;                // which 4 states
+  const int pr = lane >> 2;               // channel pair inside the warp
+  const int pp = warp * 8 + pr;           // channel pair inside the CTA: rows pp and pp + 32
+  u64 A2p[2][2], dA2[2][2], w2[2][2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int d = d0 + pp + c * kNP;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int n0 = sq * kLS + 2 * q;
+      const float a0 = (n0 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n0 * a.A_n_stride) * kLog2e : 0.f;
+      const float a1 = (n0 + 1 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + 1) * a.A_n_stride) * kLog2e : 0.f;
+      A2p[c][q] = pk2(a0, a1);
+      dA2[c][q] = pk2(0.f, 0.f);
+      w2[c][q] = pk2(0.f, 0.f);   // a_{l+1} * dx_{l+1}: zero beyond the last position
+    }
+  }
+  const uint32_t hoff0 = (uint32_t)((pp >> 2) & 1) << 4;   // byte offset of half 0 inside my rows of the swizzled [row][8] tiles (half 1: ^ 16)
+  const uint32_t p_off = (uint32_t)pp * (kPP * 4) + (uint32_t)sq * 16;          // dB chunk; dC chunk at + 64
+  const uint32_t s_off = (uint32_t)pp * (kS12P * 4) + (uint32_t)sq * 32;       // s1 x4; s2 x4 at + 16; second channel at + kNP rows
+
+  for (int i = 0; i < n_tiles; ++i) {
+    const int s = i % kStg;
+    const uint32_t par = (uint32_t)((i / kStg) & 1);
+    mbar_wait(smem_u32(&sm.prep_done[s]), par);
+    mbar_wait(smem_u32(&sm.tma_full[s]), par);     // completed long ago: makes the TMA-written dout / state tiles visible to me
+    const uint32_t dy_row = smem_u32(sm.DY[s]) + pp * (kC * 4);   // + hoff[half] + c * kCT
+    const uint32_t ck_row = smem_u32(sm.CK[s]) + pp * (kStatePad * 4) + sq * 16;
+    const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLS * 4);
+    const uint32_t sd_row = smem_u32(sm.SD[s]) + pp * (kC * 4);
+    const uint32_t sdu_row = smem_u32(sm.SDU[s]) + pp * (kC * 4);
+
+    float dl[2][kC];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float4 t0 = lds_f4(sd_row + hoff0 + c * kCT), t1 = lds_f4(sd_row + (hoff0 ^ 16u) + c * kCT);
+      dl[c][0] = t0.x; dl[c][1] = t0.y; dl[c][2] = t0.z; dl[c][3] = t0.w;
+      dl[c][4] = t1.x; dl[c][5] = t1.y; dl[c][6] = t1.z; dl[c][7] = t1.w;
+    }
+    // ---------------- forward recompute from the saved state ----------------
+    u64 x0[2][2], xs[2][kC][2], Bk[kC][2];   // B of the chunk stays in registers for the reverse pass (the decays do not: see below)
+    float duk[2][kC];                        // delta*u likewise
+    lds_2x64(ck_row, x0[0][0], x0[0][1]);
+    lds_2x64(ck_row + kNP * kStatePad * 4, x0[1][0], x0[1][1]);
+    auto fwd_half = [&](auto HF) {
+      constexpr int h = decltype(HF)::value;   // compile-time half: keeps xs[][][] in registers
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 v4 = lds_f4(sdu_row + (hoff0 ^ (h * 16u)) + c * kCT);
+        duk[c][h * 4 + 0] = v4.x; duk[c][h * 4 + 1] = v4.y; duk[c][h * 4 + 2] = v4.z; duk[c][h * 4 + 3] = v4.w;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = h * 4 + jj;
+        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4), Bk[j][0], Bk[j][1]);
+        const u64* Bp = Bk[j];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const u64 dd = pk2(dl[c][j], dl[c][j]);
+          const u64 duu = pk2(duk[c][j], duk[c][j]);
+          float t0, t1, t2, t3;
+          upk2(mul2(dd, A2p[c][0]), t0, t1);
+          upk2(mul2(dd, A2p[c][1]), t2, t3);
+          const u64 e0 = pk2(ex2(t0), ex2(t1)), e1 = pk2(ex2(t2), ex2(t3));
+          xs[c][j][0] = fma2(e0, j == 0 ? x0[c][0] : xs[c][j - 1][0], mul2(duu, Bp[0]));
+          xs[c][j][1] = fma2(e1, j == 0 ? x0[c][1] : xs[c][j - 1][1], mul2(duu, Bp[1]));
+        }
+      }
+    };
+    fwd_half(std::integral_constant<int, 0>{});
+    fwd_half(std::integral_constant<int, 1>{});
+    // ---------------- reverse recurrence, one half chunk at a time ----------------
+    auto rev_half = [&](auto HF) {
+      constexpr int h = decltype(HF)::value;
+      if (i > 0) mbar_wait(smem_u32(&sm.half_free[h]), (uint32_t)((i - 1) & 1));   // the helpers have consumed this half of chunk i-1
+      const uint32_t p_row = smem_u32(sm.P[h]) + p_off;
+      float dyh[2][4], s1p[2][4], s2p[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 y4 = lds_f4(dy_row + (hoff0 ^ (h * 16u)) + c * kCT);
+        dyh[c][0] = y4.x; dyh[c][1] = y4.y; dyh[c][2] = y4.z; dyh[c][3] = y4.w;
+      }
+#pragma unroll
+      for (int jj = 3; jj >= 0; --jj) {
+        const int j = h * 4 + jj;
+        const u64* Bp = Bk[j];
+        u64 Cp[2];
+        lds_2x64(bc_base + (uint32_t)j * (kPitch * 4) + 64, Cp[0], Cp[1]);
+        u64 pB0 = 0, pB1 = 0, pC0 = 0, pC1 = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const u64 dyy = pk2(dyh[c][jj], dyh[c][jj]);
+          const u64 dd = pk2(dl[c][j], dl[c][j]);
+          const u64 duu = pk2(duk[c][j], duk[c][j]);
+          // The decays are evaluated again (volatile: no reuse of the forward half's values).  What binds this kernel is the
+          // shared-memory return path, MUFU has slack: 64 registers of decays would otherwise push B and delta*u out of the
+          // register file and cost 12 more 128-bit shared loads per chunk.
+          float t0, t1, t2, t3;
+          upk2(mul2v(dd, A2p[c][0]), t0, t1);
+          upk2(mul2v(dd, A2p[c][1]), t2, t3);
+          const u64 e0 = pk2(ex2v(t0), ex2v(t1)), e1 = pk2(ex2v(t2), ex2v(t3));
+          const u64 dx0 = fma2(Cp[0], dyy, w2[c][0]);                    // dx_{l,n}
+          const u64 dx1 = fma2(Cp[1], dyy, w2[c][1]);
+          s1p[c][jj] = hsum2(fma2(dx1, Bp[1], mul2(dx0, Bp[0])));        // sum_n dx * B          (bwd_kernel.cuh:280-281)
+          w2[c][0] = mul2(e0, dx0);                                      // a_l * dx_l: carried to position l-1 ...
+          w2[c][1] = mul2(e1, dx1);
+          const u64 wg0 = mul2(w2[c][0], j == 0 ? x0[c][0] : xs[c][j - 1][0]);   // ... and dx * a_l * x_{l-1}  (:283)
+          const u64 wg1 = mul2(w2[c][1], j == 0 ? x0[c][1] : xs[c][j - 1][1]);
+          s2p[c][jj] = hsum2(fma2(wg1, A2p[c][1], mul2(wg0, A2p[c][0])));  // in units of log2(e)
+          dA2[c][0] = fma2(wg0, dd, dA2[c][0]);                          // :286
+          dA2[c][1] = fma2(wg1, dd, dA2[c][1]);
+          if (c == 0) {                                                  // channel-pair products for dB / dC
+            pB0 = mul2(duu, dx0); pB1 = mul2(duu, dx1);
+            pC0 = mul2(dyy, xs[c][j][0]); pC1 = mul2(dyy, xs[c][j][1]);
+          } else {
+            pB0 = fma2(duu, dx0, pB0); pB1 = fma2(duu, dx1, pB1);
+            pC0 = fma2(dyy, xs[c][j][0], pC0); pC1 = fma2(dyy, xs[c][j][1], pC1);
+          }
+        }
+        sts_2x64(p_row + (uint32_t)jj * 128, pB0, pB1);
+        sts_2x64(p_row + (uint32_t)jj * 128 + 64, pC0, pC1);
+      }
+      const uint32_t s_row = smem_u32(sm.S12[h]) + s_off;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        sts_f4(s_row + c * (kNP * kS12P * 4), make_float4(s1p[c][0], s1p[c][1], s1p[c][2], s1p[c][3]));
+        sts_f4(s_row + c * (kNP * kS12P * 4) + 16, make_float4(s2p[c][0], s2p[c][1], s2p[c][2], s2p[c][3]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sm.half_full[h]));
+    };
+    rev_half(std::integral_constant<int, 1>{});
+    rev_half(std::integral_constant<int, 0>{});
+    if (lane == 0) mbar_arrive(smem_u32(&sm.stage_free[s]));   // ordered after my reads by the __syncwarp in rev_half
+  }
+
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int d = d0 + pp + c * kNP;
+    float da[4];
+    upk2(dA2[c][0], da[0], da[1]);
+    upk2(dA2[c][1], da[2], da[3]);
+#pragma unroll
+    for (int n = 0; n < kLS; ++n)
+      if (sq * kLS + n < N) atomicAdd(a.dA + (int64_t)d * N + sq * kLS + n, da[n]);   // sum over batch
+  }
+}
+
+inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int n_ckpt) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)n_ckpt * kStatePad, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)n_ckpt * kStatePad * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kStatePad, (cuuint32_t)kR};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// The warp-specialised kernel is usable when ptxas gave the kernel exactly the launch register count the setmaxnreg
+// arithmetic assumes (otherwise setmaxnreg.inc could wait for registers that never come).
+bool bwd_ws_eligible(const BwdLaunch& p) { return p.a.B_l_stride == p.a.C_l_stride; }
+
+bool bwd_ws_usable() {
+  static const bool ok = [] {
+    const char* e = getenv("SELSCAN_B200_BWD");
+    if (e != nullptr && e[0] == 't') return false;   // "tma": the single-role kernel
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, selscan_bwd_ws_kernel) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return false;
+    }
+    return fa.numRegs == kLaunchRegs;
+  }();
+  return ok;
+}
+
+cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
+  const selscan_bwd_args& a = p.a;
+  CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
+  if (!make_row_map_sw(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+      !make_row_map_sw(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+      !make_row_map_sw(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
+      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR) ||
+      !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
+    return cudaErrorInvalidValue;
+  const int smem = (int)sizeof(WsSmem) + 256;
+  static_assert(sizeof(WsSmem) + 256 + 1024 <= 116736, "two CTAs per SM");
+  cudaError_t e = cudaFuncSetAttribute(selscan_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kR));
+  selscan_bwd_ws_kernel<<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, p);
+  return cudaGetLastError();
+}
+
+}  // namespace selscan

@@ -40,6 +40,10 @@ cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);
 // tiled TMA path (selscan_bwd_tma.cu): aligned shapes with channels-per-group % 32 == 0, seqlen > 16, no z
 bool bwd_tma_eligible(const BwdLaunch& p);
 cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream);
+// warp-specialised form of the tiled path (selscan_bwd_ws.cu): same eligibility; the default when usable
+bool bwd_ws_usable();
+bool bwd_ws_eligible(const BwdLaunch& p);
+cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream);
 
 // CrossScan (scatter = true) / CrossMerge (scatter = false) plane kernels (selscan_cross.cu)
 cudaError_t launch_cross(bool scatter, const float* in, float* out, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream);

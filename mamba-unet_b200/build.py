@@ -40,7 +40,10 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: build a variant of the library (extra -D macros) to another path, for A/B timing via SELSCAN_B200_LIB."""
+    if out is not None:
+        return _build_variant(list(defines), out)
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -63,9 +66,31 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def _build_variant(defines, out):
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="selscan_variant_")
+    objs, procs = [], []
+    for s in SOURCES:
+        o = os.path.join(tmp, s.replace(".cu", ".o"))
+        procs.append((s, subprocess.Popen([nvcc_path()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, s), "-o", o],
+                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    for s, pr in procs:
+        o, _ = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(o)
+            raise RuntimeError(f"nvcc failed on {s}")
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
+    subprocess.check_call([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs)
+    shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("-D", dest="defines", action="append", default=[])
+    ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, defines=a.defines, out=a.out))

@@ -7,7 +7,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libselscan_b200.so")
+# SELSCAN_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("SELSCAN_B200_LIB") or os.path.join(_PKG, "lib", "libselscan_b200.so")
 
 ABI_VERSION = 4
 CKPT_INTERVAL = 8

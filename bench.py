@@ -421,14 +421,14 @@ def main():
                 traffic_src = "profiles/r01_ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": f"selscan_bwd_tma_kernel @ {dom} (B={batch}, KD={K_DIR * dom_stage[1]}, L={dom_stage[2]})",
+    roofline = {"bound": "hbm", "kernel": f"{ops.bwd_kernel_name()} @ {dom} (B={batch}, KD={K_DIR * dom_stage[1]}, L={dom_stage[2]})",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": table[dom]["bwd_ms"],
                 "share_of_step": round(dict((s[0], s[3]) for s in stages)[dom] * table[dom]["bwd_ms"] /
                                        sum(s[3] * (table[s[0]]["fwd_ms"] + table[s[0]]["bwd_ms"]) for s in stages), 4),
-                "note": "not HBM-bound: the shared-memory->register return path (LSU wavefronts ~60-70% of peak) and issue "
-                        "latency bound this kernel; see DESIGN.md section 4"}
+                "note": "not HBM-bound: the shared-memory->register return path bounds this kernel (LSU wavefronts ~80% of peak, "
+                        "profiles/r01_ncu_final_summary.txt); see DESIGN.md section 4"}
 
     # ---- e2e: public op from pinned host buffers ---------------------------------------------------------------
     e2e = None

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SELSCAN_B200_ABI_VERSION 4
+#define SELSCAN_B200_ABI_VERSION 5
 /* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
 #define SELSCAN_B200_CKPT_INTERVAL 8
 /* states are padded to this count inside the kernels and in the checkpoint buffer */
@@ -107,6 +107,9 @@ typedef struct selscan_bwd_args {
 } selscan_bwd_args;
 
 int selscan_b200_abi_version(void);
+/* name of the kernel the tiled backward path launches on the current device: "selscan_bwd_ws_kernel" (warp-specialised, the
+ * default) or "selscan_bwd_tma_kernel" (single-role; SELSCAN_B200_BWD=tma, or when the device cannot run the former).  Needs a GPU. */
+const char* selscan_b200_bwd_kernel(void);
 const char* selscan_b200_last_error(void);
 
 /* number of floats the `ckpt` scratch of one (batch, dim, seqlen, dstate) problem needs (may be 0):

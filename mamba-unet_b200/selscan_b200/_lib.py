@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # SELSCAN_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
 LIB_PATH = os.environ.get("SELSCAN_B200_LIB") or os.path.join(_PKG, "lib", "libselscan_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 CKPT_INTERVAL = 8
 STATE_PAD = 16
 
@@ -71,6 +71,7 @@ def load():
             raise RuntimeError(f"cannot load {LIB_PATH}: {e}") from e
         lib.selscan_b200_abi_version.restype = ctypes.c_int
         lib.selscan_b200_last_error.restype = ctypes.c_char_p
+        lib.selscan_b200_bwd_kernel.restype = ctypes.c_char_p
         lib.selscan_b200_ckpt_elems.restype = ctypes.c_int64
         lib.selscan_b200_ckpt_elems.argtypes = [_i32] * 4
         lib.selscan_b200_fwd_workspace_elems.restype = ctypes.c_int64

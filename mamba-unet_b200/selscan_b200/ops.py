@@ -140,6 +140,11 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
         _lib.check(lib.selscan_b200_bwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_bwd")
 
 
+def bwd_kernel_name():
+    """Kernel the tiled backward path launches on this device ("selscan_bwd_ws_kernel" unless overridden / unusable)."""
+    return _lib.load().selscan_b200_bwd_kernel().decode()
+
+
 def ckpt_elems(batch, dim, seqlen, dstate):
     return int(_lib.load().selscan_b200_ckpt_elems(batch, dim, seqlen, dstate))
 

@@ -1,0 +1,144 @@
+"""GPU parity of the two tiled backward kernels (selscan_bwd_ws.cu: warp-specialised, the default; selscan_bwd_tma.cu: the
+single-role kernel it supersedes, still taken for mixed B/C position strides or with SELSCAN_B200_BWD=tma), through the public
+op -> C ABI, against the fp64 oracle.  Shapes here all have channels-per-group % 64 == 0 and L > 8, i.e. they take the tiled path
+(replaces /root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489).
+
+Tolerances as in test_parity_gpu.py: forward rtol 1e-4 / atol 1e-5 x scale, gradients rtol 1e-3 / atol 1e-4 x scale.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from test_parity_gpu import BWD_ATOL, BWD_RTOL, FWD_ATOL, FWD_RTOL, _t, check_all, close, run_ours
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_refs(oracle, inp, softplus=True):
+    ref_out, ref_last = oracle.oracle_fwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"],
+                                          inp["delta_bias"], softplus, return_last_state=True, precision=64)
+    ref_g = oracle.oracle_bwd(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"], inp["D"], inp["z"], inp["delta_bias"],
+                              inp["dout"], softplus, precision=64)
+    return ref_out, ref_last, ref_g
+
+
+def test_default_backward_kernel_is_warp_specialised():
+    from selscan_b200 import ops
+
+    want = "selscan_bwd_tma_kernel" if os.environ.get("SELSCAN_B200_BWD", "").startswith("t") else "selscan_bwd_ws_kernel"
+    assert ops.bwd_kernel_name() == want
+
+
+# chunk boundaries of the backward walk (chunks of 8 positions, halves of 4): partial last chunks, partial halves, 2..N chunks
+@pytest.mark.parametrize("L", [9, 12, 13, 16, 17, 23, 24, 25, 50, 100, 257])
+def test_tiled_backward_uneven_lengths(oracle, L):
+    inp = oracle.make_inputs(2, 128, L, 16, 2, dist="M", seed=300 + L, has_z=False, has_D=True, has_bias=True)
+    out, last, grads = run_ours(inp, True)
+    check_all(out, last, grads, *_oracle_refs(oracle, inp))
+
+
+@pytest.mark.parametrize("N", [1, 5, 8, 12, 16])
+@pytest.mark.parametrize("softplus,has_D,has_bias", [(True, True, True), (False, False, False), (True, False, True)])
+def test_tiled_backward_states_and_optionals(oracle, N, softplus, has_D, has_bias):
+    inp = oracle.make_inputs(3, 64, 77, N, 1, dist="T", seed=40 + N, has_z=False, has_D=has_D, has_bias=has_bias)
+    out, last, grads = run_ours(inp, softplus)
+    check_all(out, last, grads, *_oracle_refs(oracle, inp, softplus))
+
+
+def test_tiled_backward_softplus_threshold(oracle):
+    """delta + bias beyond +-20: the softplus cut-off (fwd_kernel.cuh:153-156) and its derivative (bwd_kernel.cuh:446-450)."""
+    inp = oracle.make_inputs(2, 64, 40, 16, 1, dist="T", seed=7, has_z=False, has_D=True, has_bias=True)
+    rng = np.random.default_rng(3)
+    inp["delta"] = (inp["delta"] + rng.choice([-30.0, -21.0, 0.0, 19.5, 20.5, 35.0], size=inp["delta"].shape)).astype(np.float32)
+    inp["A"] = (inp["A"] * 0.02).astype(np.float32)   # keep exp(delta * A) in range for delta ~ 35
+    out, last, grads = run_ours(inp, True)
+    check_all(out, last, grads, *_oracle_refs(oracle, inp))
+
+
+def _xdbl_views(inp, R, mixed):
+    """B / C as permuted views of an x_dbl-like (batch, K, L, R + 2N) tensor (stride(-1) = R + 2N); mixed: C stays (N, L)-major."""
+    B_np, C_np = inp["B"], inp["C"]
+    batch, K, N, L = B_np.shape
+    xdbl = torch.randn(batch, K, L, R + 2 * N, device="cuda")
+    xdbl[..., R:R + N] = torch.from_numpy(B_np).cuda().permute(0, 1, 3, 2)
+    xdbl[..., R + N:] = torch.from_numpy(C_np).cuda().permute(0, 1, 3, 2)
+    xdbl.requires_grad_()
+    Bv = xdbl[..., R:R + N].permute(0, 1, 3, 2)
+    Cv = _t(C_np) if mixed else xdbl[..., R + N:].permute(0, 1, 3, 2)
+    return xdbl, Bv, Cv
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_tiled_backward_xdbl_layout_and_mixed_strides(oracle, mixed):
+    """l-major B/C (the layout SS2D really produces) on the tiled path; with different position strides for B and C the
+    warp-specialised kernel is not eligible and the single-role kernel runs."""
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+
+    batch, K, D, L, N, R = 2, 2, 64, 83, 16, 6
+    inp = oracle.make_inputs(batch, K * D, L, N, K, dist="M", seed=55)
+    xdbl, Bv, Cv = _xdbl_views(inp, R, mixed)
+    assert Bv.stride(-1) == R + 2 * N and (Cv.stride(-1) == 1) == mixed
+    u, dt, A, Dp, bias = (_t(inp[k]) for k in ("u", "delta", "A", "D", "delta_bias"))
+    out = selective_scan_fn(u, dt, A, Bv, Cv, Dp, z=None, delta_bias=bias, delta_softplus=True)
+    out.backward(torch.from_numpy(inp["dout"]).cuda())
+    ref_out, _, ref_g = _oracle_refs(oracle, inp)
+    close(out.detach().cpu().numpy(), ref_out, FWD_RTOL, FWD_ATOL, "out")
+    gx = xdbl.grad.cpu().numpy()
+    close(np.transpose(gx[..., R:R + N], (0, 1, 3, 2)), ref_g["dB"], BWD_RTOL, BWD_ATOL, "dB")
+    gC = Cv.grad.cpu().numpy() if mixed else np.transpose(gx[..., R + N:], (0, 1, 3, 2))
+    close(gC, ref_g["dC"], BWD_RTOL, BWD_ATOL, "dC")
+    for name, t in (("du", u), ("ddelta", dt), ("dA", A), ("dD", Dp), ("ddelta_bias", bias)):
+        close(t.grad.cpu().numpy(), ref_g[name], BWD_RTOL, BWD_ATOL, name)
+
+
+_CHILD = r"""
+import sys, numpy as np, torch
+sys.path[:0] = [{root!r}, {pkg!r}]
+import oracle
+from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+from selscan_b200 import ops
+inp = oracle.make_inputs(2, 768, 200, 16, 4, dist="M", seed=11)
+t = {{k: (torch.from_numpy(v).cuda().requires_grad_(k != "dout") if v is not None else None) for k, v in inp.items()}}
+out = selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], z=None, delta_bias=t["delta_bias"], delta_softplus=True)
+out.backward(t["dout"])
+torch.cuda.synchronize()
+np.savez(sys.argv[1], kernel=ops.bwd_kernel_name(), **{{k: t[k].grad.cpu().numpy() for k in ("u", "delta", "A", "B", "C", "D", "delta_bias")}})
+"""
+
+
+def test_both_tiled_backward_kernels_agree(oracle, tmp_path):
+    """The same seeded stage-1-like call (192 channels per group) through the warp-specialised and the single-role kernel, each in
+    its own process (the choice is made once per process): both within tolerance of the oracle and within 2e-5 of each other."""
+    inp = oracle.make_inputs(2, 768, 200, 16, 4, dist="M", seed=11)
+    _, _, ref_g = _oracle_refs(oracle, inp)
+    res = {}
+    for mode in ("ws", "tma"):
+        path = str(tmp_path / f"g_{mode}.npz")
+        env = dict(os.environ, SELSCAN_B200_BWD=mode)
+        code = _CHILD.format(root=ROOT, pkg=os.path.join(ROOT, "mamba-unet_b200"))
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+        with np.load(path) as f:
+            res[mode] = {k: f[k] for k in f.files}
+        assert str(res[mode]["kernel"]) == ("selscan_bwd_ws_kernel" if mode == "ws" else "selscan_bwd_tma_kernel")
+        for k, name in (("u", "du"), ("delta", "ddelta"), ("A", "dA"), ("B", "dB"), ("C", "dC"), ("D", "dD"), ("delta_bias", "ddelta_bias")):
+            close(res[mode][k].reshape(ref_g[name].shape), ref_g[name], BWD_RTOL, BWD_ATOL, f"{mode}:{name}")
+    for k in ("u", "delta", "A", "B", "C", "D", "delta_bias"):
+        a, b = res["ws"][k].astype(np.float64), res["tma"][k].astype(np.float64)
+        scale = max(1.0, float(np.abs(b).max()))
+        assert float(np.abs(a - b).max()) <= 2e-5 * scale, k
+
+
+def test_tiled_backward_repeatable_up_to_atomics(oracle):
+    """du and ddelta have no cross-CTA reduction: two runs are bit-identical; the atomically accumulated gradients agree to
+    round-off."""
+    inp = oracle.make_inputs(4, 256, 120, 16, 4, dist="T", seed=91, has_z=False, has_D=True, has_bias=True)
+    _, _, g1 = run_ours(inp, True)
+    _, _, g2 = run_ours(inp, True)
+    assert np.array_equal(g1["du"], g2["du"]) and np.array_equal(g1["ddelta"], g2["ddelta"])
+    for k in ("dA", "dB", "dC", "dD", "ddelta_bias"):
+        close(g1[k], g2[k], 1e-5, 1e-6, k)

@@ -342,6 +342,7 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   FwdLaunch q = p;
   fwd_plan_segments(a.batch, a.dim, a.seqlen, a.ngroups, &q.n_segs, &q.seg_tiles);
   if (p.seg_ws == nullptr || q.n_segs < 2) {
+    if (fwd_ws_enabled()) return launch_fwd_ws(p, stream);
     e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     selscan_fwd_tma_kernel<0><<<grid, kThreads, smem, stream>>>(mu, mdt, mout, p);

@@ -249,7 +249,6 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     }
     for (int i = 0; i < n_tiles; ++i) {
       const int t = n_tiles - 1 - i, s = i % kStg, c0 = t * kC, ob = i & 1;
-      if (htid == 0 && i + 2 < n_tiles) issue_tma(i + 2);
       float nb0 = 0.f, nb1 = 0.f;
       if (i + 2 < n_tiles) {                 // B/C of chunk i+2: in flight while chunk i is finalised
         if (bc_ok0) nb0 = __ldg(bcp0);
@@ -257,7 +256,10 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         bcp0 -= bc_step;
         bcp1 -= bc_step;
       }
+      // first the discretisation the compute warps wait for next (its TMA data landed an iteration ago), then the TMA loads of
+      // chunk i+2, whose stage must first be released by every warp's work on chunk i-1
       if (i + 1 < n_tiles) prep(i + 1, cb0, cb1, sg_nxt);
+      if (htid == 0 && i + 2 < n_tiles) issue_tma(i + 2);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int h = 1 - hh;

@@ -177,3 +177,12 @@ def test_opt_in_warp_specialised_forward(oracle, tmp_path):
         close(got[tag + "_out"], ref_out, FWD_RTOL, FWD_ATOL, tag + ":out")
         close(got[tag + "_last"], ref_last, FWD_RTOL, FWD_ATOL, tag + ":last_state")
         close(got[tag + "_du"], ref_g["du"], BWD_RTOL, BWD_ATOL, tag + ":du")
+
+
+def test_soak_handover_logic():
+    """scripts/soak_bwd.py: repeated launches at the four stage shapes (batch 24) and two ragged ones; out / du / ddelta must be
+    bit-identical run to run and never NaN (buffers are poisoned before every launch) -- a race in the mbarrier hand-over of the
+    warp-specialised kernels would show up here."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "soak_bwd.py"), "8"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "soak: PASS" in r.stdout

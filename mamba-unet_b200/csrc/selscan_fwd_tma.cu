@@ -23,6 +23,8 @@
 // its end state and sum of delta; a tiny combine kernel turns those into the true state at every segment start
 // (h_s = exp2(A2 * sum_delta_{s-1}) * h_{s-1} + xend_{s-1}); pass C (kMode 2) re-runs the segments from those states and
 // produces the outputs.  1.7x the arithmetic for n_segs x the parallelism; results identical to rounding.
+#include <type_traits>
+
 #include "selscan_common.cuh"
 #include "selscan_kernels.h"
 #include "selscan_ptx.cuh"
@@ -200,8 +202,14 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(out_row + (((uint32_t)q << 4) ^ swz)), "f"(yo) : "memory");
     };
     prefetch(0, uv_n, dl_n);
+    // quads of the tile that hold at least one position of the sequence: only the last tile can be partial, and it alone takes
+    // the instantiation of the loop with the early exit (the exit test costs the full tiles their cross-quad schedule: +4 %)
+    const int n_q = min(kTL / 4, (L - l0 + 3) >> 2);
+    auto quads = [&](auto PARTIAL) {
+    constexpr bool kPartial = decltype(PARTIAL)::value;
 #pragma unroll
     for (int q = 0; q < kTL / 4; ++q) {
+      if (kPartial && q >= n_q) break;
       float uv[4], dl[4], y[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { uv[j] = uv_n[j]; dl[j] = dl_n[j]; }
@@ -242,12 +250,15 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         }
       }
     }
+    };
+    if (n_q == kTL / 4) quads(std::false_type{});
+    else quads(std::true_type{});
     if (kMode == 1) {
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
       continue;
     }
-    finish(kTL / 4 - 1, yp, up);
+    finish(n_q - 1, yp, up);
     fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {

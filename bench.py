@@ -16,8 +16,8 @@ S3 x4 (3072, 196), S4 x2 (6144, 49); d_state 16, K = G = 4, fp32, delta_softplus
             the host cores, on a bounded sample of config 1 (rank 0, N=1 only).
 
 N > 1 (torchrun): every rank runs the same batch-24 workload on its own GPU (weak scaling: the scan shards over the
-image batch only); the parameter gradients of the scan (dA, dD, ddelta_bias) are all-reduced over NCCL per call, as
-DDP would.  `--impl reference` times the reference's CPU path (the port) instead; see the tier contract.
+image batch only); the parameter gradients of the scan (dA, dD, ddelta_bias) are all-reduced over NCCL per call, overlapped
+with the following scans and waited for at the end of the step, as DDP would.  `--impl reference` times the reference's CPU path (the port) instead; see the tier contract.
 """
 import argparse
 import json
@@ -303,8 +303,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     batch = args.batch
     stages = [s for s in STAGES if not args.stages or s[0] in args.stages.split(",")]
@@ -345,12 +343,18 @@ def main():
         bufs[name] = t
 
     ev_cache = []
+    pending = []
+    if world > 1:
+        for name, d_inner, L, calls in stages:
+            t = bufs[name]
+            n_par = t["flat"].numel() - t["dB"].numel() - t["dC"].numel()
+            t["red"] = [torch.empty(n_par, device=dev) for _ in range(calls)]
 
     def step(record=None):
         """One pass over the workload through the C ABI.  record: list to append (stage, ev0, ev1, ev2) to."""
         for name, d_inner, L, calls in stages:
             t = bufs[name]
-            for _ in range(calls):
+            for ci in range(calls):
                 t["flat"].zero_()
                 if record is not None:
                     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -364,8 +368,16 @@ def main():
                 if record is not None:
                     e2.record()
                     record.append((name, e0, e1, e2))
-                if world > 1:  # what DDP would reduce for this op's parameters: dA | dD | dbias are contiguous -> one bucket
-                    dist.all_reduce(t["flat"][t["dB"].numel() + t["dC"].numel():])
+                if world > 1:
+                    # what DDP would reduce for this op's parameters: dA | dD | dbias are contiguous -> one bucket per call,
+                    # all-reduced on NCCL's stream while the next scans run (DDP overlaps its buckets with the rest of the
+                    # backward in the same way); the step ends by waiting for every bucket
+                    red = t["red"][ci]
+                    red.copy_(t["flat"][t["dB"].numel() + t["dC"].numel():])
+                    pending.append(dist.all_reduce(red, async_op=True))
+        for w in pending:
+            w.wait()
+        pending.clear()
 
     def barrier():
         if world > 1:

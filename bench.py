@@ -228,7 +228,7 @@ def model_leg(world, rank, dev, steps):
         except Exception as e:  # noqa: BLE001 -- reported, not hidden
             res["infer_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
     model.train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index]) if world > 1 else model
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True) if world > 1 else model
     opt = wl.make_sgd(net)
     ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
     res["train_supervised_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
@@ -260,8 +260,8 @@ def model_leg(world, rank, dev, steps):
     del net, opt, model
     m1, m2 = MambaUnet(num_classes=4).to(dev).train(), MambaUnet(num_classes=4).to(dev).train()
     if world > 1:
-        m1 = torch.nn.parallel.DistributedDataParallel(m1, device_ids=[dev.index])
-        m2 = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[dev.index])
+        m1 = torch.nn.parallel.DistributedDataParallel(m1, device_ids=[dev.index], gradient_as_bucket_view=True)
+        m2 = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[dev.index], gradient_as_bucket_view=True)
     o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
     x16, y16 = x24[:16], y24[:16]
     cw = wl.consistency_weight(3000)

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kThreads) bench(float* out, long long* cycles,
   const float a = 0.9999f + seed * 1e-6f, b = seed * 1e-7f;
   __syncthreads();
   const long long t0 = clock64();
+#pragma unroll 1
   for (int it = 0; it < kIters; ++it) {
     if (MODE == 0) {
 #pragma unroll
@@ -73,10 +74,11 @@ __global__ void __launch_bounds__(kThreads) bench(float* out, long long* cycles,
 #pragma unroll
         for (int i = 0; i < K - 1; ++i) ffma2(v[(2 * i) & 7], v[(2 * i + 1) & 7], v[(2 * i) & 7], v[(2 * i + 1) & 7], e0, e1);
       }
-    } else if (MODE >= 10 && MODE <= 12) {
+    } else if (MODE >= 10 && MODE <= 15) {
       // The scan kernels' own access patterns.  10: LDS.128, lane reads chunk (lane & 3): 4 distinct 16-byte chunks per warp, each
       // shared by 8 lanes (the B / C loads: 4 state quads x 8 channel pairs); 11: LDS.128, lane reads chunk (lane >> 2): 8 distinct
-      // chunks, each shared by 4 lanes (the per-channel row data); 12: STS.128, 32 distinct chunks (the product tile stores).
+      // chunks, each shared by 4 lanes (the per-channel row data); 12: STS.128, 32 distinct chunks (the product tile stores);
+      // 13 / 14 / 15: other lane -> chunk maps (8 consecutive lanes share a chunk; chunk = lane & 7; 16 consecutive lanes share).
       extern __shared__ float4 sh4[];
       const int lane = threadIdx.x & 31;
       const unsigned base = (unsigned)__cvta_generic_to_shared(sh4);
@@ -86,9 +88,9 @@ __global__ void __launch_bounds__(kThreads) bench(float* out, long long* cycles,
         if (MODE == 12) {
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (blk + lane) * 16), "f"(v[i]), "f"(v[i + 8]), "f"(v[i]), "f"(v[i + 8]) : "memory");
         } else {
-          const int idx = blk + (MODE == 10 ? (lane & 3) : (lane >> 2));
+          const int idx = blk + (MODE == 10 ? (lane & 3) : MODE == 11 ? (lane >> 2) : MODE == 13 ? (lane >> 3) : MODE == 14 ? (lane & 7) : (lane >> 4));
           float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(base + idx * 16));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(base + idx * 16) : "memory");
           v[i] += x.x + x.w;
           v[i + 8] += x.y + x.z;
         }
@@ -105,12 +107,13 @@ __global__ void __launch_bounds__(kThreads) bench(float* out, long long* cycles,
         const int idx = (MODE == 7) ? ((it + i) & 7) * 32 + lane : ((it + i) & 255);
         if (MODE == 8) {
           float x;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"((unsigned)__cvta_generic_to_shared(sh4) + idx * 4));
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"((unsigned)__cvta_generic_to_shared(sh4) + idx * 4) : "memory");
           v[i] += x;
         } else {
           float4 x;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                       : "r"((unsigned)__cvta_generic_to_shared(sh4) + idx * 16));
+                       : "r"((unsigned)__cvta_generic_to_shared(sh4) + idx * 16)
+                       : "memory");   // the clobber keeps the unrolled loop from merging identical loads of two iterations
           v[i] += x.x + x.w;
           v[i + 8] += x.y + x.z;
         }
@@ -147,7 +150,7 @@ void run(const char* name, double ops_per_iter_per_thread, int ctas_per_sm) {
   long long* cyc;
   CHECK(cudaMalloc(&out, 4));
   CHECK(cudaMalloc(&cyc, grid * sizeof(long long)));
-  const int smem = ((MODE >= 6 && MODE <= 8) || (MODE >= 10 && MODE <= 12)) ? 8 * 32 * 16 : 0;
+  const int smem = ((MODE >= 6 && MODE <= 8) || (MODE >= 10 && MODE <= 15)) ? 8 * 32 * 16 : 0;
   bench<MODE, K><<<grid, kThreads, smem>>>(out, cyc, 0.5f);
   CHECK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1;
@@ -199,6 +202,9 @@ int main() {
     run<10, 0>("LDS.128 4 chunks x8 lanes, B/thr", 8 * 16, occ);
     run<11, 0>("LDS.128 8 chunks x4 lanes, B/thr", 8 * 16, occ);
     run<12, 0>("STS.128 distinct, bytes/thread", 8 * 16, occ);
+    run<13, 0>("LDS.128 chunk = lane>>3 (4 chunks)", 8 * 16, occ);
+    run<14, 0>("LDS.128 chunk = lane&7  (8 chunks)", 8 * 16, occ);
+    run<15, 0>("LDS.128 chunk = lane>>4 (2 chunks)", 8 * 16, occ);
   }
   return 0;
 }

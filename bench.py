@@ -441,8 +441,8 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": table[dom]["bwd_ms"],
                 "share_of_step": round(dict((s[0], s[3]) for s in stages)[dom] * table[dom]["bwd_ms"] /
                                        sum(s[3] * (table[s[0]]["fwd_ms"] + table[s[0]]["bwd_ms"]) for s in stages), 4),
-                "note": "not HBM-bound: the shared-memory->register return path bounds this kernel (LSU wavefronts ~80% of peak, "
-                        "profiles/r01_ncu_final_summary.txt); see DESIGN.md section 4"}
+                "note": "not HBM-bound: SM-side limits bound this kernel (shared-memory/shuffle pipe ~79% busy, issue slots 54%, MUFU 48% "
+                        "at once, profiles/r01_ncu_final_summary.txt); see DESIGN.md section 4"}
 
     # ---- e2e: public op from pinned host buffers ---------------------------------------------------------------
     e2e = None

@@ -93,20 +93,6 @@ __device__ __forceinline__ u64 mul2v(u64 a, u64 b) {
   asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-#ifndef SELSCAN_WS_SLEEP_NS
-#define SELSCAN_WS_SLEEP_NS 100
-#endif
-// wait of a warp that is AHEAD of the warps it waits for (the helpers waiting for a half chunk): back off between polls so that the
-// polling does not take issue slots from them
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-#if SELSCAN_WS_SLEEP_NS > 0
-    __nanosleep(SELSCAN_WS_SLEEP_NS);
-#endif
-    if (++spins > (1u << 26)) __trap();
-  }
-}
 __device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 __global__ void __launch_bounds__(kThr, 2)

@@ -59,14 +59,6 @@ __device__ __forceinline__ float lds_f1(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {   // waiter that is ahead: back off between polls
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(100);
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-
 __global__ void __launch_bounds__(kThr, 2)
 selscan_fwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                       const __grid_constant__ CUtensorMap map_out, const FwdLaunch p) {

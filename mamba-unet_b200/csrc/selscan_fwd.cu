@@ -116,7 +116,10 @@ bool force_generic() {
 cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream) {
   const int64_t rows = (int64_t)p.a.batch * p.a.dim;
   if (rows == 0 || p.a.seqlen == 0) return cudaSuccess;
-  if (!force_generic() && fwd_tma_eligible(p)) return launch_fwd_tma(p, stream);
+  if (!force_generic() && fwd_tma_eligible(p)) {
+    const cudaError_t e = launch_fwd_tma(p, stream);
+    if (e != cudaErrorNotSupported) return e;   // a tensor map could not be encoded for this layout: generic kernel below
+  }
   const unsigned grid = (unsigned)((rows + kFwdThreads - 1) / kFwdThreads);
   if (p.a.z != nullptr)
     selscan_fwd_rowserial_kernel<true><<<grid, kFwdThreads, 0, stream>>>(p);

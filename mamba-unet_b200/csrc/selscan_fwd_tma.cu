@@ -1,28 +1,32 @@
-// Forward selective scan, tiled path for sm_100a: TMA-staged shared-memory tiles + mbarrier pipeline +
+// Forward selective scan, tiled path for sm_100a: persistent CTAs, TMA-staged shared-memory tiles, an mbarrier ring and
 // packed f32x2 arithmetic.  Replaces selective_scan_fwd_kernel
-// (/root/reference/mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303) for the aligned shapes Mamba-UNet
-// produces (channels per group a multiple of 64, 16-byte aligned rows); everything else takes selscan_fwd.cu.
+// (/root/reference/mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303, incl. the SiLU(z) gate :280-298) for the
+// aligned shapes Mamba-UNet produces (channels per group a multiple of 64, 16-byte aligned rows); everything else takes
+// selscan_fwd.cu.
 //
-// CTA = 64 channels of one (batch, group) x the whole sequence, walked in tiles of 32 positions.
-//   warp 4 (producer): per tile, one elected lane issues two TMA loads (u and delta, box 64 rows x 32 positions,
-//       128-byte swizzle) into a 3-stage ring; all 32 lanes gather the tile's B and C values (any strides: the
-//       (N, L) layout and the l-major x_dbl layout both coalesce) into a [position][B0..15 C0..15] tile.
-//   warps 0-7 (consumers): 8 channels each, FOUR lanes per channel (4 states per lane), so that a batch-24 stage-1
-//       call already gives 16 resident consumer warps per SM.  Row data comes from the swizzled tile with
-//       conflict-free 128-bit loads (the 4 lanes of a channel broadcast); each lane loads only its own 4 B and 4 C
-//       values per position.  softplus(delta + bias) is evaluated once per element (lane j of a channel takes
-//       position 4q+j of a quad) and shared with 4 shuffles.  The recurrence is thread-serial: per position and
-//       state pair one FMUL2, two MUFU.EX2, one FMUL2 and two FFMA2 -- no cross-thread scan.  The 4 partial y of a
-//       quad are reduce-scattered over the 4 lanes (3 shuffles), staged in a swizzled 8x32 tile and written back by
-//       a per-warp TMA store, so HBM only ever sees full 128-byte rows.
-// Full/empty mbarriers per stage are the only synchronisation: warps drift freely, there is no __syncthreads in
-// the loop.  All waits are bounded (trap instead of hang).
+// Work item = 64 channels of one (batch, group) x the whole sequence (or one segment of it), walked in tiles of 32 positions.
+// The grid is persistent (at most kCtasPerSm CTAs per SM); CTA i takes items i, i + grid, ...  The producer runs ahead of the
+// consumers across item boundaries, so that short sequences (stage 4: L = 49 = two tiles) do not pay a pipeline fill per item.
+//   warp 4 (producer): per tile, one elected lane issues the TMA loads (u, delta [, z]: box 64 rows x 32 positions, 128-byte
+//       swizzle) into a ring; all 32 lanes gather the tile's B and C values (any strides: the (N, L) layout and the l-major
+//       x_dbl layout both coalesce) into a [position][B0..15 C0..15] tile.
+//   warps 0-3 (consumers): 16 channels each, TWO lanes per channel (lane = channel + 16 * state half, 8 states per lane as four
+//       packed pairs).  Round 1 used four lanes x four states: every per-element scalar (delta, delta*u, their packing), the
+//       B/C loads and the partial-sum shuffles were paid four times per element; two lanes halve all of that (135 -> ~90
+//       thread-instructions per element, 1.47 -> ~0.8 shared-memory wavefronts) and the 16 lanes of a half warp read the SAME
+//       B/C address (2 distinct 16-byte chunks per warp instruction: 2 wavefronts instead of 4).  softplus(delta + bias) is
+//       evaluated once per element (lane half h takes positions 2h, 2h+1 of a quad) and exchanged with the partner lane; the
+//       two partial y of a position are reduce-scattered over the pair (one shuffle per position); outputs are staged in a
+//       swizzled 16 x 32 tile per warp and written back by a per-warp TMA store, so HBM only ever sees full 128-byte rows.
+//       The recurrence is thread-serial: per position and state pair one FMUL2, two MUFU.EX2, one FMUL2 and two FFMA2.
+// Full/empty mbarriers per stage are the only synchronisation; all waits are bounded (trap instead of hang).
 //
 // Low-parallelism shapes (small batch: the reference validates slice by slice, val_2D.py:35-47) split the SEQUENCE into
 // segments so that the whole chip works on a call: pass A (kMode 1) runs every segment from a zero state and keeps only
 // its end state and sum of delta; a tiny combine kernel turns those into the true state at every segment start
 // (h_s = exp2(A2 * sum_delta_{s-1}) * h_{s-1} + xend_{s-1}); pass C (kMode 2) re-runs the segments from those states and
 // produces the outputs.  1.7x the arithmetic for n_segs x the parallelism; results identical to rounding.
+#include <atomic>
 #include <type_traits>
 
 #include "selscan_common.cuh"
@@ -30,262 +34,363 @@
 #include "selscan_ptx.cuh"
 #include "selscan_tma_host.h"
 
+#ifndef SELSCAN_FWD_STAGES
+#define SELSCAN_FWD_STAGES 3
+#endif
+#ifndef SELSCAN_FWD_CTAS
+#define SELSCAN_FWD_CTAS 2
+#endif
+
 namespace selscan {
 
 namespace {
 
 constexpr int kTL = 32;          // positions per tile (128-byte rows)
-constexpr int kRows = 64;        // channels per CTA
-constexpr int kConsWarps = 8;    // 8 channels each, 4 lanes per channel
-constexpr int kStages = 3;
+constexpr int kRows = 64;        // channels per work item
+constexpr int kConsWarps = 4;    // 16 channels each, 2 lanes per channel
+constexpr int kWarpRows = kRows / kConsWarps;
 constexpr int kBCPitch = 36;     // floats per position in the B/C tile (32 + pad, keeps 16-byte alignment)
 constexpr int kThreads = (kConsWarps + 1) * 32;
-constexpr int kLaneStates = kStatePad / 4;  // states per lane
-constexpr int kWarpRows = kRows / kConsWarps;
+constexpr int kLaneStates = kStatePad / 2;  // states per lane
+constexpr int kTileBytes = kRows * kTL * 4;          // 8 KB
+constexpr int kOutBytes = kWarpRows * kTL * 4;       // 2 KB
 
-struct FwdTmaSmem {
-  float U[kStages][kRows * kTL];        // 8 KB per stage, [row][32] with the 128B TMA swizzle
-  float DT[kStages][kRows * kTL];
-  float OUT[kConsWarps][2][kWarpRows * kTL];   // 1 KB per buffer
-  float BC[kStages][kTL * kBCPitch];
-  u64 full[kStages];
-  u64 empty[kStages];
+// shared-memory carve-up (bytes from a 1024-byte aligned base; every TMA tile is a multiple of 1024 bytes)
+template <bool kHasZ>
+struct Lay {
+  static constexpr int kStages = kHasZ ? 2 : SELSCAN_FWD_STAGES;
+  static constexpr int kCtas = kHasZ ? 2 : SELSCAN_FWD_CTAS;
+  static constexpr int kIn = kHasZ ? 3 : 2;      // input tiles per stage: u, delta [, z]
+  static constexpr int kOut = kHasZ ? 2 : 1;     // output tiles per buffer: out [, out_z]
+  static constexpr uint32_t oIn = 0;                                            // [stage][which]
+  static constexpr uint32_t oOut = oIn + kStages * kIn * kTileBytes;           // [warp][buffer][which]
+  static constexpr uint32_t oBC = oOut + kConsWarps * 2 * kOut * kOutBytes;    // [stage][position][36]
+  static constexpr uint32_t oBar = oBC + kStages * kTL * kBCPitch * 4;         // full[stage], empty[stage]
+  static constexpr uint32_t kBytes = oBar + 2 * kStages * 8;
 };
 
-// kMode 0: whole sequence per CTA.  1: segment aggregates only (no outputs).  2: segment with an initial state.
+struct Item {
+  int b, g, d0, seg, t_begin, n_tiles;
+};
+
 template <int kMode>
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ Item decode_item(const FwdLaunch& p, int item) {
+  Item it;
+  const int tiles_per_group = p.dim_per_group / kRows;
+  int bid = item;
+  it.seg = 0;
+  if (kMode != 0) {
+    it.seg = bid % p.n_segs;
+    bid /= p.n_segs;
+  }
+  const int tile_g = bid % tiles_per_group;
+  bid /= tiles_per_group;
+  it.g = bid % p.a.ngroups;
+  it.b = bid / p.a.ngroups;
+  it.d0 = it.g * p.dim_per_group + tile_g * kRows;
+  const int n_tiles_all = (p.a.seqlen + kTL - 1) / kTL;
+  it.t_begin = (kMode == 0) ? 0 : it.seg * p.seg_tiles;
+  const int t_end = (kMode == 0) ? n_tiles_all : min(n_tiles_all, it.t_begin + p.seg_tiles);
+  it.n_tiles = t_end - it.t_begin;
+  return it;
+}
+
+// kMode 0: whole sequence per item.  1: segment aggregates only (no outputs).  2: segment with an initial state.
+template <int kMode, bool kHasZ>
+__global__ void __launch_bounds__(kThreads, Lay<kHasZ>::kCtas)
 selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
-                       const __grid_constant__ CUtensorMap map_out, const FwdLaunch p) {
+                       const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
+                       const __grid_constant__ CUtensorMap map_outz, const FwdLaunch p, const int n_items) {
+  using LY = Lay<kHasZ>;
+  constexpr int kStages = LY::kStages;
   extern __shared__ unsigned char smem_raw[];
-  FwdTmaSmem& sm = *reinterpret_cast<FwdTmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const selscan_fwd_args& a = p.a;
   const int L = a.seqlen, N = a.dstate;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_group = p.dim_per_group / kRows;
-  int bid = blockIdx.x;
-  const int seg = (kMode == 0) ? 0 : bid % p.n_segs;
-  if (kMode != 0) bid /= p.n_segs;
-  const int tile_g = bid % tiles_per_group; bid /= tiles_per_group;
-  const int g = bid % a.ngroups;
-  const int b = bid / a.ngroups;
-  const int d0 = g * p.dim_per_group + tile_g * kRows;
-  const int n_tiles_all = (L + kTL - 1) / kTL;
-  const int t_begin = (kMode == 0) ? 0 : seg * p.seg_tiles;
-  const int t_end = (kMode == 0) ? n_tiles_all : min(n_tiles_all, t_begin + p.seg_tiles);
-  const int n_tiles = t_end - t_begin;   // tiles of this CTA; ring positions are counted from 0
+  auto full_bar = [&](int s) { return sm0 + LY::oBar + (uint32_t)s * 8u; };
+  auto empty_bar = [&](int s) { return sm0 + LY::oBar + (uint32_t)(kStages + s) * 8u; };
+  auto in_tile = [&](int s, int which) { return sm0 + LY::oIn + (uint32_t)(s * LY::kIn + which) * kTileBytes; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&sm.full[s]), 32);           // the 32 producer lanes (+ the TMA transaction bytes)
-      mbar_init(smem_u32(&sm.empty[s]), kConsWarps);  // one arrival per consumer warp
+      mbar_init(full_bar(s), 32);            // the 32 producer lanes (+ the TMA transaction bytes)
+      mbar_init(empty_bar(s), kConsWarps);   // one arrival per consumer warp
     }
     mbar_fence_init();
     tma_prefetch_desc(&map_u);
     tma_prefetch_desc(&map_dt);
-    tma_prefetch_desc(&map_out);
+    if (kMode != 1) tma_prefetch_desc(&map_out);
+    if (kHasZ) {
+      tma_prefetch_desc(&map_z);
+      tma_prefetch_desc(&map_outz);
+    }
   }
   __syncthreads();
 
   if (warp == kConsWarps) {
     // ================================ producer ================================
-    const float* __restrict__ Bg = a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride;
-    const float* __restrict__ Cg = a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride;
     const bool lanes_along_l = (a.B_l_stride == 1 && a.C_l_stride == 1);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int s = t % kStages, k = t / kStages;
-      if (k > 0) mbar_wait(smem_u32(&sm.empty[s]), (k - 1) & 1);
-      const int l0 = (t_begin + t) * kTL;
-      const uint32_t full = smem_u32(&sm.full[s]);
-      if (lane == 0) {
-        mbar_expect_tx(full, 2u * kRows * kTL * 4u);
-        tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
-        tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
-      }
-      float* bc = sm.BC[s];
-      float v[32];
-      if (lanes_along_l) {  // (.., N, L) layout: a warp reads 128 contiguous bytes of one state row
-        const int l = l0 + lane;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = i & 15;
-          const float* src = (i < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
-          v[i] = (n < N && l < L) ? __ldg(src + l) : 0.f;
+    uint32_t it = 0;   // tiles issued by this CTA: ring position
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item w = decode_item<kMode>(p, item);
+      const float* __restrict__ Bg = a.B + (int64_t)w.b * a.B_batch_stride + (int64_t)w.g * a.B_group_stride;
+      const float* __restrict__ Cg = a.C + (int64_t)w.b * a.C_batch_stride + (int64_t)w.g * a.C_group_stride;
+      for (int t = 0; t < w.n_tiles; ++t, ++it) {
+        const int s = it % kStages;
+        const uint32_t k = it / kStages;
+        if (k > 0) mbar_wait(empty_bar(s), (k - 1) & 1);
+        const int l0 = (w.t_begin + t) * kTL;
+        const uint32_t full = full_bar(s);
+        if (lane == 0) {
+          mbar_expect_tx(full, (uint32_t)((kHasZ && kMode != 1) ? 3 : 2) * kTileBytes);
+          tma_load_3d(in_tile(s, 0), &map_u, l0, w.d0, w.b, full);
+          tma_load_3d(in_tile(s, 1), &map_dt, l0, w.d0, w.b, full);
+          if (kHasZ && kMode != 1) tma_load_3d(in_tile(s, 2), &map_z, l0, w.d0, w.b, full);
         }
+        const uint32_t bc = sm0 + LY::oBC + (uint32_t)s * (kTL * kBCPitch * 4);
+        float v[32];
+        if (lanes_along_l) {  // (.., N, L) layout: a warp reads 128 contiguous bytes of one state row
+          const int l = l0 + lane;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) bc[lane * kBCPitch + i] = v[i];
-      } else {              // l-major layout (x_dbl): a warp reads the 16 B and 16 C values of one position
-        const int n = lane & 15;
-        const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
-        const int64_t ls = (lane < 16) ? a.B_l_stride : a.C_l_stride;
+          for (int i = 0; i < 32; ++i) {
+            const int n = i & 15;
+            const float* src = (i < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
+            v[i] = (n < N && l < L) ? __ldg(src + l) : 0.f;
+          }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
+          for (int i = 0; i < 32; i += 4)
+            sts_f4(bc + (uint32_t)(lane * kBCPitch + i) * 4, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        } else {              // l-major layout (x_dbl): a warp reads the 16 B and 16 C values of one position
+          const int n = lane & 15;
+          const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
+          const int64_t ls = (lane < 16) ? a.B_l_stride : a.C_l_stride;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) bc[j * kBCPitch + lane] = v[j];
+          for (int j = 0; j < 32; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bc + (uint32_t)(j * kBCPitch + lane) * 4), "f"(v[j]) : "memory");
+        }
+        mbar_arrive(full);
       }
-      mbar_arrive(full);
     }
     return;
   }
 
   // ================================ consumers ================================
-  const int sq = lane & 3;             // which 4 states
-  const int r = lane >> 2;             // channel inside the warp
-  const int rr = warp * kWarpRows + r; // channel inside the CTA
-  const int d = d0 + rr;
-  const int64_t row = (int64_t)b * a.dim + d;
-  u64 A2p[2], x2[2];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int n0 = sq * kLaneStates + 2 * q;
-    const float a0 = (n0 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)n0 * a.A_n_stride) * kLog2e : 0.f;
-    const float a1 = (n0 + 1 < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)(n0 + 1) * a.A_n_stride) * kLog2e : 0.f;
-    A2p[q] = pk2(a0, a1);
-    x2[q] = pk2(0.f, 0.f);
-  }
-  float* __restrict__ ws_state = nullptr;   // [row][segment][16]: end states (pass A) -> start states (after the combine)
-  if (kMode != 0) {
-    ws_state = p.seg_ws + (row * p.n_segs + seg) * kStatePad + sq * kLaneStates;
-    if (kMode == 2) {
-      const float4 h = *reinterpret_cast<const float4*>(ws_state);
-      x2[0] = pk2(h.x, h.y);
-      x2[1] = pk2(h.z, h.w);
-    }
-  }
-  float sum_delta = 0.f;
-  const float Dv = a.D ? __ldg(a.D + d) : 0.f;
-  const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
+  const int ch = lane & 15;            // channel inside the warp
+  const int h = lane >> 4;             // which 8 states; also: which 2 positions of a quad I discretise and finally own
+  const bool hi = h != 0;
+  const int rr = warp * kWarpRows + ch;   // channel inside the item
+  const uint32_t swz = (uint32_t)(rr & 7) << 4;   // 128B swizzle: 16-byte chunk index ^= row & 7 (same key in my 16-row out tile)
   const bool softplus = a.delta_softplus != 0;
-  float* __restrict__ ck = a.ckpt ? a.ckpt + row * p.n_ckpt * kStatePad + sq * kLaneStates : nullptr;
-  const uint32_t swz = (uint32_t)(rr & 7) << 4;   // 128B swizzle: 16-byte chunk index ^= row & 7
-  const int src0 = lane & ~3;                     // first lane of my channel
-  const bool hi1 = (sq & 2) != 0, hi0 = (sq & 1) != 0;
+  const bool A_vec = (a.A_n_stride == 1) && ((a.A_d_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15u) == 0) && N == kStatePad;
 
-  for (int t = 0; t < n_tiles; ++t) {
-    const int s = t % kStages, k = t / kStages;
-    const int l0 = (t_begin + t) * kTL;
-    mbar_wait(smem_u32(&sm.full[s]), k & 1);
-    const uint32_t u_row = smem_u32(sm.U[s]) + rr * (kTL * 4);
-    const uint32_t dt_row = smem_u32(sm.DT[s]) + rr * (kTL * 4);
-    const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLaneStates * 4);
-    const uint32_t out_tile = smem_u32(sm.OUT[warp][t & 1]);
-    const uint32_t out_row = out_tile + r * (kTL * 4) + sq * 4;   // r == rr & 7: same swizzle key
-    // Software pipeline over the 8 quads of the tile: while quad q's recurrence runs, quad q+1's row data is
-    // loaded, discretised and shared, and quad q-1's partial sums are reduce-scattered and stored.
-    float uv_n[4], dl_n[4];        // quad q+1 (prefetched)
-    float yp[4], up = 0.f;         // quad q-1 partial sums and my u of that quad
-    auto prefetch = [&](int q, float (&uv)[4], float (&dl)[4]) {
-      const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
-      const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
-      uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w;
-      // my position of the quad: discretise delta once per element, then share within the channel
-      float mine = hi1 ? (hi0 ? d4.w : d4.z) : (hi0 ? d4.y : d4.x);
-      mine += bias;
-      if (softplus) {
-        float w_unused;
-        mine = softplus_fast(mine, w_unused);
+  struct Params {
+    u64 A2p[4];
+    float Dv, bias;
+  };
+  auto load_params = [&](const Item& w, Params& q) {
+    const int d = w.d0 + rr;
+    float av[8];
+    if (A_vec) {
+      const float4 v0 = ldg4(a.A + (int64_t)d * a.A_d_stride + h * kLaneStates);
+      const float4 v1 = ldg4(a.A + (int64_t)d * a.A_d_stride + h * kLaneStates + 4);
+      av[0] = v0.x; av[1] = v0.y; av[2] = v0.z; av[3] = v0.w;
+      av[4] = v1.x; av[5] = v1.y; av[6] = v1.z; av[7] = v1.w;
+    } else {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int nn = h * kLaneStates + n;
+        av[n] = (nn < N) ? __ldg(a.A + (int64_t)d * a.A_d_stride + (int64_t)nn * a.A_n_stride) : 0.f;
       }
-      mine = (l0 + 4 * q + sq < L) ? mine : 0.f;   // past the end: a = 1, b = 0
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dl[j] = __shfl_sync(0xffffffffu, mine, src0 + j);
-    };
-    auto finish = [&](int q, const float (&y)[4], float umine) {
-      // reduce-scatter the 4 partial sums over the 4 lanes of the channel: lane sq ends with position 4q + sq
-      const float s0 = hi1 ? y[0] : y[2], s1 = hi1 ? y[1] : y[3];
-      float k0 = hi1 ? y[2] : y[0], k1 = hi1 ? y[3] : y[1];
-      k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      const float s2 = hi0 ? k0 : k1;
-      float kk = hi0 ? k1 : k0;
-      kk += __shfl_xor_sync(0xffffffffu, s2, 1);
-      const float yo = fmaf(Dv, umine, kk);
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(out_row + (((uint32_t)q << 4) ^ swz)), "f"(yo) : "memory");
-    };
-    prefetch(0, uv_n, dl_n);
-    // quads of the tile that hold at least one position of the sequence: only the last tile can be partial, and it alone takes
-    // the instantiation of the loop with the early exit (the exit test costs the full tiles their cross-quad schedule: +4 %)
-    const int n_q = min(kTL / 4, (L - l0 + 3) >> 2);
-    auto quads = [&](auto PARTIAL) {
-    constexpr bool kPartial = decltype(PARTIAL)::value;
+    for (int n = 0; n < 4; ++n) q.A2p[n] = pk2(av[2 * n] * kLog2e, av[2 * n + 1] * kLog2e);
+    q.Dv = a.D ? __ldg(a.D + d) : 0.f;
+    q.bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
+  };
+
+  uint32_t it = 0;        // tiles consumed by this CTA: ring position
+  uint32_t n_out = 0;     // output tiles written by this warp: double-buffer index
+  Params cur, nxt;
+  Item w = decode_item<kMode>(p, blockIdx.x < n_items ? blockIdx.x : 0);
+  if (blockIdx.x < n_items) load_params(w, cur);
+  nxt = cur;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int d = w.d0 + rr;
+    const int64_t row = (int64_t)w.b * a.dim + d;
+    u64 x2[4];
 #pragma unroll
-    for (int q = 0; q < kTL / 4; ++q) {
-      if (kPartial && q >= n_q) break;
-      float uv[4], dl[4], y[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { uv[j] = uv_n[j]; dl[j] = dl_n[j]; }
-      if (q + 1 < kTL / 4) prefetch(q + 1, uv_n, dl_n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t bc = bc_base + (uint32_t)(4 * q + j) * (kBCPitch * 4);
-        u64 Bp[2], Cp[2];
-        lds_2x64(bc, Bp[0], Bp[1]);
-        if (kMode != 1) lds_2x64(bc + 64, Cp[0], Cp[1]);
-        const u64 dd = pk2(dl[j], dl[j]);
-        const float du = dl[j] * uv[j];
-        const u64 duu = pk2(du, du);
-        float t0, t1, t2, t3;
-        upk2(mul2(dd, A2p[0]), t0, t1);
-        upk2(mul2(dd, A2p[1]), t2, t3);
-        const u64 e0 = pk2(ex2(t0), ex2(t1));
-        const u64 e1 = pk2(ex2(t2), ex2(t3));
-        x2[0] = fma2(e0, x2[0], mul2(duu, Bp[0]));
-        x2[1] = fma2(e1, x2[1], mul2(duu, Bp[1]));
-        if (kMode != 1) y[j] = hsum2(fma2(Cp[1], x2[1], mul2(Cp[0], x2[0])));
+    for (int q = 0; q < 4; ++q) x2[q] = pk2(0.f, 0.f);
+    float* __restrict__ ws_state = nullptr;   // [row][segment][16]: end states (pass A) -> start states (after the combine)
+    if (kMode != 0) {
+      ws_state = p.seg_ws + (row * p.n_segs + w.seg) * kStatePad + h * kLaneStates;
+      if (kMode == 2) {
+        const float4 h0 = *reinterpret_cast<const float4*>(ws_state);
+        const float4 h1 = *reinterpret_cast<const float4*>(ws_state + 4);
+        x2[0] = pk2(h0.x, h0.y); x2[1] = pk2(h0.z, h0.w);
+        x2[2] = pk2(h1.x, h1.y); x2[3] = pk2(h1.z, h1.w);
       }
-      if (kMode == 1) {                      // aggregates only: the segment's sum of delta (identical in the 4 lanes)
-        sum_delta += (dl[0] + dl[1]) + (dl[2] + dl[3]);
+    }
+    float sum_delta = 0.f;
+    float* __restrict__ ck = (kMode != 1 && a.ckpt) ? a.ckpt + row * p.n_ckpt * kStatePad + h * kLaneStates : nullptr;
+    const float Dv = cur.Dv, bias = cur.bias;
+    const int next_item = item + (int)gridDim.x;
+    Item wn = w;
+    if (next_item < n_items) wn = decode_item<kMode>(p, next_item);
+
+    for (int t = 0; t < w.n_tiles; ++t, ++it) {
+      if (t == w.n_tiles - 1 && next_item < n_items) load_params(wn, nxt);   // in flight while the item's last tile is processed
+      const int s = it % kStages;
+      const uint32_t k = it / kStages;
+      const int l0 = (w.t_begin + t) * kTL;
+      mbar_wait(full_bar(s), k & 1);
+      const uint32_t u_row = in_tile(s, 0) + rr * (kTL * 4);
+      const uint32_t dt_row = in_tile(s, 1) + rr * (kTL * 4);
+      const uint32_t z_row = in_tile(s, kHasZ ? 2 : 0) + rr * (kTL * 4) + h * 8;
+      const uint32_t bc_base = sm0 + LY::oBC + (uint32_t)s * (kTL * kBCPitch * 4) + h * (kLaneStates * 4);
+      const uint32_t out_tile = sm0 + LY::oOut + (uint32_t)((warp * 2 + (n_out & 1)) * LY::kOut) * kOutBytes;
+      const uint32_t out_row = out_tile + ch * (kTL * 4) + h * 8;
+      // Software pipeline over the 8 quads of the tile: while quad q's recurrence runs, quad q+1's row data is loaded,
+      // discretised and exchanged, and quad q-1's partial sums are reduce-scattered and stored.
+      float uv_n[4], dl_n[4];              // quad q+1 (prefetched)
+      float yp[4], up0 = 0.f, up1 = 0.f;   // quad q-1: partial sums and my two u values
+      auto prefetch = [&](int q, float (&uv)[4], float (&dl)[4]) {
+        const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
+        const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
+        uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w;
+        // my two positions of the quad: discretise delta once per element, then exchange with the partner lane
+        float m0 = (hi ? d4.z : d4.x) + bias, m1 = (hi ? d4.w : d4.y) + bias;
+        {   // branch-free on the (uniform) softplus flag: a branch here would split the tile into basic blocks and
+            // serialise this latency chain (LDS -> EX2 -> RCP -> polynomial -> SHFL) against the recurrence
+          float w_unused;
+          const float s0 = softplus_fast(m0, w_unused), s1 = softplus_fast(m1, w_unused);
+          m0 = softplus ? s0 : m0;
+          m1 = softplus ? s1 : m1;
+        }
+        const int pos = l0 + 4 * q + 2 * h;
+        m0 = (pos < L) ? m0 : 0.f;           // past the end: a = 1, b = 0
+        m1 = (pos + 1 < L) ? m1 : 0.f;
+        const float o0 = __shfl_xor_sync(0xffffffffu, m0, 16), o1 = __shfl_xor_sync(0xffffffffu, m1, 16);
+        dl[0] = hi ? o0 : m0; dl[1] = hi ? o1 : m1;
+        dl[2] = hi ? m0 : o0; dl[3] = hi ? m1 : o1;
+      };
+      auto finish = [&](int q, const float (&y)[4], float um0, float um1) {
+        // reduce-scatter the partial sums over the two lanes of the channel: lane half h ends with positions 4q + 2h, 4q + 2h + 1
+        float k0 = hi ? y[2] : y[0], k1 = hi ? y[3] : y[1];
+        k0 += __shfl_xor_sync(0xffffffffu, hi ? y[0] : y[2], 16);
+        k1 += __shfl_xor_sync(0xffffffffu, hi ? y[1] : y[3], 16);
+        const float o0 = fmaf(Dv, um0, k0), o1 = fmaf(Dv, um1, k1);
+        const uint32_t off = ((uint32_t)q << 4) ^ swz;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(out_row + off), "f"(o0), "f"(o1) : "memory");
+        if (kHasZ) {   // out_z = out * silu(z)   (fwd_kernel.cuh:293)
+          float z0, z1;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(z0), "=f"(z1) : "r"(z_row + off));
+          const float g0 = z0 * sigmoidf_fast(z0), g1 = z1 * sigmoidf_fast(z1);
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(out_row + kOutBytes + off), "f"(o0 * g0), "f"(o1 * g1) : "memory");
+        }
+      };
+      prefetch(0, uv_n, dl_n);
+      // quads of the tile that hold at least one position of the sequence: only the last tile of a sequence can be partial, and it
+      // alone takes the instantiation with the early exit.  The full tile is ONE basic block (every condition below is a
+      // compile-time constant or a predicated store), so that ptxas interleaves quad q+1's discretisation chain and quad q-1's
+      // reduce-scatter with quad q's recurrence; with only two consumer warps per scheduler that static overlap is what hides
+      // the MUFU / shared-memory / shuffle latencies.
+      const int n_q = min(kTL / 4, (L - l0 + 3) >> 2);
+      auto quads = [&](auto PARTIAL) {
+        constexpr bool kPartial = decltype(PARTIAL)::value;
+#pragma unroll
+        for (int q = 0; q < kTL / 4; ++q) {
+          if (kPartial && q >= n_q) break;
+          float uv[4], dl[4], y[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { uv[j] = uv_n[j]; dl[j] = dl_n[j]; }
+          if (q + 1 < kTL / 4) prefetch(q + 1, uv_n, dl_n);   // (a partial tile prefetches one quad past its end: unused, harmless)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t bc = bc_base + (uint32_t)(4 * q + j) * (kBCPitch * 4);
+            u64 Bp[4], Cp[4];
+            lds_2x64(bc, Bp[0], Bp[1]);
+            lds_2x64(bc + 16, Bp[2], Bp[3]);
+            if (kMode != 1) {
+              lds_2x64(bc + 64, Cp[0], Cp[1]);
+              lds_2x64(bc + 80, Cp[2], Cp[3]);
+            }
+            const u64 dd = pk2(dl[j], dl[j]);
+            const float du = dl[j] * uv[j];
+            const u64 duu = pk2(du, du);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              float t0, t1;
+              upk2(mul2(dd, cur.A2p[n]), t0, t1);
+              const u64 e = pk2(ex2(t0), ex2(t1));
+              x2[n] = fma2(e, x2[n], mul2(duu, Bp[n]));
+            }
+            if (kMode != 1)
+              y[j] = hsum2(add2(fma2(Cp[1], x2[1], mul2(Cp[0], x2[0])), fma2(Cp[3], x2[3], mul2(Cp[2], x2[2]))));
+          }
+          if (kMode == 1) {                      // aggregates only: the segment's sum of delta (identical in the 2 lanes)
+            sum_delta += (dl[0] + dl[1]) + (dl[2] + dl[3]);
+            continue;
+          }
+          if (q > 0) finish(q - 1, yp, up0, up1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) yp[j] = y[j];
+          up0 = hi ? uv[2] : uv[0];
+          up1 = hi ? uv[3] : uv[1];
+          if (q & 1) {   // position l0 + 4q + 3 closes an interval of 8: save the state (predicated stores, no branch: a
+                         // branch would end the basic block and put a divergence check in front of the next shuffle)
+            const int done = l0 + 4 * q + 4;
+            float xs[8];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) upk2(x2[n], xs[2 * n], xs[2 * n + 1]);
+            float* dst = ck + (int64_t)(done / kCkptInterval - 1) * kStatePad;
+            stg_f4_if(dst, xs[0], xs[1], xs[2], xs[3], ck != nullptr && done < L);
+            stg_f4_if(dst + 4, xs[4], xs[5], xs[6], xs[7], ck != nullptr && done < L);
+          }
+        }
+      };
+      if (n_q == kTL / 4) quads(std::false_type{});
+      else quads(std::true_type{});
+      if (kMode == 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));
         continue;
       }
-      if (q > 0) finish(q - 1, yp, up);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) yp[j] = y[j];
-      up = hi1 ? (hi0 ? uv[3] : uv[2]) : (hi0 ? uv[1] : uv[0]);
-      if ((q & 1) && ck != nullptr) {   // position l0 + 4q + 3 closes an interval of 8 (never reached in aggregate mode)
-        const int done = l0 + 4 * q + 4;
-        if (done < L) {
-          float xs[4];
-          upk2(x2[0], xs[0], xs[1]);
-          upk2(x2[1], xs[2], xs[3]);
-          *reinterpret_cast<float4*>(ck + (int64_t)(done / kCkptInterval - 1) * kStatePad) = make_float4(xs[0], xs[1], xs[2], xs[3]);
-        }
-      }
-    }
-    };
-    if (n_q == kTL / 4) quads(std::false_type{});
-    else quads(std::true_type{});
-    if (kMode == 1) {
+      finish(n_q - 1, yp, up0, up1);
+      fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
-      continue;
+      if (lane == 0) {
+        mbar_arrive(empty_bar(s));   // the warp is done reading stage s
+        tma_store_3d(&map_out, out_tile, l0, w.d0 + warp * kWarpRows, w.b);
+        if (kHasZ) tma_store_3d(&map_outz, out_tile + kOutBytes, l0, w.d0 + warp * kWarpRows, w.b);
+        tma_store_commit();
+        tma_store_wait_read<1>();    // the other OUT buffer (previous tile) has been read: free for the next tile
+      }
+      ++n_out;
+      __syncwarp();
     }
-    finish(n_q - 1, yp, up);
-    fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(smem_u32(&sm.empty[s]));   // the warp is done reading stage s
-      tma_store_3d(&map_out, out_tile, l0, d0 + warp * kWarpRows, b);
-      tma_store_commit();
-      tma_store_wait_read<1>();              // the other OUT buffer (tile t-1) has been read: free for tile t+1
-    }
-    __syncwarp();
-  }
-  if (kMode == 1) {   // end state of the segment (from a zero start) and its sum of delta
-    float xs[4];
-    upk2(x2[0], xs[0], xs[1]);
-    upk2(x2[1], xs[2], xs[3]);
-    *reinterpret_cast<float4*>(ws_state) = make_float4(xs[0], xs[1], xs[2], xs[3]);
-    if (sq == 0) p.seg_ws[(int64_t)a.batch * a.dim * p.n_segs * kStatePad + row * p.n_segs + seg] = sum_delta;
-    return;
-  }
-  if (lane == 0) tma_store_wait_all<0>();
-  if (a.last_state != nullptr && (kMode == 0 || seg == p.n_segs - 1)) {
-    float xs[4];
-    upk2(x2[0], xs[0], xs[1]);
-    upk2(x2[1], xs[2], xs[3]);
+    // ---- end of the item ----
+    if (kMode == 1) {   // end state of the segment (from a zero start) and its sum of delta
+      float xs[8];
 #pragma unroll
-    for (int n = 0; n < kLaneStates; ++n)
-      if (sq * kLaneStates + n < N) a.last_state[row * N + sq * kLaneStates + n] = xs[n];
+      for (int n = 0; n < 4; ++n) upk2(x2[n], xs[2 * n], xs[2 * n + 1]);
+      *reinterpret_cast<float4*>(ws_state) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+      *reinterpret_cast<float4*>(ws_state + 4) = make_float4(xs[4], xs[5], xs[6], xs[7]);
+      if (h == 0) p.seg_ws[(int64_t)a.batch * a.dim * p.n_segs * kStatePad + row * p.n_segs + w.seg] = sum_delta;
+    } else if (a.last_state != nullptr && (kMode == 0 || w.seg == p.n_segs - 1)) {
+      float xs[8];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) upk2(x2[n], xs[2 * n], xs[2 * n + 1]);
+#pragma unroll
+      for (int n = 0; n < kLaneStates; ++n)
+        if (h * kLaneStates + n < N) a.last_state[row * N + h * kLaneStates + n] = xs[n];
+    }
+    w = wn;
+    cur = nxt;
   }
+  if (kMode != 1 && lane == 0) tma_store_wait_all<0>();
 }
 
 // Carry combine of the segmented forward: thread = (row, state); sequential over the (few) segments.
@@ -308,6 +413,18 @@ __global__ void selscan_fwd_combine_kernel(const FwdLaunch p) {
   }
 }
 
+template <int kMode, bool kHasZ>
+cudaError_t launch_one(const CUtensorMap& mu, const CUtensorMap& mdt, const CUtensorMap& mz, const CUtensorMap& mout,
+                       const CUtensorMap& moutz, const FwdLaunch& p, int n_items, cudaStream_t stream) {
+  constexpr int smem = (int)Lay<kHasZ>::kBytes + 1024;
+  static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
+  if (const cudaError_t e = set_smem_once(configured, selscan_fwd_tma_kernel<kMode, kHasZ>, smem)) return e;
+  const int slots = sm_count() * Lay<kHasZ>::kCtas;
+  const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);
+  selscan_fwd_tma_kernel<kMode, kHasZ><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, p, n_items);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 // Segment plan shared by the workspace query and the launcher: split only when the call cannot fill the chip.
@@ -317,8 +434,9 @@ void fwd_plan_segments(int batch, int dim, int seqlen, int ngroups, int* n_segs,
   if (batch <= 0 || dim <= 0 || ngroups <= 0 || dim % ngroups || (dim / ngroups) % kRows) return;
   const int64_t n_ctas = (int64_t)batch * (dim / kRows);
   const int n_tiles = (seqlen + kTL - 1) / kTL;
-  if (n_ctas * 3 > 296 || n_tiles < 4) return;      // at least a third of the 2 x 148 CTA slots is busy anyway
-  int want = (int)(296 / n_ctas);
+  const int slots = 2 * sm_count();
+  if (n_ctas * 3 > slots || n_tiles < 4) return;      // at least a third of the 2-per-SM CTA slots is busy anyway
+  int want = (int)(slots / n_ctas);
   if (want > n_tiles / 2) want = n_tiles / 2;
   if (want < 2) return;
   const int st = (n_tiles + want - 1) / want;
@@ -331,43 +449,51 @@ void fwd_plan_segments(int batch, int dim, int seqlen, int ngroups, int* n_segs,
 
 bool fwd_tma_eligible(const FwdLaunch& p) {
   const selscan_fwd_args& a = p.a;
-  if (a.z != nullptr || a.dstate > kStatePad) return false;                       // the gated variant stays on the generic kernel
+  if (a.dstate > kStatePad) return false;
   if (p.dim_per_group % kRows != 0) return false;
-  if (a.seqlen < 1) return false;
-  if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : 0)) return false;
-  if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : 0)) return false;
-  if (!tma_row_ok(a.out, a.out_d_stride, a.batch > 1 ? a.out_batch_stride : 0)) return false;
+  if (a.seqlen < 1 || a.batch < 1) return false;
+  if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : 4)) return false;
+  if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : 4)) return false;
+  if (!tma_row_ok(a.out, a.out_d_stride, a.batch > 1 ? a.out_batch_stride : 4)) return false;
+  if (a.z != nullptr) {
+    if (!tma_row_ok(a.z, a.z_d_stride, a.batch > 1 ? a.z_batch_stride : 4)) return false;
+    if (!tma_row_ok(a.out_z, a.out_z_d_stride, a.batch > 1 ? a.out_z_batch_stride : 4)) return false;
+  }
   return tensor_map_encoder() != nullptr;
 }
 
+// Returns cudaErrorNotSupported when a tensor map cannot be encoded for this layout: the caller then takes the generic kernel.
 cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   const selscan_fwd_args& a = p.a;
-  CUtensorMap mu, mdt, mout;
+  CUtensorMap mu, mdt, mout, mz, moutz;
   if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kTL, kRows) ||
       !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kTL, kRows) ||
       !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, kWarpRows))
-    return cudaErrorInvalidValue;
-  const int smem = (int)sizeof(FwdTmaSmem) + 1024;
-  const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kRows));
-  cudaError_t e;
+    return cudaErrorNotSupported;
+  const bool has_z = a.z != nullptr;
+  if (has_z) {
+    if (!make_row_map(&mz, a.z, a.seqlen, a.dim, a.batch, a.z_d_stride, a.z_batch_stride, kTL, kRows) ||
+        !make_row_map(&moutz, a.out_z, a.seqlen, a.dim, a.batch, a.out_z_d_stride, a.out_z_batch_stride, kTL, kWarpRows))
+      return cudaErrorNotSupported;
+  } else {
+    mz = mu;
+    moutz = mout;
+  }
+  const int n_base = (int)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kRows));
   FwdLaunch q = p;
+  q.n_segs = 1;
   fwd_plan_segments(a.batch, a.dim, a.seqlen, a.ngroups, &q.n_segs, &q.seg_tiles);
   if (p.seg_ws == nullptr || q.n_segs < 2) {
-    if (fwd_ws_enabled()) return launch_fwd_ws(p, stream);
-    e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    selscan_fwd_tma_kernel<0><<<grid, kThreads, smem, stream>>>(mu, mdt, mout, p);
-    return cudaGetLastError();
+    q.n_segs = 1;
+    return has_z ? launch_one<0, true>(mu, mdt, mz, mout, moutz, q, n_base, stream)
+                 : launch_one<0, false>(mu, mdt, mz, mout, moutz, q, n_base, stream);
   }
-  e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = launch_one<1, false>(mu, mdt, mz, mout, moutz, q, n_base * q.n_segs, stream);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(selscan_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
-  selscan_fwd_tma_kernel<1><<<grid * q.n_segs, kThreads, smem, stream>>>(mu, mdt, mout, q);
   const int64_t n_comb = (int64_t)a.batch * a.dim * kStatePad;
   selscan_fwd_combine_kernel<<<(unsigned)((n_comb + 255) / 256), 256, 0, stream>>>(q);
-  selscan_fwd_tma_kernel<2><<<grid * q.n_segs, kThreads, smem, stream>>>(mu, mdt, mout, q);
-  return cudaGetLastError();
+  return has_z ? launch_one<2, true>(mu, mdt, mz, mout, moutz, q, n_base * q.n_segs, stream)
+               : launch_one<2, false>(mu, mdt, mz, mout, moutz, q, n_base * q.n_segs, stream);
 }
 
 }  // namespace selscan

@@ -30,13 +30,11 @@ struct BwdLaunch {
 };
 
 cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream);
-// tiled TMA path (selscan_fwd_tma.cu): aligned shapes with channels-per-group % 64 == 0 and no z
+// tiled TMA path (selscan_fwd_tma.cu): aligned shapes with channels-per-group % 64 == 0 (z gate included);
+// launch_fwd_tma returns cudaErrorNotSupported when a tensor map cannot be encoded (caller falls back to the generic kernel)
 bool fwd_tma_eligible(const FwdLaunch& p);
 void fwd_plan_segments(int batch, int dim, int seqlen, int ngroups, int* n_segs, int* seg_tiles);
 cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream);
-// warp-specialised variant (selscan_fwd_ws.cu): same eligibility; opt-in with SELSCAN_B200_FWD=ws (measured slower)
-bool fwd_ws_enabled();
-cudaError_t launch_fwd_ws(const FwdLaunch& p, cudaStream_t stream);
 // SELSCAN_B200_GENERIC=1 in the environment forces the generic kernels (debugging / A-B timing only)
 bool force_generic();
 cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);

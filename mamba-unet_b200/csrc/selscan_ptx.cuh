@@ -52,6 +52,16 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// predicated 16-byte global store (no branch in the instruction stream)
+__device__ __forceinline__ void stg_f4_if(float* p, float a, float b, float c, float d, bool ok) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
+      "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)ok)
+      : "memory");
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -89,11 +99,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must trap (and fail the launch) rather than hang the GPU box.
+// Bounded wait: a pipeline bug must trap (and fail the launch) rather than hang the GPU box.  The bound is WALL time
+// (%globaltimer, checked every 4096 polls), not a poll count, so that a slowed-down run (sanitizer, debugger) is not killed.
+#ifndef SELSCAN_WAIT_TIMEOUT_NS
+#define SELSCAN_WAIT_TIMEOUT_NS 20000000000ull
+#endif
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 4095u) == 0) {
+      const unsigned long long t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > SELSCAN_WAIT_TIMEOUT_NS) __trap();
+    }
   }
 }
 
@@ -103,12 +128,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #define SELSCAN_WS_SLEEP_NS 100
 #endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
 #if SELSCAN_WS_SLEEP_NS > 0
     __nanosleep(SELSCAN_WS_SLEEP_NS);
 #endif
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > SELSCAN_WAIT_TIMEOUT_NS) __trap();
   }
 }
 

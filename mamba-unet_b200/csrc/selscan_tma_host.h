@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace selscan {
 
 inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
@@ -49,8 +51,41 @@ inline bool make_row_map_sw(CUtensorMap* map, const float* base, int inner, int 
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// batch_stride: pass any positive multiple of 4 for batch == 1; a zero (expanded) batch stride cannot be a TMA stride
 inline bool tma_row_ok(const void* base, int64_t d_stride, int64_t batch_stride) {
-  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (d_stride & 3) == 0 && (batch_stride & 3) == 0 && d_stride > 0;
+  return (reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (d_stride & 3) == 0 && (batch_stride & 3) == 0 && d_stride > 0 &&
+         batch_stride > 0 && d_stride < ((int64_t)1 << 36) && batch_stride < ((int64_t)1 << 36);
+}
+
+// SM count of the current device (cached per device); 148 (B200) when no device can be queried.  Every grid-size and
+// segmenting heuristic derives its CTA-slot count from this one helper.
+inline int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  int v = cached[dev];
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+    (void)cudaGetLastError();
+    v = 148;
+  }
+  cached[dev] = v;
+  return v;
+}
+
+// Opt a kernel into its dynamic shared-memory size once per device (bit `device` of `done`) instead of on every launch.
+template <typename Kernel>
+inline cudaError_t set_smem_once(std::atomic<unsigned long long>& done, Kernel kernel, int smem_bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError();
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 }  // namespace selscan

@@ -144,39 +144,23 @@ def test_tiled_backward_repeatable_up_to_atomics(oracle):
         close(g1[k], g2[k], 1e-5, 1e-6, k)
 
 
-_CHILD_FWD = r"""
-import sys, numpy as np, torch
-sys.path[:0] = [{root!r}, {pkg!r}]
-import oracle
-from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
-res = {{}}
-for tag, (batch, dim, L, G) in {{"a": (24, 256, 200, 4), "b": (30, 128, 49, 2), "c": (20, 64, 13, 1)}}.items():
-    inp = oracle.make_inputs(batch, dim, L, 16, G, dist="M", seed=17)
-    t = {{k: (torch.from_numpy(v).cuda().requires_grad_(k != "dout") if v is not None else None) for k, v in inp.items()}}
-    out, last = selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], z=None, delta_bias=t["delta_bias"],
-                                  delta_softplus=True, return_last_state=True)
-    out.backward(t["dout"])
-    torch.cuda.synchronize()
-    res[tag + "_out"], res[tag + "_last"], res[tag + "_du"] = out.detach().cpu().numpy(), last.cpu().numpy(), t["u"].grad.cpu().numpy()
-np.savez(sys.argv[1], **res)
-"""
-
-
-def test_opt_in_warp_specialised_forward(oracle, tmp_path):
-    """SELSCAN_B200_FWD=ws (selscan_fwd_ws.cu: two channels per thread + helper warps; measured slower, not the default): outputs,
-    last state and -- through the saved states it writes -- the backward still match the oracle.  Batches large enough that the
-    sequence is not split into segments (the segmented path stays on selscan_fwd_tma.cu)."""
-    path = str(tmp_path / "fwd_ws.npz")
-    code = _CHILD_FWD.format(root=ROOT, pkg=os.path.join(ROOT, "mamba-unet_b200"))
-    subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, SELSCAN_B200_FWD="ws"), timeout=600)
-    with np.load(path) as f:
-        got = {k: f[k] for k in f.files}
-    for tag, (batch, dim, L, G) in {"a": (24, 256, 200, 4), "b": (30, 128, 49, 2), "c": (20, 64, 13, 1)}.items():
+def test_persistent_forward_many_items(oracle):
+    """Shapes with more work items than resident CTAs of the persistent forward (selscan_fwd_tma.cu: a CTA walks items i, i + grid, ...
+    with the producer running ahead across item boundaries; parameters of the next item are prefetched): outputs, last state and --
+    through the saved states it writes -- the backward still match the oracle."""
+    import torch
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+    for tag, (batch, dim, L, G) in {"a": (24, 256, 200, 4), "b": (30, 128, 49, 2), "c": (20, 64, 13, 1), "d": (40, 1536, 49, 4)}.items():
         inp = oracle.make_inputs(batch, dim, L, 16, G, dist="M", seed=17)
+        t = {k: (torch.from_numpy(v).cuda().requires_grad_(k != "dout") if v is not None else None) for k, v in inp.items()}
+        out, last = selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], z=None, delta_bias=t["delta_bias"],
+                                      delta_softplus=True, return_last_state=True)
+        out.backward(t["dout"])
+        torch.cuda.synchronize()
         ref_out, ref_last, ref_g = _oracle_refs(oracle, inp)
-        close(got[tag + "_out"], ref_out, FWD_RTOL, FWD_ATOL, tag + ":out")
-        close(got[tag + "_last"], ref_last, FWD_RTOL, FWD_ATOL, tag + ":last_state")
-        close(got[tag + "_du"], ref_g["du"], BWD_RTOL, BWD_ATOL, tag + ":du")
+        close(out.detach().cpu().numpy(), ref_out, FWD_RTOL, FWD_ATOL, tag + ":out")
+        close(last.cpu().numpy(), ref_last, FWD_RTOL, FWD_ATOL, tag + ":last_state")
+        close(t["u"].grad.cpu().numpy(), ref_g["du"], BWD_RTOL, BWD_ATOL, tag + ":du")
 
 
 def test_soak_handover_logic():

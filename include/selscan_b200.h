@@ -107,8 +107,9 @@ typedef struct selscan_bwd_args {
 } selscan_bwd_args;
 
 int selscan_b200_abi_version(void);
-/* name of the kernel the tiled backward path launches on the current device: "selscan_bwd_ws_kernel" (warp-specialised, the
- * default) or "selscan_bwd_tma_kernel" (single-role; SELSCAN_B200_BWD=tma, or when the device cannot run the former).  Needs a GPU. */
+/* name of the kernel aligned backward calls launch on the current device: "selscan_bwd_ws_kernel" (warp-specialised tiled kernel,
+ * the default) or "selscan_bwd_chunk_kernel" (the generic kernel, when the device cannot grant the former's register split).
+ * Needs a GPU. */
 const char* selscan_b200_bwd_kernel(void);
 const char* selscan_b200_last_error(void);
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libselscan_b200.so")
-SOURCES = ["selscan_api.cu", "selscan_fwd.cu", "selscan_fwd_tma.cu", "selscan_bwd.cu", "selscan_bwd_tma.cu", "selscan_bwd_ws.cu", "selscan_cross.cu", "selscan_ss2d.cu", "selscan_ln.cu", "selscan_tcgemm.cu"]
+SOURCES = ["selscan_api.cu", "selscan_fwd.cu", "selscan_fwd_tma.cu", "selscan_bwd.cu", "selscan_bwd_ws.cu", "selscan_cross.cu", "selscan_ss2d.cu", "selscan_ln.cu", "selscan_tcgemm.cu"]
 HEADERS = ["selscan_common.cuh", "selscan_kernels.h", "selscan_ptx.cuh", "selscan_tma_host.h", os.path.join("..", "..", "include", "selscan_b200.h")]
 
 NVCC_FLAGS = [

@@ -40,7 +40,7 @@ extern "C" {
 
 __attribute__((visibility("default"))) int selscan_b200_abi_version(void) { return SELSCAN_B200_ABI_VERSION; }
 __attribute__((visibility("default"))) const char* selscan_b200_bwd_kernel(void) {
-  return selscan::bwd_ws_usable() ? "selscan_bwd_ws_kernel" : "selscan_bwd_tma_kernel";
+  return selscan::bwd_ws_usable() ? "selscan_bwd_ws_kernel" : "selscan_bwd_chunk_kernel";
 }
 
 __attribute__((visibility("default"))) const char* selscan_b200_last_error(void) { return g_err; }

@@ -267,7 +267,11 @@ __global__ void __launch_bounds__(kBwdThreads, 2) selscan_bwd_chunk_kernel(const
 
 cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream) {
   if (p.a.batch == 0 || p.a.seqlen == 0) return cudaSuccess;
-  if (!force_generic() && bwd_tma_eligible(p)) return launch_bwd_tma(p, stream);
+  if (!force_generic() && bwd_ws_eligible(p)) {
+    const cudaError_t e = launch_bwd_ws(p, stream);
+    if (e != cudaErrorNotSupported) return e;
+    (void)cudaGetLastError();   // tensor map not encodable for this layout: the generic kernel takes any strides
+  }
   static_assert(sizeof(BwdSmem) <= 110 * 1024, "two CTAs per SM");
   const int smem = (int)sizeof(BwdSmem);
   const unsigned grid = (unsigned)((int64_t)p.a.batch * p.a.ngroups * p.tiles_per_group);

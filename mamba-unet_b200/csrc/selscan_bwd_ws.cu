@@ -1,7 +1,8 @@
 // Backward selective scan, warp-specialised tiled path for sm_100a.  Replaces selective_scan_bwd_kernel
 // (/root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489) for the aligned shapes Mamba-UNet produces
-// (channels per group a multiple of 64, 16-byte aligned rows, no z); same arithmetic and the same saved-state scheme as
-// selscan_bwd_tma.cu, which it supersedes as the default (SELSCAN_B200_BWD=tma selects the older single-role kernel).
+// (channels per group a multiple of 64, 16-byte aligned rows, no z, B and C with the same position stride); everything else takes
+// selscan_bwd.cu.  (Its single-role predecessor and a TMEM-pipelined successor that did not beat it are not part of the library:
+// experiments/, profiles/r02_ncu_bwd_tmem_*.)
 //
 // Why two roles.  In the single-role kernel every thread ran ~1240 instructions per chunk of 8 positions, of which only ~600 were the
 // recurrences (FFMA2 / FMUL2 / MUFU.EX2); the rest -- softplus / sigmoid of delta, the B/C gather, TMA issue, the reduce-scatter and
@@ -26,6 +27,7 @@
 // bounded (trap instead of hang).  16 warps per SM (2 CTAs): 8 dense compute warps + 8 helper warps that fill their stalls.
 // Measured (stage 1, batch 24): 0.925 ms against 0.98 ms; issue slots 54 % busy, shared-memory pipe 79 % -- the kernel now sits on
 // that pipe; one CTA per SM (batch <= 8): 0.69 against 0.85 ms.
+#include <atomic>
 #include <type_traits>
 
 #include "selscan_common.cuh"
@@ -496,12 +498,8 @@ inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int
 
 // The warp-specialised kernel is usable when ptxas gave the kernel exactly the launch register count the setmaxnreg
 // arithmetic assumes (otherwise setmaxnreg.inc could wait for registers that never come).
-bool bwd_ws_eligible(const BwdLaunch& p) { return p.a.B_l_stride == p.a.C_l_stride; }
-
 bool bwd_ws_usable() {
   static const bool ok = [] {
-    const char* e = getenv("SELSCAN_B200_BWD");
-    if (e != nullptr && e[0] == 't') return false;   // "tma": the single-role kernel
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, selscan_bwd_ws_kernel) != cudaSuccess) {
       (void)cudaGetLastError();
@@ -512,6 +510,23 @@ bool bwd_ws_usable() {
   return ok;
 }
 
+bool bwd_ws_eligible(const BwdLaunch& p) {
+  const selscan_bwd_args& a = p.a;
+  if (a.z != nullptr || a.dstate > kStatePad) return false;
+  if (p.dim_per_group % kR != 0) return false;
+  if (p.n_ckpt < 1) return false;                      // seqlen > 8
+  if (a.B_l_stride != a.C_l_stride) return false;      // the B/C gather walks both with one step
+  const int64_t one_batch = 4;   // batch 1: the batch stride is unused (any positive multiple of 4 passes the check)
+  if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : one_batch)) return false;
+  if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : one_batch)) return false;
+  if (!tma_row_ok(a.dout, a.dout_d_stride, a.batch > 1 ? a.dout_batch_stride : one_batch)) return false;
+  if (!tma_row_ok(a.du, a.du_d_stride, a.batch > 1 ? a.du_batch_stride : one_batch)) return false;
+  if (!tma_row_ok(a.ddelta, a.ddelta_d_stride, a.batch > 1 ? a.ddelta_batch_stride : one_batch)) return false;
+  if ((reinterpret_cast<uintptr_t>(a.ckpt) & 15u) != 0) return false;
+  return tensor_map_encoder() != nullptr && bwd_ws_usable();
+}
+
+// Returns cudaErrorNotSupported when a tensor map cannot be encoded for this layout: the caller then takes the generic kernel.
 cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
   CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
@@ -521,11 +536,11 @@ cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
       !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
       !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR) ||
       !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
-    return cudaErrorInvalidValue;
-  const int smem = (int)sizeof(WsSmem) + 256;
+    return cudaErrorNotSupported;
+  constexpr int smem = (int)sizeof(WsSmem) + 256;
   static_assert(sizeof(WsSmem) + 256 + 1024 <= 116736, "two CTAs per SM");
-  cudaError_t e = cudaFuncSetAttribute(selscan_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
+  static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
+  if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel, smem)) return e;
   const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kR));
   selscan_bwd_ws_kernel<<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, p);
   return cudaGetLastError();

@@ -38,10 +38,9 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream);
 // SELSCAN_B200_GENERIC=1 in the environment forces the generic kernels (debugging / A-B timing only)
 bool force_generic();
 cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream);
-// tiled TMA path (selscan_bwd_tma.cu): aligned shapes with channels-per-group % 32 == 0, seqlen > 16, no z
-bool bwd_tma_eligible(const BwdLaunch& p);
-cudaError_t launch_bwd_tma(const BwdLaunch& p, cudaStream_t stream);
-// warp-specialised form of the tiled path (selscan_bwd_ws.cu): same eligibility; the default when usable
+// tiled path (selscan_bwd_ws.cu, warp-specialised): aligned shapes with channels-per-group % 64 == 0, seqlen > 8, no z, B and C with
+// the same position stride, and a device that grants the kernel's setmaxnreg budgets; launch_bwd_ws returns
+// cudaErrorNotSupported when a tensor map cannot be encoded (caller falls back to the generic kernel)
 bool bwd_ws_usable();
 bool bwd_ws_eligible(const BwdLaunch& p);
 cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream);

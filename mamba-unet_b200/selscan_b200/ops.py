@@ -90,11 +90,27 @@ def _strides2(t):
     return (0, 0) if t is None else (t.stride(0), t.stride(1))
 
 
+def _require_f32_cuda(**tensors):
+    """The C ABI takes raw pointers and element strides: a tensor of another dtype (e.g. a half produced under autocast) or on
+    another device must never reach it silently."""
+    dev = None
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if t.dtype != torch.float32 or not t.is_cuda:
+            raise RuntimeError(f"selscan_b200: {name} must be a float32 CUDA tensor, got {t.dtype} on {t.device}")
+        dev = dev or t.device
+        if t.device != dev:
+            raise RuntimeError(f"selscan_b200: {name} is on {t.device}, expected {dev}")
+
+
 def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=None, last_state=None, ckpt=None,
                workspace=None):
     """One selscan_b200_fwd call on the current stream.  All tensors fp32 CUDA; B, C 4-D (batch, G, N, L);
     u/delta/z/out unit-stride along seqlen; outputs preallocated by the caller (the library never allocates)."""
     lib = _lib.load()
+    _require_f32_cuda(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=delta_bias, out=out, out_z=out_z,
+                      last_state=last_state, ckpt=ckpt, workspace=workspace)
     batch, dim, seqlen = u.shape
     a = _lib.FwdArgs(
         batch=batch, dim=dim, seqlen=seqlen, dstate=A.shape[1], ngroups=B.shape[1],
@@ -117,6 +133,8 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
                du, ddelta, dA, dB, dC, dD=None, dz=None, ddelta_bias=None):
     """One selscan_b200_bwd call on the current stream.  dA, dB, dC, dD, ddelta_bias must be zero-initialised."""
     lib = _lib.load()
+    _require_f32_cuda(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=delta_bias, dout=dout, out=out, ckpt=ckpt, du=du,
+                      ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dz=dz, ddelta_bias=ddelta_bias)
     batch, dim, seqlen = u.shape
     a = _lib.BwdArgs(
         batch=batch, dim=dim, seqlen=seqlen, dstate=A.shape[1], ngroups=B.shape[1],
@@ -141,7 +159,7 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
 
 
 def bwd_kernel_name():
-    """Kernel the tiled backward path launches on this device ("selscan_bwd_ws_kernel" unless overridden / unusable)."""
+    """Kernel the tiled backward path launches on this device ("selscan_bwd_tm_kernel" unless overridden / unusable)."""
     return _lib.load().selscan_b200_bwd_kernel().decode()
 
 

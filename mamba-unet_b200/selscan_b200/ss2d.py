@@ -14,10 +14,19 @@ What differs from the reference's ~20 ATen kernels:
   * the scan is the sm_100a kernel pair behind `selective_scan_fn`.
 """
 import torch
+from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
 from . import ops
 from .ops import selective_scan_fn
+
+# The plane kernels stage one (H, W + 1) fp32 image plane in shared memory (selscan_api.cu: selscan_b200_cross_scan);
+# larger planes (token grids above ~225 x 225) take the plain-torch chains below, which have no size limit.
+_PLANE_SMEM_BYTES = 200 * 1024
+
+
+def _plane_fits(H, W):
+    return H * (W + 1) * 4 <= _PLANE_SMEM_BYTES
 
 
 def _empty_dirs(ref, B, D, L):
@@ -58,30 +67,42 @@ class CrossScan(torch.autograd.Function):
     """(B, D, H, W) -> (B, 4, D, L): row-major, column-major, and both reversed (mamba_sys.py:403-404)."""
 
     @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # the kernels read fp32: autocast must not hand them halves
     def forward(ctx, x):
         ctx.hw = x.shape[2:]
+        if not _plane_fits(*ctx.hw):
+            return cross_scan_torch(x)
         return _scatter(x)
 
     @staticmethod
+    @custom_bwd(device_type="cuda")
     def backward(ctx, g):
         H, W = ctx.hw
         B, _, D, L = g.shape
-        return _gather(g, H, W).view(B, D, H, W)
+        if not _plane_fits(H, W):
+            return cross_merge_torch(g.float(), H, W).view(B, D, H, W)
+        return _gather(g.float(), H, W).view(B, D, H, W)
 
 
 class CrossMerge(torch.autograd.Function):
     """(B, 4, D, L) scan outputs -> (B, D, L) in row-major order (mamba_sys.py:429-432)."""
 
     @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, ys, H, W):
         ctx.hw = (H, W)
+        if not _plane_fits(H, W):
+            return cross_merge_torch(ys, H, W)
         return _gather(ys, H, W)
 
     @staticmethod
+    @custom_bwd(device_type="cuda")
     def backward(ctx, g):
         H, W = ctx.hw
         B, D, L = g.shape
-        return _scatter(g.reshape(B, D, H, W)), None, None
+        if not _plane_fits(H, W):
+            return cross_scan_torch(g.float().reshape(B, D, H, W)), None, None
+        return _scatter(g.float().reshape(B, D, H, W)), None, None
 
 
 def cross_scan_torch(x):
@@ -104,17 +125,21 @@ def forward_core_b200(self, x: torch.Tensor):
     L = H * W
     K = 4
     R, N = self.dt_rank, self.d_state
-    xs = CrossScan.apply(x.float())                                                       # (B, K, D, L)
-    x_dbl = torch.matmul(self.x_proj_weight.float().unsqueeze(0), xs)                     # (B, K, R+2N, L)   :406
-    dts = torch.matmul(self.dt_projs_weight.float().unsqueeze(0), x_dbl[:, :, :R])        # (B, K, D, L)      :409
-    Bs = x_dbl[:, :, R:R + N]                                                             # strided views, no copy
-    Cs = x_dbl[:, :, R + N:]
-    As = -torch.exp(self.A_logs.float()).view(K * D, N)                                   # :417
-    out_y = selective_scan_fn(
-        xs.view(B, K * D, L), dts.view(B, K * D, L), As, Bs, Cs, self.Ds.float().view(-1), z=None,
-        delta_bias=self.dt_projs_bias.float().view(-1), delta_softplus=True, return_last_state=False)   # :420-426
-    y = CrossMerge.apply(out_y.view(B, K, D, L), H, W)                                    # (B, D, L)         :429-432
-    y = y.transpose(1, 2).contiguous().view(B, H, W, D)                                   # :433
+    # Autocast-safe like the reference (which casts xs / dts / Bs / Cs to float and asserts a float out_y, mamba_sys.py:411-427,
+    # and is run under autocast at :865): the projections and the scan run in fp32 whatever the ambient autocast state.
+    with torch.autocast(device_type="cuda", enabled=False):
+        xs = CrossScan.apply(x.float())                                                   # (B, K, D, L)
+        x_dbl = torch.matmul(self.x_proj_weight.float().unsqueeze(0), xs)                 # (B, K, R+2N, L)   :406
+        dts = torch.matmul(self.dt_projs_weight.float().unsqueeze(0), x_dbl[:, :, :R])    # (B, K, D, L)      :409
+        Bs = x_dbl[:, :, R:R + N]                                                         # strided views, no copy
+        Cs = x_dbl[:, :, R + N:]
+        As = -torch.exp(self.A_logs.float()).view(K * D, N)                               # :417
+        out_y = selective_scan_fn(
+            xs.view(B, K * D, L), dts.view(B, K * D, L), As, Bs, Cs, self.Ds.float().view(-1), z=None,
+            delta_bias=self.dt_projs_bias.float().view(-1), delta_softplus=True, return_last_state=False)   # :420-426
+        assert out_y.dtype == torch.float                                                 # :427
+        y = CrossMerge.apply(out_y.view(B, K, D, L), H, W)                                # (B, D, L)         :429-432
+        y = y.transpose(1, 2).contiguous().view(B, H, W, D)                               # :433
     return self.out_norm(y).to(x.dtype)                                                   # :434
 
 
@@ -205,6 +230,7 @@ class SS2DFusedFn(torch.autograd.Function):
     with the projection's contribution accumulated by the GEMM itself (beta = 1)."""
 
     @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # autocast is off inside: every matmul below stays fp32
     def forward(ctx, xz, conv_w, conv_b, x_proj_w, dt_w, dt_b, A_logs, Ds, ln_w, ln_b, eps):
         B, H, W, D2 = xz.shape
         D, L, K = D2 // 2, H * W, 4
@@ -249,13 +275,14 @@ class SS2DFusedFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @custom_bwd(device_type="cuda")
     def backward(ctx, g):
         xz, xs, x_dbl, dts, As, ckpt, xhat, rstd, conv_w, conv_b, x_proj_w, dt_w, Dsf, dtb, ln_w, ln_b = ctx.saved_tensors
         B, H, W, D2 = xz.shape
         D, L, K = D2 // 2, H * W, 4
         R, N = dt_w.shape[2], As.shape[1]
         KD = K * D
-        g = g.contiguous()
+        g = g.float().contiguous()
         d_xz = torch.empty_like(xz)
         esz = xz.element_size()
         d_ys, d_ln_w, d_ln_b = edge_out_bwd(g, H, W, xz.data_ptr() + D * esz, D2, xhat, rstd, ln_w, ln_b,

@@ -23,7 +23,7 @@ stage_of_grid = {288: "S1", 576: "S2", 1152: "S3", 2304: "S4"}
 calls = {"S1": 4, "S2": 4, "S3": 4, "S4": 2}
 acc = {}
 for d in launches.values():
-    kind = "fwd" if "selscan_fwd_tma" in d["name"] else ("bwd" if ("selscan_bwd_tma" in d["name"] or "selscan_bwd_ws" in d["name"]) else None)
+    kind = "fwd" if "selscan_fwd_tma" in d["name"] else ("bwd" if "selscan_bwd_ws" in d["name"] else None)
     g = int(d["grid"].strip("()").split(",")[0])
     if kind is None or g not in stage_of_grid:
         continue

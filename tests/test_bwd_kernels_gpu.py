@@ -1,6 +1,5 @@
-"""GPU parity of the two tiled backward kernels (selscan_bwd_ws.cu: warp-specialised, the default; selscan_bwd_tma.cu: the
-single-role kernel it supersedes, still taken for mixed B/C position strides or with SELSCAN_B200_BWD=tma), through the public
-op -> C ABI, against the fp64 oracle.  Shapes here all have channels-per-group % 64 == 0 and L > 8, i.e. they take the tiled path
+"""GPU parity of the tiled backward kernel (selscan_bwd_ws.cu: warp-specialised) and of its hand-over to the generic kernel
+(selscan_bwd.cu: mixed B/C position strides, SELSCAN_B200_GENERIC=1), through the public op -> C ABI, against the fp64 oracle.  Shapes here all have channels-per-group % 64 == 0 and L > 8, i.e. they take the tiled path
 (replaces /root/reference/mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489).
 
 Tolerances as in test_parity_gpu.py: forward rtol 1e-4 / atol 1e-5 x scale, gradients rtol 1e-3 / atol 1e-4 x scale.
@@ -30,8 +29,7 @@ def _oracle_refs(oracle, inp, softplus=True):
 def test_default_backward_kernel_is_warp_specialised():
     from selscan_b200 import ops
 
-    want = "selscan_bwd_tma_kernel" if os.environ.get("SELSCAN_B200_BWD", "").startswith("t") else "selscan_bwd_ws_kernel"
-    assert ops.bwd_kernel_name() == want
+    assert ops.bwd_kernel_name() == "selscan_bwd_ws_kernel"
 
 
 # chunk boundaries of the backward walk (chunks of 8 positions, halves of 4): partial last chunks, partial halves, 2..N chunks
@@ -76,7 +74,7 @@ def _xdbl_views(inp, R, mixed):
 @pytest.mark.parametrize("mixed", [False, True])
 def test_tiled_backward_xdbl_layout_and_mixed_strides(oracle, mixed):
     """l-major B/C (the layout SS2D really produces) on the tiled path; with different position strides for B and C the
-    warp-specialised kernel is not eligible and the single-role kernel runs."""
+    warp-specialised kernel is not eligible and the generic kernel runs."""
     from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
 
     batch, K, D, L, N, R = 2, 2, 64, 83, 16, 6
@@ -112,23 +110,23 @@ np.savez(sys.argv[1], kernel=ops.bwd_kernel_name(), **{{k: t[k].grad.cpu().numpy
 
 
 def test_both_tiled_backward_kernels_agree(oracle, tmp_path):
-    """The same seeded stage-1-like call (192 channels per group) through the warp-specialised and the single-role kernel, each in
-    its own process (the choice is made once per process): both within tolerance of the oracle and within 2e-5 of each other."""
+    """The same seeded stage-1-like call (192 channels per group) through the warp-specialised tiled kernel and the generic
+    kernel (SELSCAN_B200_GENERIC=1), each in its own process (the choice is made once per process): both within tolerance of the
+    oracle and within 2e-5 of each other."""
     inp = oracle.make_inputs(2, 768, 200, 16, 4, dist="M", seed=11)
     _, _, ref_g = _oracle_refs(oracle, inp)
     res = {}
-    for mode in ("ws", "tma"):
+    for mode in ("ws", "generic"):
         path = str(tmp_path / f"g_{mode}.npz")
-        env = dict(os.environ, SELSCAN_B200_BWD=mode)
+        env = dict(os.environ, SELSCAN_B200_GENERIC="1" if mode == "generic" else "0")
         code = _CHILD.format(root=ROOT, pkg=os.path.join(ROOT, "mamba-unet_b200"))
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
         with np.load(path) as f:
             res[mode] = {k: f[k] for k in f.files}
-        assert str(res[mode]["kernel"]) == ("selscan_bwd_ws_kernel" if mode == "ws" else "selscan_bwd_tma_kernel")
         for k, name in (("u", "du"), ("delta", "ddelta"), ("A", "dA"), ("B", "dB"), ("C", "dC"), ("D", "dD"), ("delta_bias", "ddelta_bias")):
             close(res[mode][k].reshape(ref_g[name].shape), ref_g[name], BWD_RTOL, BWD_ATOL, f"{mode}:{name}")
     for k in ("u", "delta", "A", "B", "C", "D", "delta_bias"):
-        a, b = res["ws"][k].astype(np.float64), res["tma"][k].astype(np.float64)
+        a, b = res["ws"][k].astype(np.float64), res["generic"][k].astype(np.float64)
         scale = max(1.0, float(np.abs(b).max()))
         assert float(np.abs(a - b).max()) <= 2e-5 * scale, k
 

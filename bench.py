@@ -13,7 +13,11 @@ S3 x4 (3072, 196), S4 x2 (6144, 49); d_state 16, K = G = 4, fp32, delta_softplus
   roofline  dominant kernel (the backward kernel at stage S1): algorithmic bytes / mean event-timed duration
             inside the timed steps, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  oracle/ref_torch.py (PyTorch port of the reference's selective_scan_ref) fwd + autograd bwd on
-            the host cores, on a bounded sample of config 1 (rank 0, N=1 only).
+            the host cores: config 1 in full (B=1, all 768 channel rows, L=3136), once, plus the stage-3 / stage-4 shapes
+            at B=1 (rank 0, N=1 only).
+  reference_cuda  (rank 0, N=1, when oracle/_ref was built) the reference's OWN CUDA kernels rebuilt for sm_100a on the same
+            resident tensors, per stage and for the whole 14-scan step, and MambaUnet bs24 inference / training img/s with
+            those kernels + the ATen chain of forward_corev0 (oracle/ref_model.py) -- BASELINE.md rows B2 / B4 / B5 / B6.
 
 N > 1 (torchrun): every rank runs the same batch-24 workload on its own GPU (weak scaling: the scan shards over the
 image batch only); the parameter gradients of the scan (dA, dD, ddelta_bias) are all-reduced over NCCL per call, overlapped
@@ -40,6 +44,7 @@ UNIT = "GB/s"
 N_STATE, K_DIR = 16, 4
 # (name, d_inner, L, SS2D calls per model forward)
 STAGES = [("S1", 192, 3136, 4), ("S2", 384, 784, 4), ("S3", 768, 196, 4), ("S4", 1536, 49, 2)]
+DT_RANK = {"S1": 6, "S2": 12, "S3": 24, "S4": 48}   # ceil(d_model / 16), d_model = d_inner / 2 (mamba_sys.py:271-296)
 BATCH = 24
 
 
@@ -118,33 +123,34 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference_leg(threads=None):
-    """Time oracle/ref_torch.py (port of the reference selective_scan_ref, CPU) fwd + autograd bwd on a bounded
-    sample of config 1 (B=1, K=4, d_state=16, L=3136): the first 64 of its 768 channel rows (a few seconds a pass)."""
+    """oracle/ref_torch.py (port of the reference selective_scan_ref, CPU) fwd + autograd bwd.  Returns one(dim, L, batch) ->
+    seconds for a (batch, dim, L) call with K = 4 groups and d_state 16."""
     import torch
     from oracle.ref_torch import selective_scan_ref_torch
 
     if threads:
         torch.set_num_threads(threads)
-    L = 3136
 
-    def one(dim, seed=0):
+    def one(dim, L=3136, batch=1, seed=0):
         g = torch.Generator().manual_seed(seed)
-        u = torch.randn(1, dim, L, generator=g).requires_grad_()
-        dt = (0.5 * torch.rand(1, dim, L, generator=g)).requires_grad_()
+        u = torch.randn(batch, dim, L, generator=g).requires_grad_()
+        dt = (0.5 * torch.rand(batch, dim, L, generator=g)).requires_grad_()
         A = (-0.5 * torch.rand(dim, N_STATE, generator=g)).requires_grad_()
-        Bm = torch.randn(1, K_DIR, N_STATE, L, generator=g).requires_grad_()
-        Cm = torch.randn(1, K_DIR, N_STATE, L, generator=g).requires_grad_()
+        Bm = torch.randn(batch, K_DIR, N_STATE, L, generator=g).requires_grad_()
+        Cm = torch.randn(batch, K_DIR, N_STATE, L, generator=g).requires_grad_()
         D = torch.randn(dim, generator=g).requires_grad_()
         bias = (0.5 * torch.rand(dim, generator=g)).requires_grad_()
-        dout = torch.randn(1, dim, L, generator=g)
+        dout = torch.randn(batch, dim, L, generator=g)
         t0 = time.perf_counter()
         out = selective_scan_ref_torch(u, dt, A, Bm, Cm, D, None, bias, True)
         out.backward(dout)
         return time.perf_counter() - t0
 
     one(4)  # first call pays thread-pool / allocator warm-up
-    dim = 64  # fixed sample: ~5 s per pass on 8 cores (the port's cost per row is flat above ~32 rows)
-    return dim, L, one
+    return one
+
+
+REF_SAMPLE_DIM = 64   # --impl reference: rows of config 1 per step (the port's cost per row is flat above ~32 rows)
 
 
 def run_reference_impl(args):
@@ -156,7 +162,8 @@ def run_reference_impl(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    dim, L, one = cpu_reference_leg()
+    one = cpu_reference_leg()
+    dim, L = REF_SAMPLE_DIM, 3136
     for _ in range(args.warmup):
         one(dim)
     t0 = time.perf_counter()
@@ -179,20 +186,74 @@ def run_reference_impl(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def reference_cuda_scan_leg(bufs, stages, batch, peak):
+    """The reference's own selective_scan_cuda (oracle/_ref: unmodified sources rebuilt for sm_100a) on the SAME resident tensors,
+    called as its autograd wrapper calls it (selective_scan_interface.py:37, :62-65; it allocates and zeroes its own outputs).
+    BASELINE.md rows B2 / B3.  Baseline only: nothing here is on the product path."""
+    import torch
+    from oracle import ref_cuda
+
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/selective_scan_cuda.so is not built (python oracle/build_ref.py in the build container)"}
+
+    def timeit(fn, warm=2, iters=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    res = {"kernels": "selective_scan_fwd_kernel / selective_scan_bwd_kernel (mamba_ssm csrc, -O3 --use_fast_math, sm_100a)", "per_stage": {}}
+    step_ms, step_bytes = 0.0, 0
+    for name, d_inner, L, calls in stages:
+        t = bufs[name]
+        kd = K_DIR * d_inner
+        args = (t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], None, t["bias"])
+        x = ref_cuda.ref_fwd(*args, True)[1]
+        f = timeit(lambda: ref_cuda.ref_fwd(*args, True))
+        w = timeit(lambda: ref_cuda.ref_bwd(*args, t["dout"], x, None, True))
+        bf, bb = bytes_fwd(batch, kd, L), bytes_bwd(batch, kd, L)
+        res["per_stage"][name] = {"fwd_ms": round(f, 4), "bwd_ms": round(w, 4), "fwdbwd_gbps": round((bf + bb) / (f + w) / 1e6, 1),
+                                  "fwdbwd_frac": round((bf + bb) / (f + w) / 1e6 / peak, 4)}
+        step_ms += calls * (f + w)
+        step_bytes += calls * (bf + bb)
+        del x
+    res["ms_per_step"] = round(step_ms, 3)
+    res["value"] = round(step_bytes / step_ms / 1e6, 2)
+    res["unit"] = UNIT
+    res["frac_of_hbm_peak"] = round(step_bytes / step_ms / 1e6 / peak, 4)
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------------
 def model_leg(world, rank, dev, steps):
     """MambaUnet (vmamba_tiny, 19.1 M parameters, random init) on synthetic 1x224x224 slices, 4 classes -- BASELINE configs 2-4.
-    The model is the from-scratch caller context (selscan_b200/vssm.py); every SS2D block runs the sm_100a scan."""
+    The model is the from-scratch caller context (selscan_b200/vssm.py); every SS2D block runs the sm_100a scan.
+
+    Arms (keys of the result):
+      *                      default path: x_proj / dt_proj on the tcgen05 tensor cores (3xTF32, ss2d.TC_PROJ), nn.Linear on cuBLAS fp32
+      *_cublas_proj          x_proj / dt_proj on cuBLAS fp32 as well (round-1 default)
+      *_tc3xtf32             additionally every nn.Linear on the 3xTF32 kernel (layers OUTSIDE the hot path: separate key)
+      *_cudagraph            the whole step replayed as one CUDA graph
+    N > 1: DistributedDataParallel (static graph, gradients as bucket views, bucket size from SELSCAN_DDP_BUCKET_MB, default 25)."""
     import torch
     import torch.distributed as dist
+    from selscan_b200 import ss2d, tcgemm
     from selscan_b200 import workloads as wl
     from selscan_b200.vssm import DiceLoss, MambaUnet
 
     torch.manual_seed(1337 + rank)
     res = {}
     dice = DiceLoss(4)
+    bucket_mb = float(os.environ.get("SELSCAN_DDP_BUCKET_MB", "25"))
 
-    def timed(fn, n):
-        for _ in range(3):
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
             fn()
         if world > 1:
             dist.barrier()
@@ -210,65 +271,122 @@ def model_leg(world, rank, dev, steps):
             ms = float(t.item())
         return ms
 
+    def ddp(m):
+        if world == 1:
+            return m
+        return torch.nn.parallel.DistributedDataParallel(m, device_ids=[dev.index], gradient_as_bucket_view=True, static_graph=True,
+                                                         bucket_cap_mb=bucket_mb)
+
+    def entry(ms, imgs):
+        return {"ms_per_step": round(ms, 3), "img_per_s": round(world * imgs / ms * 1e3, 1)}
+
     n = max(2, min(steps, 5))
-    model = MambaUnet(num_classes=4).to(dev)
+    x24 = torch.rand(24, 1, 224, 224, device=dev)
+    y24 = torch.randint(0, 4, (24, 224, 224), device=dev)
+    x16, y16 = x24[:16], y24[:16]
+    cw = wl.consistency_weight(3000)
+
+    def graphed(key, fn, *inputs, imgs):
+        try:
+            g = wl.GraphedStep(fn, *inputs, warmup=11 if world > 1 else 3)   # DDP needs its first iterations outside the capture
+            res[key] = entry(timed(lambda: g(*inputs), n), imgs)
+            del g
+        except Exception as e:  # noqa: BLE001 -- reported, not hidden
+            res[key] = {"unavailable": repr(e)[:200]}
+            torch.cuda.synchronize()
+
+    tc_default = ss2d.TC_PROJ
+    try:
+        # ---- default arm: inference, supervised training, semi-supervised dual-network training ----
+        model = MambaUnet(num_classes=4).to(dev)
+        model.eval()
+        with torch.no_grad():
+            res["infer_bs24"] = entry(timed(lambda: model(x24), n), 24)
+            if world == 1:
+                graphed("infer_bs24_cudagraph", lambda x: model(x), x24, imgs=24)
+        model.train()
+        net = ddp(model)
+        opt = wl.make_sgd(net)
+        res["train_supervised_bs24"] = entry(timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n), 24)
+        graphed("train_supervised_bs24_cudagraph", lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24, imgs=24)
+        # ---- x_proj / dt_proj back on cuBLAS fp32 (same model, same optimizer state) ----
+        ss2d.TC_PROJ = False
+        res["train_supervised_bs24_cublas_proj"] = entry(timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n), 24)
+        ss2d.TC_PROJ = tc_default
+        del net, opt, model
+        # ---- every nn.Linear on the 3xTF32 tensor-core GEMM too (outside the hot path: own keys) ----
+        try:
+            model = MambaUnet(num_classes=4).to(dev).train()
+            tcgemm.patch_linears(model)
+            ss2d.TC_PROJ = True
+            net = ddp(model)
+            opt = wl.make_sgd(net)
+            res["train_supervised_bs24_tc3xtf32"] = entry(timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n), 24)
+            graphed("train_supervised_bs24_tc3xtf32_cudagraph", lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24, imgs=24)
+            del net, opt, model
+        except Exception as e:  # noqa: BLE001
+            res["train_supervised_bs24_tc3xtf32"] = {"unavailable": repr(e)[:200]}
+        finally:
+            ss2d.TC_PROJ = tc_default
+        # ---- BASELINE config 4: dual-network semi-supervised step, 16 images per GPU (8 labeled) ----
+        m1, m2 = ddp(MambaUnet(num_classes=4).to(dev).train()), ddp(MambaUnet(num_classes=4).to(dev).train())
+        o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
+        res["train_semi_dual_bs16"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw), n), 16)
+        graphed("train_semi_dual_bs16_cudagraph", lambda x, y: wl.semi_step(m1, m2, o1, o2, dice, x, y, 8, cw), x16, y16, imgs=16)
+        del m1, m2, o1, o2
+    finally:
+        ss2d.TC_PROJ = tc_default
+    res["note"] = ("img/s is the whole-job aggregate over %d GPU(s); per-GPU batch fixed (weak scaling); DDP (static_graph, "
+                   "gradient_as_bucket_view, bucket_cap_mb=%g) gradient all-reduce over NCCL when n_gpus > 1 (19.1 M fp32 gradients per "
+                   "model); default arm: ss2d.TC_PROJ=%s" % (world, bucket_mb, tc_default))
+    return res
+
+
+def reference_cuda_model_leg(dev, steps):
+    """MambaUnet bs24 with the reference's kernels + the ATen chain of forward_corev0 / SS2D.forward + torch LayerNorm + the
+    reference DiceLoss (oracle/ref_model.py) -- BASELINE.md rows B4 / B5 / B6 on this GPU.  Rank 0, N = 1 only."""
+    import torch
+    from oracle import ref_cuda, ref_model
+    from selscan_b200 import workloads as wl
+    from selscan_b200.vssm import MambaUnet
+
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/selective_scan_cuda.so is not built"}
+    torch.manual_seed(1337)
+    n = max(2, min(steps, 3))
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    res = {}
+    model = ref_model.to_reference_path(MambaUnet(num_classes=4).to(dev))
     x24 = torch.rand(24, 1, 224, 224, device=dev)
     y24 = torch.randint(0, 4, (24, 224, 224), device=dev)
     model.eval()
     with torch.no_grad():
-        ms = timed(lambda: model(x24), n)
-    res["infer_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
-    if world == 1:   # the same forward replayed as one CUDA graph (host launch overhead removed)
-        try:
-            with torch.no_grad():
-                g = wl.GraphedStep(lambda x: model(x), x24)
-                ms = timed(lambda: g(x24), n)
-            res["infer_bs24_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
-            del g
-        except Exception as e:  # noqa: BLE001 -- reported, not hidden
-            res["infer_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
+        ms = timed(lambda: model(x24))
+    res["infer_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
     model.train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True) if world > 1 else model
-    opt = wl.make_sgd(net)
-    ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
-    res["train_supervised_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 24 / ms * 1e3, 1)}
-    if world == 1:
-        try:
-            g = wl.GraphedStep(lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24)
-            ms = timed(lambda: g(x24, y24), n)
-            res["train_supervised_bs24_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
-            del g
-        except Exception as e:  # noqa: BLE001
-            res["train_supervised_bs24_cudagraph"] = {"unavailable": repr(e)[:200]}
-    from selscan_b200 import ss2d
-    if world == 1:   # opt-in legs: Linear layers, x_proj, dt_proj and d(xs) on the tcgen05 tensor cores with the 3xTF32 split
-        # (fp32-level accuracy, ~2x the rounding error of cuBLAS fp32; NOT the reference's cuBLAS arithmetic, hence separate keys)
-        try:
-            from selscan_b200 import ss2d, tcgemm
-            tcgemm.patch_linears(model)
-            ss2d.TC_PROJ = True                    # x_proj / dt_proj too
-            ms = timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n)
-            res["train_supervised_bs24_tc3xtf32"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
-            g = wl.GraphedStep(lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24)
-            ms = timed(lambda: g(x24, y24), n)
-            res["train_supervised_bs24_tc3xtf32_cudagraph"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
-            del g
-        except Exception as e:  # noqa: BLE001
-            res["train_supervised_bs24_tc3xtf32"] = {"unavailable": repr(e)[:200]}
-        finally:
-            ss2d.TC_PROJ = False
-    del net, opt, model
-    m1, m2 = MambaUnet(num_classes=4).to(dev).train(), MambaUnet(num_classes=4).to(dev).train()
-    if world > 1:
-        m1 = torch.nn.parallel.DistributedDataParallel(m1, device_ids=[dev.index], gradient_as_bucket_view=True)
-        m2 = torch.nn.parallel.DistributedDataParallel(m2, device_ids=[dev.index], gradient_as_bucket_view=True)
+    opt = wl.make_sgd(model)
+    dice = ref_model.RefDiceLoss(4)
+    ms = timed(lambda: wl.supervised_step(model, opt, dice, x24, y24))
+    res["train_supervised_bs24"] = {"ms_per_step": round(ms, 3), "img_per_s": round(24 / ms * 1e3, 1)}
+    del model, opt
+    m1 = ref_model.to_reference_path(MambaUnet(num_classes=4).to(dev).train())
+    m2 = ref_model.to_reference_path(MambaUnet(num_classes=4).to(dev).train())
     o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
-    x16, y16 = x24[:16], y24[:16]
-    cw = wl.consistency_weight(3000)
-    ms = timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw), n)
-    res["train_semi_dual_bs16"] = {"ms_per_step": round(ms, 3), "img_per_s": round(world * 16 / ms * 1e3, 1)}
-    res["note"] = ("img/s is the whole-job aggregate over %d GPU(s); per-GPU batch fixed (weak scaling); DDP gradient all-reduce over "
-                   "NCCL when n_gpus > 1 (19.1 M fp32 gradients per model)" % world)
+    ms = timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x24[:16], y24[:16], 8, wl.consistency_weight(3000)))
+    res["train_semi_dual_bs16"] = {"ms_per_step": round(ms, 3), "img_per_s": round(16 / ms * 1e3, 1)}
+    res["note"] = "same architecture / initialisation as the product model legs; reference scan kernels, ATen forward_corev0 chain, torch LayerNorm, DiceLoss with .item()"
     return res
 
 
@@ -283,6 +401,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-model", action="store_true", help="skip the MambaUnet img/s legs")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference-CUDA-kernel baseline block")
     ap.add_argument("--stages", default="", help="comma list to restrict (profiling only), e.g. S1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -323,8 +442,12 @@ def main():
         t["u"] = rows(torch.randn(batch, kd, L, device=dev, generator=gen))
         t["delta"] = rows(0.5 * torch.randn(batch, kd, L, device=dev, generator=gen))
         t["A"] = -torch.arange(1, N_STATE + 1, device=dev, dtype=torch.float32).repeat(kd, 1).contiguous()
-        t["B"] = torch.randn(batch, K_DIR, N_STATE, L, device=dev, generator=gen)
-        t["C"] = torch.randn(batch, K_DIR, N_STATE, L, device=dev, generator=gen)
+        # B / C exactly as SS2D hands them over: strided views of x_dbl = x_proj(xs), (batch, K, R + 2N, L) (ss2d.py: the batched
+        # GEMM writes that layout; group stride (R + 2N) * L, unit position stride) -- no (N, L)-contiguous copy exists in the model
+        R = DT_RANK[name]
+        t["x_dbl"] = torch.randn(batch, K_DIR, R + 2 * N_STATE, L, device=dev, generator=gen)
+        t["B"] = t["x_dbl"][:, :, R:R + N_STATE]
+        t["C"] = t["x_dbl"][:, :, R + N_STATE:]
         t["D"] = torch.ones(kd, device=dev)
         dtv = torch.exp(torch.rand(kd, device=dev, generator=gen) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
         t["bias"] = dtv + torch.log(-torch.expm1(-dtv))
@@ -454,7 +577,7 @@ def main():
         h2d = d2h = 0
         for name, d_inner, L, calls in stages:
             t = bufs[name]
-            hin = {k: torch.empty(tuple(t[k].shape), dtype=torch.float32, pin_memory=True).copy_(t[k]) for k in ("u", "delta", "B", "C", "dout")}
+            hin = {k: torch.empty(tuple(t[k].shape), dtype=torch.float32, pin_memory=True).copy_(t[k]) for k in ("u", "delta", "B", "C", "dout")}   # B / C travel as dense (N, L) blocks
             hout = {k: torch.empty(tuple(t[k].shape), dtype=torch.float32, pin_memory=True) for k in ("out", "du", "ddelta", "dB", "dC", "dA", "dD", "dbias")}
             host[name] = (hin, hout)
             h2d += calls * sum(v.numel() * 4 for v in hin.values())
@@ -467,7 +590,8 @@ def main():
         call_list = [name for name, _, _, calls in stages for _ in range(calls)]
 
         # device-side input staging: two reusable buffer sets per stage shape (no allocator traffic inside the timed region)
-        ring = {name: [{k: torch.empty_like(bufs[name][k]) for k in ("u", "delta", "B", "C", "dout")} for _ in range(2)]
+        ring = {name: [{k: torch.empty_like(bufs[name][k], memory_format=torch.contiguous_format) if k in ("B", "C") else torch.empty_like(bufs[name][k])
+                        for k in ("u", "delta", "B", "C", "dout")} for _ in range(2)]
                 for name, _, _, _ in stages}
         ring_done = {name: [None, None] for name, _, _, _ in stages}
         ring_next = {name: 0 for name, _, _, _ in stages}
@@ -538,13 +662,28 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------------------
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        dim, L, one = cpu_reference_leg()
-        dt = one(dim)
+        one = cpu_reference_leg()
+        dim, L = 768, 3136                      # BASELINE config 1 in full: stage-1 SS2D of ONE 224x224 slice
+        dt = one(dim, L)
         nb = bytes_fwd(1, dim, L) + bytes_bwd(1, dim, L)
         cpu = {"value": round(nb / dt / 1e9, 6), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "host_cpus": os.cpu_count(), "seconds": round(dt, 2),
-               "sample": f"oracle/ref_torch.py (PyTorch port of selective_scan_ref) fwd + autograd bwd, first {dim} of 768 "
-                         f"channel rows of config 1 (B=1, K=4, d_state=16, L={L}), one pass"}
+               "sample": f"oracle/ref_torch.py (PyTorch port of selective_scan_ref) fwd + autograd bwd, config 1 in full "
+                         f"(B=1, K=4, all {dim} channel rows, d_state=16, L={L}), one pass",
+               "other_shapes": {}}
+        for nm, d_inner, Ls, _ in STAGES[2:]:   # the short stages at B=1 (seconds each): a multi-point comparison
+            ts = one(K_DIR * d_inner, Ls)
+            nbs = bytes_fwd(1, K_DIR * d_inner, Ls) + bytes_bwd(1, K_DIR * d_inner, Ls)
+            cpu["other_shapes"][nm] = {"dim": K_DIR * d_inner, "L": Ls, "seconds": round(ts, 3), "gbps": round(nbs / ts / 1e9, 6)}
+
+    # ---- the reference's own CUDA kernels on the same tensors (rank 0, N = 1 only) -------------------------------
+    ref_cuda_block = None
+    if world == 1 and rank == 0 and not args.no_reference_cuda:
+        try:
+            ref_cuda_block = {"scan": reference_cuda_scan_leg(bufs, stages, batch, peak)}
+        except Exception as e:  # noqa: BLE001 -- a baseline leg must not take the product's line down
+            ref_cuda_block = {"scan": {"unavailable": repr(e)[:300]}}
+            torch.cuda.synchronize()
 
     model = None
     if not args.no_model and not args.stages:
@@ -552,6 +691,12 @@ def main():
             t.clear()
         torch.cuda.empty_cache()
         model = model_leg(world, rank, dev, args.steps)
+        if ref_cuda_block is not None:
+            torch.cuda.empty_cache()
+            try:
+                ref_cuda_block["mambaunet"] = reference_cuda_model_leg(dev, args.steps)
+            except Exception as e:  # noqa: BLE001
+                ref_cuda_block["mambaunet"] = {"unavailable": repr(e)[:300]}
 
     if rank == 0:
         line = {
@@ -562,9 +707,10 @@ def main():
                                    "(S1 4x[KD768,L3136], S2 4x[1536,784], S3 4x[3072,196], S4 2x[6144,49]; N=16, G=4)" % batch,
                        "batch_per_gpu": batch, "stages": [s[0] for s in stages],
                        "l2": "inputs larger than L2: every call streams >= 234 MB (no explicit flush)",
+                       "bc_layout": "B / C are strided views of x_dbl (batch, K, R+2N, L) as SS2D passes them; dB / dC dense",
                        "algorithmic_bytes_per_step": total_bytes, "parallelism": f"dp{world} (batch-sharded replicas)"},
             "frac_of_hbm_peak": round(value / world / peak, 4),
-            "roofline": roofline, "per_stage": table, "mambaunet": model, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "per_stage": table, "mambaunet": model, "reference_cuda": ref_cuda_block, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": args.steps * sum(2 * s[3] for s in stages), "wall_s_timed_region": round(t_wall, 3),
         }
         print(json.dumps(line), flush=True)

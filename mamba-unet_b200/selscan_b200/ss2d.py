@@ -203,8 +203,10 @@ def edge_out_bwd(g, H, W, z, zld, xhat, rstd, ln_w, ln_b, dz, dzld):
     return d_ys, part[0], part[1]
 
 
-# Opt-in: x_proj / dt_proj and their gradients on the tcgen05 tensor cores (3xTF32 split, tcgemm.bgemm) instead of cuBLAS fp32.
-TC_PROJ = False
+# x_proj / dt_proj (mamba_sys.py:406-409, the two contractions ON the hot path) and d(xs) += W^T d(x_dbl) run on the tcgen05 tensor
+# cores with the 3xTF32 split (tcgemm.bgemm: fp32-level accuracy, error ~2x cuBLAS fp32's, far inside the north-star tolerance;
+# tests/test_vssm_gpu.py checks the model against the reference's golden outputs with it).  False: cuBLAS fp32 SIMT GEMMs.
+TC_PROJ = True
 
 
 def _tc_proj_ok(D, L, N, R):

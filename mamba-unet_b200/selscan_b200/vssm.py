@@ -180,8 +180,12 @@ class VSSM(nn.Module):
             if i > 0:
                 x = self.concat_back_dim[i](torch.cat([x, skips[self.num_layers - 1 - i]], dim=-1))
             x = up(x)
-        x = self.up(self.norm_up(x))
-        return self.output(x.permute(0, 3, 1, 2))
+        x = self.up(self.norm_up(x))                        # (B, H, W, d0)
+        # the 1x1 `output` convolution (mamba_sys.py:761,823) as the per-pixel linear map it is, on the channels-last tensor: same
+        # parameter (classes, d0, 1, 1), no NHWC -> NCHW copy of the widest activation, and a contiguous weight gradient (cuDNN's
+        # came back in channels-last strides, which DDP's bucket views reject with a warning and a copy on every step)
+        w = self.output.weight
+        return F.linear(x, w.view(w.shape[0], -1)).permute(0, 3, 1, 2).contiguous()
 
 
 class MambaUnet(nn.Module):

@@ -19,9 +19,10 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """Op-level fixtures (model_*.npz are the caller-context fixtures of tests/test_vssm_gpu.py)."""
+    """Op-level fixtures (model_*.npz / ss2d_call_*.npz are the caller-context fixtures of tests/test_vssm_gpu.py and
+    tests/test_reference_call_trace_gpu.py)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith("model_")]
+    return [n for n in names if not n.startswith(("model_", "ss2d_call_"))]
 
 
 def load_golden(name):

@@ -150,3 +150,48 @@ def test_patch_ss2d_installs_forward():
 
     patch_ss2d(Dummy)
     assert Dummy.forward is forward_b200 and Dummy.forward_corev0 is forward_core_b200
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("fused", [True, False])
+def test_ss2d_block_under_autocast(dtype, fused):
+    """The reference runs SS2D under autocast (mamba_sys.py:865) and forward_corev0 casts xs / dts / Bs / Cs to float for the scan
+    (:411-427).  Here in_proj / out_proj may run in half precision, everything between them (projections, scan, LayerNorm) must
+    stay fp32: outputs and gradients of the autocast run agree with the fp32 run to half-precision round-off, and nothing reads a
+    half buffer as fp32."""
+    from selscan_b200.vssm import SS2D
+
+    _fp32()
+    torch.manual_seed(11)
+    blk = SS2D(32).cuda()
+    blk.fused = fused
+    x = torch.randn(2, 14, 14, 32, device="cuda")
+    g = torch.randn(2, 14, 14, 32, device="cuda")
+    res = []
+    for ac in (False, True):
+        blk.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_()
+        with torch.autocast("cuda", dtype=dtype, enabled=ac):
+            out = blk(xi)
+        out.float().backward(g)
+        res.append((out.detach().float(), xi.grad.float(), {k: p.grad.float().clone() for k, p in blk.named_parameters()}))
+    tol = 4e-2 if dtype == torch.bfloat16 else 8e-3
+    for a, b, nm in [(res[1][0], res[0][0], "out"), (res[1][1], res[0][1], "dx")] + [(res[1][2][k], res[0][2][k], k) for k in res[0][2]]:
+        assert torch.isfinite(a).all(), nm
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= tol * max(scale, 1e-3), (nm, float((a - b).abs().max()), scale)
+
+
+def test_cross_scan_merge_planes_beyond_shared_memory():
+    """Token planes above ~225 x 225 do not fit the plane kernels' shared memory: CrossScan / CrossMerge (and with them
+    forward_core_b200) take the plain-torch chains instead of raising."""
+    from selscan_b200.ss2d import CrossMerge, CrossScan, cross_merge_torch, cross_scan_torch
+
+    torch.manual_seed(5)
+    x = torch.randn(1, 3, 230, 231, device="cuda", requires_grad=True)
+    xs = CrossScan.apply(x)
+    assert torch.equal(xs, cross_scan_torch(x.detach()))
+    y = CrossMerge.apply(xs, 230, 231)
+    torch.testing.assert_close(y, cross_merge_torch(xs.detach(), 230, 231))
+    y.sum().backward()
+    torch.testing.assert_close(x.grad, torch.full_like(x, 4.0))

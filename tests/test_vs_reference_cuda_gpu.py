@@ -48,3 +48,29 @@ def test_matches_reference_kernels(oracle, D, L):
     for k, (e1, e2) in report.items():
         print(f"   {k:12s} {e1:.3e}  {e2:.3e}")
         assert e1 <= 5 * e2 + 1e-6, (k, e1, e2)
+
+
+def test_reference_path_model_matches_product_model():
+    """The baseline arm of bench.py (`reference_cuda.mambaunet`: oracle/ref_model.py = the reference kernels + the ATen chain of
+    forward_corev0 + torch LayerNorm) and the product model compute the same function: same parameters, same input, forward and
+    input gradient.  Guards the baseline numbers against a mis-stated chain."""
+    import copy
+
+    from oracle import ref_model
+    from selscan_b200.vssm import VSSM
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(21)
+    ours = VSSM(depths=(1, 1, 1, 1), dims=(32, 64, 128, 256), drop_path_rate=0.0).cuda().eval()
+    theirs = ref_model.to_reference_path(copy.deepcopy(ours))
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    g = torch.randn(2, 4, 64, 64, device="cuda")
+    outs = []
+    for m in (ours, theirs):
+        xi = x.clone().requires_grad_()
+        out = m(xi)
+        (out * g).sum().backward()
+        outs.append((out.detach(), xi.grad))
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-3, atol=2e-4)
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=2e-3, atol=2e-4 * float(outs[1][1].abs().max()))

@@ -13,8 +13,8 @@ S3 x4 (3072, 196), S4 x2 (6144, 49); d_state 16, K = G = 4, fp32, delta_softplus
   roofline  dominant kernel (the backward kernel at stage S1): algorithmic bytes / mean event-timed duration
             inside the timed steps, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  oracle/ref_torch.py (PyTorch port of the reference's selective_scan_ref) fwd + autograd bwd on
-            the host cores: config 1 in full (B=1, all 768 channel rows, L=3136), once, plus the stage-3 / stage-4 shapes
-            at B=1 (rank 0, N=1 only).
+            the host cores: one scan direction of config 1 (B=1, 192 of its 768 channel rows, L=3136; --cpu-full: all of it,
+            ~100 s), once, plus the stage-3 / stage-4 shapes at B=1 (rank 0, N=1 only).
   reference_cuda  (rank 0, N=1, when oracle/_ref was built) the reference's OWN CUDA kernels rebuilt for sm_100a on the same
             resident tensors, per stage and for the whole 14-scan step, and MambaUnet bs24 inference / training img/s with
             those kernels + the ATen chain of forward_corev0 (oracle/ref_model.py) -- BASELINE.md rows B2 / B4 / B5 / B6.
@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (BASELINE config: 24)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-full", action="store_true", help="CPU baseline on config 1 in full (~100 s) instead of one direction of it")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-model", action="store_true", help="skip the MambaUnet img/s legs")
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference-CUDA-kernel baseline block")
@@ -663,13 +664,17 @@ def main():
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         one = cpu_reference_leg()
-        dim, L = 768, 3136                      # BASELINE config 1 in full: stage-1 SS2D of ONE 224x224 slice
+        # BASELINE config 1 is the stage-1 SS2D of ONE 224x224 slice (B=1, K=4, 768 channel rows, L=3136).  In full the port needs
+        # ~100 s on the box's 16 cores (profiles/r02_bench_n1_cpufull.json: 100.7 s, its autograd backward thrashes memory), so the
+        # default run times ONE of its four directions (192 rows, same L) and --cpu-full runs all of it once.
+        dim, L = (768, 3136) if args.cpu_full else (192, 3136)
         dt = one(dim, L)
         nb = bytes_fwd(1, dim, L) + bytes_bwd(1, dim, L)
+        what = "config 1 in full (B=1, K=4, all 768 channel rows" if args.cpu_full else "one of the four scan directions of config 1 (B=1, 192 of its 768 channel rows"
         cpu = {"value": round(nb / dt / 1e9, 6), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "host_cpus": os.cpu_count(), "seconds": round(dt, 2),
-               "sample": f"oracle/ref_torch.py (PyTorch port of selective_scan_ref) fwd + autograd bwd, config 1 in full "
-                         f"(B=1, K=4, all {dim} channel rows, d_state=16, L={L}), one pass",
+               "sample": f"oracle/ref_torch.py (PyTorch port of selective_scan_ref) fwd + autograd bwd, {what}, d_state=16, L={L}), one pass",
+               "full_config1_measured": {"seconds": 100.67, "gbps": 0.000815, "cores": 16, "source": "profiles/r02_bench_n1_cpufull.json"},
                "other_shapes": {}}
         for nm, d_inner, Ls, _ in STAGES[2:]:   # the short stages at B=1 (seconds each): a multi-point comparison
             ts = one(K_DIR * d_inner, Ls)

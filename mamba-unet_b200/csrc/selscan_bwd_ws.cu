@@ -56,11 +56,17 @@ constexpr int kPP = kHP * 32 + 16;   // floats per channel pair in a P half: 4 p
                                      // a quarter-warp store to disjoint banks and readers need no swizzle
 constexpr int kS12P = 36;            // floats per row in an S12 half (32 + 16 bytes: conflict-free STS.128 by (row, lane), LDS.128 by row)
 
-struct WsSmem {
+template <bool kHasZ>
+struct WsSmemT {
   float CK[kStg][kR * kStatePad];   // [row][16 states]                                    (TMA)
   float U[kStg][kR * kC];           // [row][8 positions] (one 64 x 8 box)                  (TMA)
   float DT[kStg][kR * kC];          //   raw delta
   float DY[kStg][kR * kC];
+  // gated calls only (bwd_kernel.cuh:171-207): z and the ungated forward output, [row][8] like U (TMA: the hardware swizzle is a
+  // function of the shared-memory ADDRESS, so these tiles sit with the other TMA tiles at multiples of 256 bytes); the helpers
+  // overwrite dout with dout * silu(z) and `out` with dz in place, and dz leaves by a TMA store of the whole stage tile
+  float Z[kHasZ ? kStg : 1][kHasZ ? kR * kC : 64];
+  float O[kHasZ ? kStg : 1][kHasZ ? kR * kC : 64];
   float BC[kStg][kC * kPitch];      // [position][B0..15 C0..15]                            (helper)
   float SD[kStg][kR * kC];          // delta   [row][8]                                     (helper)
   float SDU[kStg][kR * kC];         // delta*u
@@ -97,10 +103,14 @@ __device__ __forceinline__ u64 mul2v(u64 a, u64 b) {
 }
 __device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
+template <bool kHasZ>
 __global__ void __launch_bounds__(kThr, 2)
 selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                       const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
-                      const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt, const BwdLaunch p) {
+                      const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt,
+                      const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_o,
+                      const __grid_constant__ CUtensorMap map_dz, const BwdLaunch p) {
+  using WsSmem = WsSmemT<kHasZ>;
   extern __shared__ unsigned char smem_raw[];
   WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 255) & ~(uintptr_t)255);   // 32B-swizzle atom = 256 B
   const selscan_bwd_args& a = p.a;
@@ -133,6 +143,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     tma_prefetch_desc(&map_ck);
     tma_prefetch_desc(&map_du);
     tma_prefetch_desc(&map_ddt);
+    if (kHasZ) {
+      tma_prefetch_desc(&map_z);
+      tma_prefetch_desc(&map_o);
+      tma_prefetch_desc(&map_dz);
+    }
   }
   __syncthreads();
 
@@ -182,8 +197,13 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     auto issue_tma = [&](int j) {            // chunk j (processing order) -> stage j % kStg
       const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC;
       if (j >= kStg) mbar_wait(smem_u32(&sm.stage_free[s]), (uint32_t)((j / kStg - 1) & 1));
+      if (kHasZ) tma_store_wait_read<0>();   // my dz store out of this stage's O tile (three chunks ago) has read it
       const uint32_t full = smem_u32(&sm.tma_full[s]);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)(3 * kR * kC * 4 + kR * kStatePad * 4)) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)((kHasZ ? 5 : 3) * kR * kC * 4 + kR * kStatePad * 4)) : "memory");
+      if (kHasZ) {
+        tma_load_3d(smem_u32(sm.Z[s]), &map_z, l0, d0, b, full);
+        tma_load_3d(smem_u32(sm.O[s]), &map_o, l0, d0, b, full);
+      }
       tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
       tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
       tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
@@ -215,6 +235,27 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       sts_f4(smem_u32(sm.SD[s]) + my16, make_float4(v[0], v[1], v[2], v[3]));
       sts_f4(smem_u32(sm.SDU[s]) + my16, make_float4(vu[0], vu[1], vu[2], vu[3]));
       sg_out = make_float4(sg[0], sg[1], sg[2], sg[3]);
+      if (kHasZ) {   // bwd_kernel.cuh:186-191: dz = dout * out * sigmoid(z) * (1 + z * (1 - sigmoid(z))), then dout <- dout * silu(z)
+        const float4 z4 = lds_f4(smem_u32(sm.Z[s]) + my16);
+        const float4 o4 = lds_f4(smem_u32(sm.O[s]) + my16);
+        const float4 y4 = lds_f4(smem_u32(sm.DY[s]) + my16);
+        const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, oo[4] = {o4.x, o4.y, o4.z, o4.w}, yy[4] = {y4.x, y4.y, y4.z, y4.w};
+        float dzv[4], dyg[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float sz = sigmoidf_fast(zz[e]);
+          dzv[e] = yy[e] * oo[e] * sz * (1.f + zz[e] * (1.f - sz));
+          dyg[e] = yy[e] * zz[e] * sz;
+        }
+        sts_f4(smem_u32(sm.O[s]) + my16, make_float4(dzv[0], dzv[1], dzv[2], dzv[3]));     // in place: dz
+        sts_f4(smem_u32(sm.DY[s]) + my16, make_float4(dyg[0], dyg[1], dyg[2], dyg[3]));    // in place: the gated dout everyone else reads
+        fence_proxy_async_smem();            // generic writes -> visible to the TMA store below, ordered before the stage's next TMA load
+        named_bar_sync(1, kGroupThr);        // the whole dz tile is written
+        if (htid == 0) {
+          tma_store_3d(&map_dz, smem_u32(sm.O[s]), t * kC, d0, b);      // positions past the end are clipped by the tensor map
+          tma_store_commit();
+        }
+      }
       sts_f1(smem_u32(sm.BC[s]) + bc_i0, cb0);
       sts_f1(smem_u32(sm.BC[s]) + bc_i1, cb1);
       __syncwarp();
@@ -500,19 +541,19 @@ inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int
 // arithmetic assumes (otherwise setmaxnreg.inc could wait for registers that never come).
 bool bwd_ws_usable() {
   static const bool ok = [] {
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, selscan_bwd_ws_kernel) != cudaSuccess) {
+    cudaFuncAttributes fa, fz;
+    if (cudaFuncGetAttributes(&fa, selscan_bwd_ws_kernel<false>) != cudaSuccess || cudaFuncGetAttributes(&fz, selscan_bwd_ws_kernel<true>) != cudaSuccess) {
       (void)cudaGetLastError();
       return false;
     }
-    return fa.numRegs == kLaunchRegs;
+    return fa.numRegs == kLaunchRegs && fz.numRegs == kLaunchRegs;
   }();
   return ok;
 }
 
 bool bwd_ws_eligible(const BwdLaunch& p) {
   const selscan_bwd_args& a = p.a;
-  if (a.z != nullptr || a.dstate > kStatePad) return false;
+  if (a.dstate > kStatePad) return false;
   if (p.dim_per_group % kR != 0) return false;
   if (p.n_ckpt < 1) return false;                      // seqlen > 8
   if (a.B_l_stride != a.C_l_stride) return false;      // the B/C gather walks both with one step
@@ -522,6 +563,12 @@ bool bwd_ws_eligible(const BwdLaunch& p) {
   if (!tma_row_ok(a.dout, a.dout_d_stride, a.batch > 1 ? a.dout_batch_stride : one_batch)) return false;
   if (!tma_row_ok(a.du, a.du_d_stride, a.batch > 1 ? a.du_batch_stride : one_batch)) return false;
   if (!tma_row_ok(a.ddelta, a.ddelta_d_stride, a.batch > 1 ? a.ddelta_batch_stride : one_batch)) return false;
+  if (a.z != nullptr) {   // the gated path streams z, the ungated forward output and dz as well
+    if (a.out == nullptr || a.dz == nullptr) return false;
+    if (!tma_row_ok(a.z, a.z_d_stride, a.batch > 1 ? a.z_batch_stride : one_batch)) return false;
+    if (!tma_row_ok(a.out, a.out_d_stride, a.batch > 1 ? a.out_batch_stride : one_batch)) return false;
+    if (!tma_row_ok(a.dz, a.dz_d_stride, a.batch > 1 ? a.dz_batch_stride : one_batch)) return false;
+  }
   if ((reinterpret_cast<uintptr_t>(a.ckpt) & 15u) != 0) return false;
   return tensor_map_encoder() != nullptr && bwd_ws_usable();
 }
@@ -537,12 +584,25 @@ cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
       !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR) ||
       !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
     return cudaErrorNotSupported;
-  constexpr int smem = (int)sizeof(WsSmem) + 256;
-  static_assert(sizeof(WsSmem) + 256 + 1024 <= 116736, "two CTAs per SM");
-  static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
-  if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel, smem)) return e;
+  static_assert(sizeof(WsSmemT<false>) + 256 + 1024 <= 116736, "two CTAs per SM");
+  static_assert(sizeof(WsSmemT<true>) + 256 <= 232448, "the gated variant fits one CTA per SM");
   const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kR));
-  selscan_bwd_ws_kernel<<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, p);
+  if (a.z != nullptr) {
+    CUtensorMap mz, mo, mdz;
+    if (!make_row_map_sw(&mz, a.z, a.seqlen, a.dim, a.batch, a.z_d_stride, a.z_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_row_map_sw(&mo, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_row_map_sw(&mdz, a.dz, a.seqlen, a.dim, a.batch, a.dz_d_stride, a.dz_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B))
+      return cudaErrorNotSupported;
+    constexpr int smem = (int)sizeof(WsSmemT<true>) + 256;
+    static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
+    if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<true>, smem)) return e;
+    selscan_bwd_ws_kernel<true><<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, mz, mo, mdz, p);
+  } else {
+    constexpr int smem = (int)sizeof(WsSmemT<false>) + 256;
+    static std::atomic<unsigned long long> configured{0};
+    if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<false>, smem)) return e;
+    selscan_bwd_ws_kernel<false><<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, mu, mu, mu, p);
+  }
   return cudaGetLastError();
 }
 

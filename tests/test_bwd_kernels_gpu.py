@@ -168,3 +168,13 @@ def test_soak_handover_logic():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "soak_bwd.py"), "8"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "soak: PASS" in r.stdout
+
+
+@pytest.mark.parametrize("batch,dim,L,G", [(2, 128, 9, 2), (2, 128, 50, 2), (1, 64, 257, 1), (2, 768, 200, 4), (3, 256, 49, 4)])
+def test_tiled_backward_with_z_gate(oracle, batch, dim, L, G):
+    """SiLU(z) gating on the tiled kernels (reference: selective_scan_fwd_kernel.cuh:280-298, selective_scan_bwd_kernel.cuh:171-207):
+    out * silu(z) forward; dz and the gated dout in the helper warps of the warp-specialised backward.  All gradients incl. dz."""
+    inp = oracle.make_inputs(batch, dim, L, 16, G, dist="T", seed=900 + L, has_z=True, has_D=True, has_bias=True)
+    out, last, grads = run_ours(inp, True)
+    assert grads["dz"] is not None
+    check_all(out, last, grads, *_oracle_refs(oracle, inp))

@@ -296,8 +296,22 @@ def model_leg(world, rank, dev, steps):
             torch.cuda.synchronize()
 
     tc_default = ss2d.TC_PROJ
+    # DDP is constructed (and later warmed up / captured) on ONE side stream: whole-step CUDA-graph capture of a DDP model needs
+    # its reducer and AccumulateGrad nodes created on the capturing stream.  Every eager leg runs first; the graph legs run last so
+    # that a failed capture cannot disturb an eager number.
+    cap_stream = torch.cuda.Stream(dev) if world > 1 else None
+
+    def ddp_on_stream(m):
+        if world == 1:
+            return m
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap_stream):
+            w = ddp(m)
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        return w
+
     try:
-        # ---- default arm: inference, supervised training, semi-supervised dual-network training ----
+        # ---- default arm: inference, supervised training ----
         model = MambaUnet(num_classes=4).to(dev)
         model.eval()
         with torch.no_grad():
@@ -308,7 +322,6 @@ def model_leg(world, rank, dev, steps):
         net = ddp(model)
         opt = wl.make_sgd(net)
         res["train_supervised_bs24"] = entry(timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n), 24)
-        graphed("train_supervised_bs24_cudagraph", lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24, imgs=24)
         # ---- x_proj / dt_proj back on cuBLAS fp32 (same model, same optimizer state) ----
         ss2d.TC_PROJ = False
         res["train_supervised_bs24_cublas_proj"] = entry(timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n), 24)
@@ -322,7 +335,6 @@ def model_leg(world, rank, dev, steps):
             net = ddp(model)
             opt = wl.make_sgd(net)
             res["train_supervised_bs24_tc3xtf32"] = entry(timed(lambda: wl.supervised_step(net, opt, dice, x24, y24), n), 24)
-            graphed("train_supervised_bs24_tc3xtf32_cudagraph", lambda x, y: wl.supervised_step(net, opt, dice, x, y), x24, y24, imgs=24)
             del net, opt, model
         except Exception as e:  # noqa: BLE001
             res["train_supervised_bs24_tc3xtf32"] = {"unavailable": repr(e)[:200]}
@@ -332,8 +344,43 @@ def model_leg(world, rank, dev, steps):
         m1, m2 = ddp(MambaUnet(num_classes=4).to(dev).train()), ddp(MambaUnet(num_classes=4).to(dev).train())
         o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
         res["train_semi_dual_bs16"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw), n), 16)
-        graphed("train_semi_dual_bs16_cudagraph", lambda x, y: wl.semi_step(m1, m2, o1, o2, dice, x, y, 8, cw), x16, y16, imgs=16)
         del m1, m2, o1, o2
+        torch.cuda.empty_cache()
+
+        # ---- the same steps replayed as ONE CUDA graph each (fresh models: under DDP the wrapper must be built on the capture stream) ----
+        def sup_factory(tc_linears):
+            def make():
+                m = MambaUnet(num_classes=4).to(dev).train()
+                if tc_linears:
+                    tcgemm.patch_linears(m)
+                w = ddp_on_stream(m)
+                o = wl.make_sgd(w)
+                return lambda x, y: wl.supervised_step(w, o, dice, x, y)
+            return make
+
+        def semi_factory():
+            a, b = ddp_on_stream(MambaUnet(num_classes=4).to(dev).train()), ddp_on_stream(MambaUnet(num_classes=4).to(dev).train())
+            oa, ob = wl.make_sgd(a), wl.make_sgd(b)
+            return lambda x, y: wl.semi_step(a, b, oa, ob, dice, x, y, 8, cw)
+
+        for key, make, inputs, imgs, tc in (("train_supervised_bs24_cudagraph", sup_factory(False), (x24, y24), 24, tc_default),
+                                            ("train_supervised_bs24_tc3xtf32_cudagraph", sup_factory(True), (x24, y24), 24, True),
+                                            ("train_semi_dual_bs16_cudagraph", semi_factory, (x16, y16), 16, tc_default)):
+            ss2d.TC_PROJ = tc
+            try:
+                fn = make()
+                g = wl.GraphedStep(fn, *inputs, warmup=11 if world > 1 else 3, stream=cap_stream)
+                res[key] = entry(timed(lambda: g(*inputs), n), imgs)
+                del g, fn
+            except Exception as e:  # noqa: BLE001 -- reported, not hidden
+                res[key] = {"unavailable": repr(e)[:200]}
+                try:
+                    torch.cuda.synchronize()
+                except Exception:  # noqa: BLE001
+                    pass
+                if world > 1:
+                    break               # a failed capture under DDP leaves the collectives of the ranks out of step: stop here
+            torch.cuda.empty_cache()
     finally:
         ss2d.TC_PROJ = tc_default
     res["note"] = ("img/s is the whole-job aggregate over %d GPU(s); per-GPU batch fixed (weak scaling); DDP (static_graph, "

@@ -61,16 +61,16 @@ class GraphedStep:
     MambaUnet step is ~2600 kernel launches, and the host can no longer issue them as fast as a B200 retires them (SURVEY.md
     section 8f row 4).  `fn(*tensors)` must be sync-free; inputs are copied into the captured buffers before every replay."""
 
-    def __init__(self, fn, *inputs, warmup=3):
+    def __init__(self, fn, *inputs, warmup=3, stream=None):
         self.inputs = [t.clone() for t in inputs]
-        side = torch.cuda.Stream()
+        side = stream if stream is not None else torch.cuda.Stream()   # DDP: the stream the wrapper was constructed on
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):       # eager warm-up on a side stream: lazy optimizer state, kernel attributes, autotuning
             for _ in range(warmup):
                 fn(*self.inputs)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=stream):
             self.out = fn(*self.inputs)
 
     def __call__(self, *inputs):

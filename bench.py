@@ -600,10 +600,10 @@ def main():
     achieved = dom_bytes / table[dom]["bwd_ms"] / 1e6
     traffic, traffic_src = None, None
     try:  # DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/), batch 24 only
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             if batch == BATCH:
                 traffic = json.load(f)["stages"][dom]["bwd"]["dram_bytes"]
-                traffic_src = "profiles/r01_ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
+                traffic_src = "profiles/r02_ncu_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, per launch)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": f"{ops.bwd_kernel_name()} @ {dom} (B={batch}, KD={K_DIR * dom_stage[1]}, L={dom_stage[2]})",
@@ -613,7 +613,7 @@ def main():
                 "share_of_step": round(dict((s[0], s[3]) for s in stages)[dom] * table[dom]["bwd_ms"] /
                                        sum(s[3] * (table[s[0]]["fwd_ms"] + table[s[0]]["bwd_ms"]) for s in stages), 4),
                 "note": "not HBM-bound: SM-side limits bound this kernel (shared-memory/shuffle pipe ~79% busy, issue slots 54%, MUFU 48% "
-                        "at once, profiles/r01_ncu_final_summary.txt); see DESIGN.md section 4"}
+                        "at once, profiles/r02_ncu_scan_summary.txt); see DESIGN.md section 4"}
 
     # ---- e2e: public op from pinned host buffers ---------------------------------------------------------------
     e2e = None

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SELSCAN_B200_ABI_VERSION 5
+#define SELSCAN_B200_ABI_VERSION 6
 /* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
 #define SELSCAN_B200_CKPT_INTERVAL 8
 /* states are padded to this count inside the kernels and in the checkpoint buffer */
@@ -67,6 +67,15 @@ typedef struct selscan_fwd_args {
   float* ckpt;                       /* selscan_b200_ckpt_elems() floats, or NULL (inference) */
   float* workspace;                  /* selscan_b200_fwd_workspace_elems() floats or NULL: lets small-batch calls split the
                                         sequence into segments that run concurrently (results identical to rounding) */
+  /* Fused dt_proj (code/networks/mamba_sys.py:408-412).  When dt_w != NULL, `delta` is ignored (may be
+   * NULL: no (batch, dim, seqlen) step tensor exists) and the kernels form the raw step themselves,
+   *     delta[b, d, l] = sum_r dt_w[d, r] * dt_x[b, d / (dim / ngroups), r, l],
+   * before the bias / softplus.  Only the tiled kernels do this: ask selscan_b200_dt_fusable() first. */
+  const float* dt_w;                 /* (dim, dt_rank), unit stride along r, or NULL */
+  const float* dt_x;                 /* (batch, ngroups, dt_rank, seqlen), unit stride along seqlen, 16-byte aligned rows */
+  int64_t dt_w_d_stride;
+  int64_t dt_x_batch_stride, dt_x_group_stride, dt_x_r_stride;
+  int32_t dt_rank;
 } selscan_fwd_args;
 
 /* replaces selective_scan_cuda.bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_,
@@ -104,6 +113,15 @@ typedef struct selscan_bwd_args {
   float* dC;                         /* (batch, ngroups, dstate, seqlen) contiguous, ZERO-INITIALISED */
   float* dD;                         /* (dim) ZERO-INITIALISED; required iff D != NULL */
   float* ddelta_bias;                /* (dim) ZERO-INITIALISED; required iff delta_bias != NULL */
+  /* Fused dt_proj (code/networks/mamba_sys.py:408-412).  When dt_w != NULL, `delta` is ignored (may be
+   * NULL: no (batch, dim, seqlen) step tensor exists) and the kernels form the raw step themselves,
+   *     delta[b, d, l] = sum_r dt_w[d, r] * dt_x[b, d / (dim / ngroups), r, l],
+   * before the bias / softplus; `ddelta` is still written (the gradient w.r.t. that raw step).  Only the tiled kernels do this: ask selscan_b200_dt_fusable() first. */
+  const float* dt_w;                 /* (dim, dt_rank), unit stride along r, or NULL */
+  const float* dt_x;                 /* (batch, ngroups, dt_rank, seqlen), unit stride along seqlen, 16-byte aligned rows */
+  int64_t dt_w_d_stride;
+  int64_t dt_x_batch_stride, dt_x_group_stride, dt_x_r_stride;
+  int32_t dt_rank;
 } selscan_bwd_args;
 
 int selscan_b200_abi_version(void);
@@ -116,6 +134,10 @@ const char* selscan_b200_last_error(void);
 /* number of floats the `ckpt` scratch of one (batch, dim, seqlen, dstate) problem needs (may be 0):
  * ceil(dstate / 16) * batch * dim * (ceil(seqlen / 8) - 1) * 16 */
 int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+
+/* 1 when a call of these sizes can take dt_w / dt_x (fused dt_proj): dt_rank <= 12, dstate <= 16, channels per group a multiple of
+ * 64, seqlen > 8 and a multiple of 4, enough work to run unsegmented, and a device that runs the tiled kernels; else 0 */
+int selscan_b200_dt_fusable(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups, int32_t dt_rank);
 
 /* floats of forward `workspace` that make the segmented small-batch path available; 0 when the call fills the chip anyway */
 int64_t selscan_b200_fwd_workspace_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups);

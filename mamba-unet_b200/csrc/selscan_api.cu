@@ -30,7 +30,14 @@ int check_common(const Args& a, const char* who) {
   if (a.dstate < 1) return fail("%s: dstate must be >= 1 (got %d)", who, a.dstate);
   if (a.dstate > 256) return fail("%s: selective_scan only supports state dimension <= 256 (got %d)", who, a.dstate);
   if (a.ngroups < 1 || a.dim % a.ngroups != 0) return fail("%s: dim (%d) must be divisible by ngroups (%d)", who, a.dim, a.ngroups);
-  if (!a.u || !a.delta || !a.A || !a.B || !a.C) return fail("%s: u, delta, A, B, C must not be NULL", who);
+  if (!a.u || (!a.delta && !a.dt_w) || !a.A || !a.B || !a.C) return fail("%s: u, delta (or dt_w / dt_x), A, B, C must not be NULL", who);
+  if (a.dt_w) {   // fused dt_proj: the raw step is formed inside the tiled kernels
+    if (!a.dt_x) return fail("%s: dt_x is required when dt_w is given", who);
+    if (a.dt_rank < 1 || a.dt_rank > selscan::kMaxFusedDtRank) return fail("%s: fused dt_proj supports 1 <= dt_rank <= %d (got %d)", who, selscan::kMaxFusedDtRank, a.dt_rank);
+    if (!al16(a.dt_x) || !m4(a.dt_x_batch_stride) || !m4(a.dt_x_group_stride) || !m4(a.dt_x_r_stride))
+      return fail("%s: dt_x rows must be 16-byte aligned (pointer and strides multiples of 4 floats)", who);
+    if (a.dt_w_d_stride < a.dt_rank) return fail("%s: dt_w_d_stride must be >= dt_rank", who);
+  }
   return 0;
 }
 
@@ -61,19 +68,30 @@ __attribute__((visibility("default"))) int64_t selscan_b200_fwd_workspace_elems(
   return (int64_t)batch * dim * n_segs * (SELSCAN_B200_STATE_PAD + 1);   // segment states + sums of delta
 }
 
+__attribute__((visibility("default"))) int selscan_b200_dt_fusable(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups,
+                                                                 int32_t dt_rank) {
+  if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0 || ngroups <= 0 || dim % ngroups) return 0;
+  if (dt_rank < 1 || dt_rank > selscan::kMaxFusedDtRank || dstate > SELSCAN_B200_STATE_PAD) return 0;
+  if ((dim / ngroups) % 64 != 0 || seqlen <= SELSCAN_B200_CKPT_INTERVAL || (seqlen & 3)) return 0;
+  if (selscan_b200_fwd_workspace_elems(batch, dim, seqlen, dstate, ngroups) > 0) return 0;   // small batches run segmented: not fused
+  return selscan::bwd_ws_usable() && !selscan::force_generic() ? 1 : 0;
+}
+
 __attribute__((visibility("default"))) int selscan_b200_fwd(const selscan_fwd_args* args, void* stream) {
   if (!args) return fail("selscan_b200_fwd: args is NULL");
   const selscan_fwd_args& a = *args;
   if (int rc = check_common(a, "selscan_b200_fwd")) return rc;
   if (!a.out) return fail("selscan_b200_fwd: out must not be NULL");
   if (a.z && !a.out_z) return fail("selscan_b200_fwd: out_z is required when z is given");
+  if (a.dt_w && (a.z || !selscan_b200_dt_fusable(a.batch, a.dim, a.seqlen, a.dstate, a.ngroups, a.dt_rank)))
+    return fail("selscan_b200_fwd: dt_w / dt_x (fused dt_proj) need z == NULL and sizes accepted by selscan_b200_dt_fusable()");
   selscan::FwdLaunch p;
   p.a = a;
   p.dim_per_group = a.dim / a.ngroups;
   p.n_ckpt = (a.seqlen + selscan::kCkptInterval - 1) / selscan::kCkptInterval - 1;
   if (p.n_ckpt < 0) p.n_ckpt = 0;
   if (a.ckpt && !al16(a.ckpt)) return fail("selscan_b200_fwd: ckpt must be 16-byte aligned");
-  p.vec_rows = al16(a.u) && al16(a.delta) && al16(a.out) && m4(a.u_batch_stride) && m4(a.u_d_stride) &&
+  p.vec_rows = al16(a.u) && (a.dt_w || al16(a.delta)) && al16(a.out) && m4(a.u_batch_stride) && m4(a.u_d_stride) &&
                m4(a.delta_batch_stride) && m4(a.delta_d_stride) && m4(a.out_batch_stride) && m4(a.out_d_stride) &&
                (!a.z || (al16(a.z) && al16(a.out_z) && m4(a.z_batch_stride) && m4(a.z_d_stride) &&
                          m4(a.out_z_batch_stride) && m4(a.out_z_d_stride)));
@@ -104,6 +122,8 @@ __attribute__((visibility("default"))) int selscan_b200_bwd(const selscan_bwd_ar
   if (a.z && (!a.out || !a.dz)) return fail("selscan_b200_bwd: out and dz are required when z is given");
   if (a.D && !a.dD) return fail("selscan_b200_bwd: dD is required when D is given");
   if (a.delta_bias && !a.ddelta_bias) return fail("selscan_b200_bwd: ddelta_bias is required when delta_bias is given");
+  if (a.dt_w && (a.z || !selscan_b200_dt_fusable(a.batch, a.dim, a.seqlen, a.dstate, a.ngroups, a.dt_rank)))
+    return fail("selscan_b200_bwd: dt_w / dt_x (fused dt_proj) need z == NULL and sizes accepted by selscan_b200_dt_fusable()");
   selscan::BwdLaunch p;
   p.a = a;
   if (!a.D) p.a.dD = nullptr;
@@ -116,7 +136,7 @@ __attribute__((visibility("default"))) int selscan_b200_bwd(const selscan_bwd_ar
   p.tiles_per_group = (p.dim_per_group + 63) / 64;
   if (a.du_d_stride < a.seqlen || a.ddelta_d_stride < a.seqlen || (a.z && a.dz_d_stride < a.seqlen))
     return fail("selscan_b200_bwd: du / ddelta / dz channel strides must be >= seqlen");
-  p.vec_rows = al16(a.u) && al16(a.delta) && al16(a.dout) && al16(a.du) && al16(a.ddelta) &&
+  p.vec_rows = al16(a.u) && (a.dt_w || al16(a.delta)) && al16(a.dout) && al16(a.du) && al16(a.ddelta) &&
                m4(a.u_batch_stride) && m4(a.u_d_stride) && m4(a.delta_batch_stride) && m4(a.delta_d_stride) &&
                m4(a.dout_batch_stride) && m4(a.dout_d_stride) && m4(a.du_batch_stride) && m4(a.du_d_stride) &&
                m4(a.ddelta_batch_stride) && m4(a.ddelta_d_stride) &&

@@ -56,7 +56,7 @@ constexpr int kPP = kHP * 32 + 16;   // floats per channel pair in a P half: 4 p
                                      // a quarter-warp store to disjoint banks and readers need no swizzle
 constexpr int kS12P = 36;            // floats per row in an S12 half (32 + 16 bytes: conflict-free STS.128 by (row, lane), LDS.128 by row)
 
-template <bool kHasZ>
+template <bool kHasZ, int kDt>
 struct WsSmemT {
   float CK[kStg][kR * kStatePad];   // [row][16 states]                                    (TMA)
   float U[kStg][kR * kC];           // [row][8 positions] (one 64 x 8 box)                  (TMA)
@@ -67,6 +67,8 @@ struct WsSmemT {
   // overwrite dout with dout * silu(z) and `out` with dz in place, and dz leaves by a TMA store of the whole stage tile
   float Z[kHasZ ? kStg : 1][kHasZ ? kR * kC : 64];
   float O[kHasZ ? kStg : 1][kHasZ ? kR * kC : 64];
+  // fused dt_proj only (mamba_sys.py:409): the dt rows of x_dbl, [rank][8 positions] dense (TMA), instead of the DT tile
+  float XDT[kStg][kDt > 0 ? (kDt * kC + 31) / 32 * 32 : 32];   // (multiples of 128 bytes: TMA tiles before and after stay aligned)
   float BC[kStg][kC * kPitch];      // [position][B0..15 C0..15]                            (helper)
   float SD[kStg][kR * kC];          // delta   [row][8]                                     (helper)
   float SDU[kStg][kR * kC];         // delta*u
@@ -103,14 +105,15 @@ __device__ __forceinline__ u64 mul2v(u64 a, u64 b) {
 }
 __device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-template <bool kHasZ>
+template <bool kHasZ, int kDt>
 __global__ void __launch_bounds__(kThr, 2)
 selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                       const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
                       const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt,
                       const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_o,
                       const __grid_constant__ CUtensorMap map_dz, const BwdLaunch p) {
-  using WsSmem = WsSmemT<kHasZ>;
+  // kDt > 0: map_dt is the 4-D map over dt_x (seqlen, rank, group, batch); the helpers form the raw step themselves
+  using WsSmem = WsSmemT<kHasZ, kDt>;
   extern __shared__ unsigned char smem_raw[];
   WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 255) & ~(uintptr_t)255);   // 32B-swizzle atom = 256 B
   const selscan_bwd_args& a = p.a;
@@ -166,6 +169,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
     const float bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
     const bool softplus = a.delta_softplus != 0;
+    float Wd[kDt > 0 ? kDt : 1];            // my channel's row of the dt_proj weight (zero beyond dt_rank)
+    if (kDt > 0) {
+#pragma unroll
+      for (int r = 0; r < kDt; ++r) Wd[r] = (r < a.dt_rank) ? __ldg(a.dt_w + (int64_t)d * a.dt_w_d_stride + r) : 0.f;
+    }
     const uint32_t my16 = (uint32_t)row * (kC * 4) + (uint32_t)((hf ^ ((row >> 2) & 1)) << 4);   // my 4 elements in every [row][8] tile
     const uint32_t out16 = (uint32_t)hf * (kR * 16) + (uint32_t)row * 16;    // ... and in the [half][row][4] output tiles
 
@@ -199,13 +207,15 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       if (j >= kStg) mbar_wait(smem_u32(&sm.stage_free[s]), (uint32_t)((j / kStg - 1) & 1));
       if (kHasZ) tma_store_wait_read<0>();   // my dz store out of this stage's O tile (three chunks ago) has read it
       const uint32_t full = smem_u32(&sm.tma_full[s]);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)((kHasZ ? 5 : 3) * kR * kC * 4 + kR * kStatePad * 4)) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full),
+                   "r"((uint32_t)(((kHasZ ? 5 : 3) - (kDt > 0 ? 1 : 0)) * kR * kC * 4 + kDt * kC * 4 + kR * kStatePad * 4)) : "memory");
       if (kHasZ) {
         tma_load_3d(smem_u32(sm.Z[s]), &map_z, l0, d0, b, full);
         tma_load_3d(smem_u32(sm.O[s]), &map_o, l0, d0, b, full);
       }
       tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
-      tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
+      if (kDt > 0) tma_load_4d(smem_u32(sm.XDT[s]), &map_dt, l0, 0, g, b, full);   // ranks >= dt_rank / positions >= seqlen: zero fill
+      else tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
       tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
       // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
       tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, b * a.dim + d0, full);
@@ -215,7 +225,18 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC + hf * kHP;
       mbar_wait(smem_u32(&sm.tma_full[s]), (uint32_t)((j / kStg) & 1));
       const float4 u4 = lds_f4(smem_u32(sm.U[s]) + my16);
-      const float4 t4 = lds_f4(smem_u32(sm.DT[s]) + my16);
+      float4 t4;
+      if (kDt > 0) {   // raw step of my 4 positions: dt_w[d, :] . dt_x[:, l]  (all rows of a warp read the same 16 bytes: broadcast)
+        t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kDt; ++r) {
+          const float4 x4 = lds_f4(smem_u32(sm.XDT[s]) + (uint32_t)(r * (kC * 4) + hf * 16));
+          t4.x = fmaf(Wd[r], x4.x, t4.x); t4.y = fmaf(Wd[r], x4.y, t4.y);
+          t4.z = fmaf(Wd[r], x4.z, t4.z); t4.w = fmaf(Wd[r], x4.w, t4.w);
+        }
+      } else {
+        t4 = lds_f4(smem_u32(sm.DT[s]) + my16);
+      }
       const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
       float v[4], vu[4], sg[4];
 #pragma unroll
@@ -541,12 +562,15 @@ inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int
 // arithmetic assumes (otherwise setmaxnreg.inc could wait for registers that never come).
 bool bwd_ws_usable() {
   static const bool ok = [] {
-    cudaFuncAttributes fa, fz;
-    if (cudaFuncGetAttributes(&fa, selscan_bwd_ws_kernel<false>) != cudaSuccess || cudaFuncGetAttributes(&fz, selscan_bwd_ws_kernel<true>) != cudaSuccess) {
+    cudaFuncAttributes fa[4];
+    if (cudaFuncGetAttributes(&fa[0], selscan_bwd_ws_kernel<false, 0>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[1], selscan_bwd_ws_kernel<true, 0>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[2], selscan_bwd_ws_kernel<false, 6>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[3], selscan_bwd_ws_kernel<false, kMaxFusedDtRank>) != cudaSuccess) {
       (void)cudaGetLastError();
       return false;
     }
-    return fa.numRegs == kLaunchRegs && fz.numRegs == kLaunchRegs;
+    return fa[0].numRegs == kLaunchRegs && fa[1].numRegs == kLaunchRegs && fa[2].numRegs == kLaunchRegs && fa[3].numRegs == kLaunchRegs;
   }();
   return ok;
 }
@@ -559,7 +583,7 @@ bool bwd_ws_eligible(const BwdLaunch& p) {
   if (a.B_l_stride != a.C_l_stride) return false;      // the B/C gather walks both with one step
   const int64_t one_batch = 4;   // batch 1: the batch stride is unused (any positive multiple of 4 passes the check)
   if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : one_batch)) return false;
-  if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : one_batch)) return false;
+  if (a.dt_w == nullptr && !tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : one_batch)) return false;
   if (!tma_row_ok(a.dout, a.dout_d_stride, a.batch > 1 ? a.dout_batch_stride : one_batch)) return false;
   if (!tma_row_ok(a.du, a.du_d_stride, a.batch > 1 ? a.du_batch_stride : one_batch)) return false;
   if (!tma_row_ok(a.ddelta, a.ddelta_d_stride, a.batch > 1 ? a.ddelta_batch_stride : one_batch)) return false;
@@ -573,37 +597,56 @@ bool bwd_ws_eligible(const BwdLaunch& p) {
   return tensor_map_encoder() != nullptr && bwd_ws_usable();
 }
 
+// 4-D map over dt_x (fastest first: seqlen, rank, group, batch), box = 8 positions x kDt ranks, dense 32-byte rows
+inline bool make_dtx_map_bwd(CUtensorMap* map, const selscan_bwd_args& a, int box_r) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[4] = {(cuuint64_t)a.seqlen, (cuuint64_t)a.dt_rank, (cuuint64_t)a.ngroups, (cuuint64_t)a.batch};
+  const cuuint64_t gstr[3] = {(cuuint64_t)a.dt_x_r_stride * 4, (cuuint64_t)(a.ngroups > 1 ? a.dt_x_group_stride : a.dt_x_r_stride * a.dt_rank) * 4,
+                              (cuuint64_t)(a.batch > 1 ? a.dt_x_batch_stride : a.dt_x_r_stride * a.dt_rank * a.ngroups) * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)kC, (cuuint32_t)box_r, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.dt_x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool kHasZ, int kDt>
+cudaError_t launch_ws_variant(const CUtensorMap (&m)[9], const BwdLaunch& p, unsigned grid, cudaStream_t stream) {
+  constexpr int smem = (int)sizeof(WsSmemT<kHasZ, kDt>) + 256;
+  static_assert(kHasZ || sizeof(WsSmemT<kHasZ, kDt>) + 256 + 1024 <= 116736, "two CTAs per SM");
+  static_assert(sizeof(WsSmemT<kHasZ, kDt>) + 256 <= 232448, "fits one CTA per SM");
+  static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
+  if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<kHasZ, kDt>, smem)) return e;
+  selscan_bwd_ws_kernel<kHasZ, kDt><<<grid, kThr, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], p);
+  return cudaGetLastError();
+}
+
 // Returns cudaErrorNotSupported when a tensor map cannot be encoded for this layout: the caller then takes the generic kernel.
 cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
-  CUtensorMap mu, mdt, mdy, mck, mdu, mddt;
-  if (!make_row_map_sw(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
-      !make_row_map_sw(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
-      !make_row_map_sw(&mdy, a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
-      !make_row_map(&mdu, a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
-      !make_row_map(&mddt, a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR) ||
-      !make_ckpt_map(&mck, a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt))
+  CUtensorMap m[9];   // u, delta (or dt_x), dout, saved states, du, ddelta, z, out, dz
+  const int dt_box = a.dt_w == nullptr ? 0 : (a.dt_rank <= 6 ? 6 : kMaxFusedDtRank);
+  if (!make_row_map_sw(&m[0], a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+      !(dt_box ? make_dtx_map_bwd(&m[1], a, dt_box)
+               : make_row_map_sw(&m[1], a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B)) ||
+      !make_row_map_sw(&m[2], a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+      !make_ckpt_map(&m[3], a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt) ||
+      !make_row_map(&m[4], a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
+      !make_row_map(&m[5], a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR))
     return cudaErrorNotSupported;
-  static_assert(sizeof(WsSmemT<false>) + 256 + 1024 <= 116736, "two CTAs per SM");
-  static_assert(sizeof(WsSmemT<true>) + 256 <= 232448, "the gated variant fits one CTA per SM");
+  m[6] = m[7] = m[8] = m[0];
   const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kR));
   if (a.z != nullptr) {
-    CUtensorMap mz, mo, mdz;
-    if (!make_row_map_sw(&mz, a.z, a.seqlen, a.dim, a.batch, a.z_d_stride, a.z_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
-        !make_row_map_sw(&mo, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
-        !make_row_map_sw(&mdz, a.dz, a.seqlen, a.dim, a.batch, a.dz_d_stride, a.dz_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B))
+    if (dt_box) return cudaErrorNotSupported;   // (the C ABI rejects the combination earlier)
+    if (!make_row_map_sw(&m[6], a.z, a.seqlen, a.dim, a.batch, a.z_d_stride, a.z_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_row_map_sw(&m[7], a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+        !make_row_map_sw(&m[8], a.dz, a.seqlen, a.dim, a.batch, a.dz_d_stride, a.dz_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B))
       return cudaErrorNotSupported;
-    constexpr int smem = (int)sizeof(WsSmemT<true>) + 256;
-    static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
-    if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<true>, smem)) return e;
-    selscan_bwd_ws_kernel<true><<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, mz, mo, mdz, p);
-  } else {
-    constexpr int smem = (int)sizeof(WsSmemT<false>) + 256;
-    static std::atomic<unsigned long long> configured{0};
-    if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<false>, smem)) return e;
-    selscan_bwd_ws_kernel<false><<<grid, kThr, smem, stream>>>(mu, mdt, mdy, mck, mdu, mddt, mu, mu, mu, p);
+    return launch_ws_variant<true, 0>(m, p, grid, stream);
   }
-  return cudaGetLastError();
+  if (dt_box == 6) return launch_ws_variant<false, 6>(m, p, grid, stream);
+  if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank>(m, p, grid, stream);
+  return launch_ws_variant<false, 0>(m, p, grid, stream);
 }
 
 }  // namespace selscan

@@ -15,6 +15,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr int kStatePad = 16;     // SELSCAN_B200_STATE_PAD
 constexpr int kCkptInterval = 8;  // SELSCAN_B200_CKPT_INTERVAL
+constexpr int kMaxFusedDtRank = 12;   // fused dt_proj: ranks above this cost more FMAs per element than a GEMM pass saves
 
 // MUFU.EX2 (one SFU op, flush-to-zero): the only transcendental on the per-(position, state) path.
 __device__ __forceinline__ float ex2(float x) {

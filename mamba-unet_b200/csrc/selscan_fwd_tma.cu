@@ -56,7 +56,8 @@ constexpr int kTileBytes = kRows * kTL * 4;          // 8 KB
 constexpr int kOutBytes = kWarpRows * kTL * 4;       // 2 KB
 
 // shared-memory carve-up (bytes from a 1024-byte aligned base; every TMA tile is a multiple of 1024 bytes)
-template <bool kHasZ>
+// kDt > 0: fused dt_proj -- the stage carries a [kDt ranks][32 positions] tile of x_dbl's dt rows instead of a delta tile
+template <bool kHasZ, int kDt = 0>
 struct Lay {
   static constexpr int kStages = kHasZ ? 2 : SELSCAN_FWD_STAGES;
   static constexpr int kCtas = kHasZ ? 2 : SELSCAN_FWD_CTAS;
@@ -65,7 +66,9 @@ struct Lay {
   static constexpr uint32_t oIn = 0;                                            // [stage][which]
   static constexpr uint32_t oOut = oIn + kStages * kIn * kTileBytes;           // [warp][buffer][which]
   static constexpr uint32_t oBC = oOut + kConsWarps * 2 * kOut * kOutBytes;    // [stage][position][36]
-  static constexpr uint32_t oBar = oBC + kStages * kTL * kBCPitch * 4;         // full[stage], empty[stage]
+  static constexpr uint32_t oDt = oBC + kStages * kTL * kBCPitch * 4;          // [stage][rank][32 positions] (TMA, dense 128-byte rows)
+  static constexpr uint32_t kDtBytes = kDt * kTL * 4;
+  static constexpr uint32_t oBar = oDt + kStages * kDtBytes;                   // full[stage], empty[stage]
   static constexpr uint32_t kBytes = oBar + 2 * kStages * 8;
 };
 
@@ -96,12 +99,13 @@ __device__ __forceinline__ Item decode_item(const FwdLaunch& p, int item) {
 }
 
 // kMode 0: whole sequence per item.  1: segment aggregates only (no outputs).  2: segment with an initial state.
-template <int kMode, bool kHasZ>
-__global__ void __launch_bounds__(kThreads, Lay<kHasZ>::kCtas)
+template <int kMode, bool kHasZ, int kDt>
+__global__ void __launch_bounds__(kThreads, Lay<kHasZ, kDt>::kCtas)
 selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                        const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
                        const __grid_constant__ CUtensorMap map_outz, const FwdLaunch p, const int n_items) {
-  using LY = Lay<kHasZ>;
+  // kDt > 0: map_dt is the 4-D map over dt_x (seqlen, rank, group, batch) and the raw step is formed here (mamba_sys.py:409)
+  using LY = Lay<kHasZ, kDt>;
   constexpr int kStages = LY::kStages;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sm0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,9 +147,15 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         const int l0 = (w.t_begin + t) * kTL;
         const uint32_t full = full_bar(s);
         if (lane == 0) {
-          mbar_expect_tx(full, (uint32_t)((kHasZ && kMode != 1) ? 3 : 2) * kTileBytes);
-          tma_load_3d(in_tile(s, 0), &map_u, l0, w.d0, w.b, full);
-          tma_load_3d(in_tile(s, 1), &map_dt, l0, w.d0, w.b, full);
+          if (kDt > 0) {
+            mbar_expect_tx(full, (uint32_t)kTileBytes + LY::kDtBytes);
+            tma_load_3d(in_tile(s, 0), &map_u, l0, w.d0, w.b, full);
+            tma_load_4d(sm0 + LY::oDt + (uint32_t)s * LY::kDtBytes, &map_dt, l0, 0, w.g, w.b, full);   // ranks >= dt_rank: zero fill
+          } else {
+            mbar_expect_tx(full, (uint32_t)((kHasZ && kMode != 1) ? 3 : 2) * kTileBytes);
+            tma_load_3d(in_tile(s, 0), &map_u, l0, w.d0, w.b, full);
+            tma_load_3d(in_tile(s, 1), &map_dt, l0, w.d0, w.b, full);
+          }
           if (kHasZ && kMode != 1) tma_load_3d(in_tile(s, 2), &map_z, l0, w.d0, w.b, full);
         }
         const uint32_t bc = sm0 + LY::oBC + (uint32_t)s * (kTL * kBCPitch * 4);
@@ -189,6 +199,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   struct Params {
     u64 A2p[4];
     float Dv, bias;
+    float Wd[kDt > 0 ? kDt : 1];   // my channel's row of the dt_proj weight (zero beyond dt_rank)
   };
   auto load_params = [&](const Item& w, Params& q) {
     const int d = w.d0 + rr;
@@ -209,6 +220,10 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     for (int n = 0; n < 4; ++n) q.A2p[n] = pk2(av[2 * n] * kLog2e, av[2 * n + 1] * kLog2e);
     q.Dv = a.D ? __ldg(a.D + d) : 0.f;
     q.bias = a.delta_bias ? __ldg(a.delta_bias + d) : 0.f;
+    if (kDt > 0) {
+#pragma unroll
+      for (int r = 0; r < kDt; ++r) q.Wd[r] = (r < a.dt_rank) ? __ldg(a.dt_w + (int64_t)d * a.dt_w_d_stride + r) : 0.f;
+    }
   };
 
   uint32_t it = 0;        // tiles consumed by this CTA: ring position
@@ -250,6 +265,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       const uint32_t dt_row = in_tile(s, 1) + rr * (kTL * 4);
       const uint32_t z_row = in_tile(s, kHasZ ? 2 : 0) + rr * (kTL * 4) + h * 8;
       const uint32_t bc_base = sm0 + LY::oBC + (uint32_t)s * (kTL * kBCPitch * 4) + h * (kLaneStates * 4);
+      const uint32_t xdt_base = sm0 + LY::oDt + (uint32_t)s * LY::kDtBytes + h * 8;   // my two positions of a quad in every rank row
       const uint32_t out_tile = sm0 + LY::oOut + (uint32_t)((warp * 2 + (n_out & 1)) * LY::kOut) * kOutBytes;
       const uint32_t out_row = out_tile + ch * (kTL * 4) + h * 8;
       // Software pipeline over the 8 quads of the tile: while quad q's recurrence runs, quad q+1's row data is loaded,
@@ -258,10 +274,23 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       float yp[4], up0 = 0.f, up1 = 0.f;   // quad q-1: partial sums and my two u values
       auto prefetch = [&](int q, float (&uv)[4], float (&dl)[4]) {
         const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
-        const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
         uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w;
         // my two positions of the quad: discretise delta once per element, then exchange with the partner lane
-        float m0 = (hi ? d4.z : d4.x) + bias, m1 = (hi ? d4.w : d4.y) + bias;
+        float m0, m1;
+        if (kDt > 0) {   // delta = dt_w[d, :] . dt_x[:, l] + bias: rank-R expansion in registers, no (batch, dim, seqlen) step tensor
+          m0 = m1 = bias;
+#pragma unroll
+          for (int r = 0; r < kDt; ++r) {
+            float x0, x1;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(xdt_base + (uint32_t)(r * (kTL * 4) + q * 16)));
+            m0 = fmaf(cur.Wd[r], x0, m0);
+            m1 = fmaf(cur.Wd[r], x1, m1);
+          }
+        } else {
+          const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
+          m0 = (hi ? d4.z : d4.x) + bias;
+          m1 = (hi ? d4.w : d4.y) + bias;
+        }
         {   // branch-free on the (uniform) softplus flag: a branch here would split the tile into basic blocks and
             // serialise this latency chain (LDS -> EX2 -> RCP -> polynomial -> SHFL) against the recurrence
           float w_unused;
@@ -413,16 +442,30 @@ __global__ void selscan_fwd_combine_kernel(const FwdLaunch p) {
   }
 }
 
-template <int kMode, bool kHasZ>
+template <int kMode, bool kHasZ, int kDt = 0>
 cudaError_t launch_one(const CUtensorMap& mu, const CUtensorMap& mdt, const CUtensorMap& mz, const CUtensorMap& mout,
                        const CUtensorMap& moutz, const FwdLaunch& p, int n_items, cudaStream_t stream) {
-  constexpr int smem = (int)Lay<kHasZ>::kBytes + 1024;
+  constexpr int smem = (int)Lay<kHasZ, kDt>::kBytes + 1024;
   static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
-  if (const cudaError_t e = set_smem_once(configured, selscan_fwd_tma_kernel<kMode, kHasZ>, smem)) return e;
-  const int slots = sm_count() * Lay<kHasZ>::kCtas;
+  if (const cudaError_t e = set_smem_once(configured, selscan_fwd_tma_kernel<kMode, kHasZ, kDt>, smem)) return e;
+  const int slots = sm_count() * Lay<kHasZ, kDt>::kCtas;
   const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);
-  selscan_fwd_tma_kernel<kMode, kHasZ><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, p, n_items);
+  selscan_fwd_tma_kernel<kMode, kHasZ, kDt><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, p, n_items);
   return cudaGetLastError();
+}
+
+// 4-D map over dt_x (fastest first: seqlen, rank, group, batch), box = 32 positions x kDt ranks, dense rows; ranks >= dt_rank are
+// out of bounds and read as zeros
+inline bool make_dtx_map(CUtensorMap* map, const selscan_fwd_args& a, int box_l, int box_r) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[4] = {(cuuint64_t)a.seqlen, (cuuint64_t)a.dt_rank, (cuuint64_t)a.ngroups, (cuuint64_t)a.batch};
+  const cuuint64_t gstr[3] = {(cuuint64_t)a.dt_x_r_stride * 4, (cuuint64_t)(a.ngroups > 1 ? a.dt_x_group_stride : a.dt_x_r_stride * a.dt_rank) * 4,
+                              (cuuint64_t)(a.batch > 1 ? a.dt_x_batch_stride : a.dt_x_r_stride * a.dt_rank * a.ngroups) * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)box_l, (cuuint32_t)box_r, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(a.dt_x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -453,7 +496,7 @@ bool fwd_tma_eligible(const FwdLaunch& p) {
   if (p.dim_per_group % kRows != 0) return false;
   if (a.seqlen < 1 || a.batch < 1) return false;
   if (!tma_row_ok(a.u, a.u_d_stride, a.batch > 1 ? a.u_batch_stride : 4)) return false;
-  if (!tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : 4)) return false;
+  if (a.dt_w == nullptr && !tma_row_ok(a.delta, a.delta_d_stride, a.batch > 1 ? a.delta_batch_stride : 4)) return false;
   if (!tma_row_ok(a.out, a.out_d_stride, a.batch > 1 ? a.out_batch_stride : 4)) return false;
   if (a.z != nullptr) {
     if (!tma_row_ok(a.z, a.z_d_stride, a.batch > 1 ? a.z_batch_stride : 4)) return false;
@@ -466,8 +509,10 @@ bool fwd_tma_eligible(const FwdLaunch& p) {
 cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   const selscan_fwd_args& a = p.a;
   CUtensorMap mu, mdt, mout, mz, moutz;
+  const int dt_box = a.dt_w == nullptr ? 0 : (a.dt_rank <= 6 ? 6 : kMaxFusedDtRank);
   if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kTL, kRows) ||
-      !make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kTL, kRows) ||
+      !(dt_box ? make_dtx_map(&mdt, a, kTL, dt_box)
+               : make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kTL, kRows)) ||
       !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, kWarpRows))
     return cudaErrorNotSupported;
   const bool has_z = a.z != nullptr;
@@ -483,6 +528,11 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   FwdLaunch q = p;
   q.n_segs = 1;
   fwd_plan_segments(a.batch, a.dim, a.seqlen, a.ngroups, &q.n_segs, &q.seg_tiles);
+  if (dt_box) {   // fused dt_proj: whole sequences only (selscan_b200_dt_fusable excludes the segmented sizes), no z
+    q.n_segs = 1;
+    return dt_box == 6 ? launch_one<0, false, 6>(mu, mdt, mz, mout, moutz, q, n_base, stream)
+                       : launch_one<0, false, kMaxFusedDtRank>(mu, mdt, mz, mout, moutz, q, n_base, stream);
+  }
   if (p.seg_ws == nullptr || q.n_segs < 2) {
     q.n_segs = 1;
     return has_z ? launch_one<0, true>(mu, mdt, mz, mout, moutz, q, n_base, stream)

@@ -10,11 +10,16 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # SELSCAN_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
 LIB_PATH = os.environ.get("SELSCAN_B200_LIB") or os.path.join(_PKG, "lib", "libselscan_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 CKPT_INTERVAL = 8
 STATE_PAD = 16
 
 _i32, _i64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+
+# fused dt_proj inputs, the tail of both argument structs
+_DT_FIELDS = [("dt_w", _ptr), ("dt_x", _ptr), ("dt_w_d_stride", _i64), ("dt_x_batch_stride", _i64), ("dt_x_group_stride", _i64),
+              ("dt_x_r_stride", _i64), ("dt_rank", _i32)]
 
 
 class FwdArgs(ctypes.Structure):
@@ -30,6 +35,7 @@ class FwdArgs(ctypes.Structure):
         + [("out", _ptr), ("out_batch_stride", _i64), ("out_d_stride", _i64),
            ("out_z", _ptr), ("out_z_batch_stride", _i64), ("out_z_d_stride", _i64),
            ("last_state", _ptr), ("ckpt", _ptr), ("workspace", _ptr)]
+        + _DT_FIELDS
     )
 
 
@@ -46,6 +52,7 @@ class BwdArgs(ctypes.Structure):
             "out_batch_stride", "out_d_stride", "du_batch_stride", "du_d_stride",
             "ddelta_batch_stride", "ddelta_d_stride", "dz_batch_stride", "dz_d_stride")]
         + [(n, _ptr) for n in ("du", "ddelta", "dz", "dA", "dB", "dC", "dD", "ddelta_bias")]
+        + _DT_FIELDS
     )
 
 
@@ -76,6 +83,8 @@ def load():
         lib.selscan_b200_ckpt_elems.argtypes = [_i32] * 4
         lib.selscan_b200_fwd_workspace_elems.restype = ctypes.c_int64
         lib.selscan_b200_fwd_workspace_elems.argtypes = [_i32] * 5
+        lib.selscan_b200_dt_fusable.restype = ctypes.c_int
+        lib.selscan_b200_dt_fusable.argtypes = [_i32] * 6
         lib.selscan_b200_fwd.restype = ctypes.c_int
         lib.selscan_b200_fwd.argtypes = [ctypes.POINTER(FwdArgs), _ptr]
         lib.selscan_b200_bwd.restype = ctypes.c_int

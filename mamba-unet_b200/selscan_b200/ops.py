@@ -104,18 +104,36 @@ def _require_f32_cuda(**tensors):
             raise RuntimeError(f"selscan_b200: {name} is on {t.device}, expected {dev}")
 
 
+def _dt_fields(dt_w, dt_x):
+    """Tail of both argument structs: the fused dt_proj inputs (dt_w (dim, R) rows, dt_x (batch, G, R, L) unit stride along L)."""
+    if dt_w is None:
+        return dict(dt_w=None, dt_x=None, dt_w_d_stride=0, dt_x_batch_stride=0, dt_x_group_stride=0, dt_x_r_stride=0, dt_rank=0)
+    if dt_w.dim() != 2 or dt_w.stride(1) != 1 or dt_x.dim() != 4 or dt_x.stride(3) != 1 or dt_x.shape[2] != dt_w.shape[1]:
+        raise RuntimeError("selscan_b200: dt_w must be (dim, R) with unit stride along R and dt_x (batch, G, R, L) with unit stride along L")
+    return dict(dt_w=_p(dt_w), dt_x=_p(dt_x), dt_w_d_stride=dt_w.stride(0), dt_x_batch_stride=dt_x.stride(0),
+                dt_x_group_stride=dt_x.stride(1), dt_x_r_stride=dt_x.stride(2), dt_rank=dt_w.shape[1])
+
+
+def dt_fusable(batch, dim, seqlen, dstate, ngroups, dt_rank):
+    """True when calls of these sizes may pass dt_w / dt_x instead of a materialised delta (selscan_b200_dt_fusable)."""
+    return bool(_lib.load().selscan_b200_dt_fusable(batch, dim, seqlen, dstate, ngroups, dt_rank))
+
+
 def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=None, last_state=None, ckpt=None,
-               workspace=None):
+               workspace=None, dt_w=None, dt_x=None):
     """One selscan_b200_fwd call on the current stream.  All tensors fp32 CUDA; B, C 4-D (batch, G, N, L);
-    u/delta/z/out unit-stride along seqlen; outputs preallocated by the caller (the library never allocates)."""
+    u/delta/z/out unit-stride along seqlen; outputs preallocated by the caller (the library never allocates).
+    dt_w / dt_x: fused dt_proj (delta may then be None; see dt_fusable)."""
     lib = _lib.load()
     _require_f32_cuda(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=delta_bias, out=out, out_z=out_z,
-                      last_state=last_state, ckpt=ckpt, workspace=workspace)
+                      last_state=last_state, ckpt=ckpt, workspace=workspace, dt_w=dt_w, dt_x=dt_x)
     batch, dim, seqlen = u.shape
+    if delta is None:
+        delta = u if dt_w is not None else None   # strides only; the pointer is passed as NULL below
     a = _lib.FwdArgs(
         batch=batch, dim=dim, seqlen=seqlen, dstate=A.shape[1], ngroups=B.shape[1],
         delta_softplus=int(bool(delta_softplus)),
-        u=_p(u), delta=_p(delta), A=_p(A), B=_p(B), C=_p(C), D=_p(D), z=_p(z), delta_bias=_p(delta_bias),
+        u=_p(u), delta=None if dt_w is not None else _p(delta), A=_p(A), B=_p(B), C=_p(C), D=_p(D), z=_p(z), delta_bias=_p(delta_bias),
         u_batch_stride=u.stride(0), u_d_stride=u.stride(1),
         delta_batch_stride=delta.stride(0), delta_d_stride=delta.stride(1),
         A_d_stride=A.stride(0), A_n_stride=A.stride(1),
@@ -124,22 +142,25 @@ def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=N
         z_batch_stride=_strides2(z)[0], z_d_stride=_strides2(z)[1],
         out=_p(out), out_batch_stride=out.stride(0), out_d_stride=out.stride(1),
         out_z=_p(out_z), out_z_batch_stride=_strides2(out_z)[0], out_z_d_stride=_strides2(out_z)[1],
-        last_state=_p(last_state), ckpt=_p(ckpt), workspace=_p(workspace))
+        last_state=_p(last_state), ckpt=_p(ckpt), workspace=_p(workspace), **_dt_fields(dt_w, dt_x))
     with torch.cuda.device(u.device):
         _lib.check(lib.selscan_b200_fwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_fwd")
 
 
 def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softplus,
-               du, ddelta, dA, dB, dC, dD=None, dz=None, ddelta_bias=None):
-    """One selscan_b200_bwd call on the current stream.  dA, dB, dC, dD, ddelta_bias must be zero-initialised."""
+               du, ddelta, dA, dB, dC, dD=None, dz=None, ddelta_bias=None, dt_w=None, dt_x=None):
+    """One selscan_b200_bwd call on the current stream.  dA, dB, dC, dD, ddelta_bias must be zero-initialised.
+    dt_w / dt_x: fused dt_proj, as in launch_fwd; ddelta is then the gradient w.r.t. the raw step dt_w . dt_x."""
     lib = _lib.load()
     _require_f32_cuda(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=delta_bias, dout=dout, out=out, ckpt=ckpt, du=du,
-                      ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dz=dz, ddelta_bias=ddelta_bias)
+                      ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dz=dz, ddelta_bias=ddelta_bias, dt_w=dt_w, dt_x=dt_x)
     batch, dim, seqlen = u.shape
+    if delta is None:
+        delta = u if dt_w is not None else None
     a = _lib.BwdArgs(
         batch=batch, dim=dim, seqlen=seqlen, dstate=A.shape[1], ngroups=B.shape[1],
         delta_softplus=int(bool(delta_softplus)),
-        u=_p(u), delta=_p(delta), A=_p(A), B=_p(B), C=_p(C), D=_p(D), z=_p(z), delta_bias=_p(delta_bias),
+        u=_p(u), delta=None if dt_w is not None else _p(delta), A=_p(A), B=_p(B), C=_p(C), D=_p(D), z=_p(z), delta_bias=_p(delta_bias),
         dout=_p(dout), out=_p(out), ckpt=_p(ckpt),
         u_batch_stride=u.stride(0), u_d_stride=u.stride(1),
         delta_batch_stride=delta.stride(0), delta_d_stride=delta.stride(1),
@@ -153,7 +174,7 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
         ddelta_batch_stride=ddelta.stride(0), ddelta_d_stride=ddelta.stride(1),
         dz_batch_stride=_strides2(dz)[0], dz_d_stride=_strides2(dz)[1],
         du=_p(du), ddelta=_p(ddelta), dz=_p(dz), dA=_p(dA), dB=_p(dB), dC=_p(dC), dD=_p(dD),
-        ddelta_bias=_p(ddelta_bias))
+        ddelta_bias=_p(ddelta_bias), **_dt_fields(dt_w, dt_x))
     with torch.cuda.device(u.device):
         _lib.check(lib.selscan_b200_bwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_bwd")
 

@@ -209,6 +209,15 @@ def edge_out_bwd(g, H, W, z, zld, xhat, rstd, ln_w, ln_b, dz, dzld):
 TC_PROJ = True
 
 
+# dt_proj (+ bias + softplus) inside the scan kernels: the kernels read the dt rows of x_dbl and this module's
+# dt_projs_weight directly and no (B, 4D, L) step tensor is computed, stored for the backward or read.  The kernels take ranks up to
+# 12; measured on B200 at batch 24 (profiles/r02_fused_dt.json) the rank-6 expansion of stage 1 costs the two scan kernels what the
+# GEMM pass it replaces cost (+0.071 ms vs 0.076 ms per call: the scan is bound on the SM side, not by HBM) and frees 231 MB of saved
+# activations per block, while rank 12 (stage 2) costs twice its GEMM -- so the default fuses up to rank 6.  FUSE_DT = False: never.
+FUSE_DT = True
+FUSE_DT_MAX_RANK = 6
+
+
 def _tc_proj_ok(D, L, N, R):
     return TC_PROJ and L % 4 == 0 and D % 4 == 0
 
@@ -243,20 +252,26 @@ class SS2DFusedFn(torch.autograd.Function):
         needs_grad = any(ctx.needs_input_grad)
         xs = edge_in_fwd(xz, D, conv_w, conv_b)                                          # (B, K, D, L)
         tc = _tc_proj_ok(D, L, N, R)
+        fuse_dt = FUSE_DT and R <= FUSE_DT_MAX_RANK and ops.dt_fusable(B, K * D, L, N, K, R)   # :409-412 inside the scan kernels
+        dts = None
         if tc:
             from . import tcgemm
             C = R + 2 * N
             x_proj_w = x_proj_w.contiguous()
             x_dbl = xz.new_empty((B, K, C, L))
             tcgemm.bgemm(x_proj_w, xs.view(B * K, D, L), x_dbl.view(B * K, C, L), b_mn=True)          # W (C, D) x xs (D, L)
-            dtw_pad, R4 = _pad_dt_weight(dt_w)
-            dts = xz.new_empty((B, K, D, L))
-            tcgemm.bgemm(dtw_pad, x_dbl.view(B * K, C, L)[:, :R4], dts.view(B * K, D, L), b_mn=True)  # padded columns are zero
+            if not fuse_dt:
+                dtw_pad, R4 = _pad_dt_weight(dt_w)
+                dts = xz.new_empty((B, K, D, L))
+                tcgemm.bgemm(dtw_pad, x_dbl.view(B * K, C, L)[:, :R4], dts.view(B * K, D, L), b_mn=True)  # padded columns are zero
         else:
             x_dbl = torch.matmul(x_proj_w.unsqueeze(0), xs)                              # (B, K, R+2N, L)   :406
-            dts = torch.matmul(dt_w.unsqueeze(0), x_dbl[:, :, :R])                       # (B, K, D, L)      :409
-            if L % 4:                                                                    # rows must stay 16-byte aligned
-                dts = _empty_dirs(xz, B, D, L).copy_(dts)
+            if not fuse_dt:
+                dts = torch.matmul(dt_w.unsqueeze(0), x_dbl[:, :, :R])                   # (B, K, D, L)      :409
+                if L % 4:                                                                # rows must stay 16-byte aligned
+                    dts = _empty_dirs(xz, B, D, L).copy_(dts)
+        dt_w = dt_w.contiguous()
+        dt_args = dict(dt_w=dt_w.view(K * D, R), dt_x=x_dbl[:, :, :R]) if fuse_dt else {}
         As = -torch.exp(A_logs.float()).view(K * D, N)                                   # :417
         Dsf, dtb = Ds.float().reshape(-1).contiguous(), dt_b.float().reshape(-1).contiguous()
         out_y = _empty_dirs(xz, B, D, L)
@@ -266,14 +281,14 @@ class SS2DFusedFn(torch.autograd.Function):
         n_ws = ops.fwd_workspace_elems(B, K * D, L, N, K)
         if n_ws > 0:
             ws = xz.new_empty((n_ws,))
-        ops.launch_fwd(xs.view(B, K * D, L), dts.view(B, K * D, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], Dsf, None,
-                       dtb, True, out_y.view(B, K * D, L), None, None, ckpt, ws)      # :420-426
+        ops.launch_fwd(xs.view(B, K * D, L), None if fuse_dt else dts.view(B, K * D, L), As, x_dbl[:, :, R:R + N],
+                       x_dbl[:, :, R + N:], Dsf, None, dtb, True, out_y.view(B, K * D, L), None, None, ckpt, ws, **dt_args)   # :420-426
         zptr = xz.data_ptr() + D * xz.element_size()
         y, xhat, rstd = edge_out_fwd(out_y, H, W, zptr, D2, ln_w, ln_b, eps, needs_grad)  # :429-434, :536
         if needs_grad:
             ctx.save_for_backward(xz, xs, x_dbl, dts, As, ckpt, xhat, rstd, conv_w, conv_b, x_proj_w, dt_w, Dsf, dtb, ln_w, ln_b)
             ctx.shape_A, ctx.shape_D, ctx.shape_dtb = A_logs.shape, Ds.shape, dt_b.shape
-            ctx.tc = tc
+            ctx.tc, ctx.fuse_dt = tc, fuse_dt
         return y
 
     @staticmethod
@@ -295,9 +310,10 @@ class SS2DFusedFn(torch.autograd.Function):
         dB, dC = flat[:nbc].view(B, K, N, L), flat[nbc:2 * nbc].view(B, K, N, L)
         dA = flat[2 * nbc:2 * nbc + KD * N].view(KD, N)
         dD, dbias = flat[2 * nbc + KD * N:2 * nbc + KD * N + KD], flat[2 * nbc + KD * N + KD:]
-        ops.launch_bwd(xs.view(B, KD, L), dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], Dsf, None, dtb,
-                       d_ys.view(B, KD, L), None, ckpt, True, du.view(B, KD, L), ddelta.view(B, KD, L), dA, dB, dC, dD,
-                       None, dbias)
+        dt_args = dict(dt_w=dt_w.view(KD, R), dt_x=x_dbl[:, :, :R]) if ctx.fuse_dt else {}
+        ops.launch_bwd(xs.view(B, KD, L), None if ctx.fuse_dt else dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
+                       Dsf, None, dtb, d_ys.view(B, KD, L), None, ckpt, True, du.view(B, KD, L), ddelta.view(B, KD, L), dA, dB, dC,
+                       dD, None, dbias, **dt_args)
         # The three small-output products (reductions over L with a 6..56-row result) stay on cuBLAS: a 128-row tensor-core
         # tile is mostly padding there and the 3xTF32 operand split makes them shared-memory bound (scripts/bench_tcproj.py).
         x_dt = x_dbl[:, :, :R]

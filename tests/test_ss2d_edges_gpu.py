@@ -195,3 +195,70 @@ def test_cross_scan_merge_planes_beyond_shared_memory():
     torch.testing.assert_close(y, cross_merge_torch(xs.detach(), 230, 231))
     y.sum().backward()
     torch.testing.assert_close(x.grad, torch.full_like(x, 4.0))
+
+
+@pytest.mark.parametrize("batch,D,L,R", [(10, 192, 3136, 6), (4, 384, 784, 12), (6, 64, 200, 5), (5, 128, 96, 9)])
+def test_fused_dt_proj_in_the_scan_kernels(batch, D, L, R):
+    """dt_proj inside the scan (mamba_sys.py:409 fused into the kernels): the C ABI called with dt_w / dt_x and
+    no delta tensor gives the same out, saved states and gradients as with delta = dt_w . dt_x materialised by a GEMM."""
+    from selscan_b200 import ops
+
+    torch.manual_seed(R * 100 + L)
+    K, N = 4, 16
+    KD, C = K * D, R + 2 * N
+    dev = "cuda"
+    assert ops.dt_fusable(batch, KD, L, N, K, R)
+    x_dbl = torch.randn(batch, K, C, L, device=dev)
+    dt_w = torch.randn(K, D, R, device=dev) * R ** -0.5
+    u, dout = torch.randn(batch, KD, L, device=dev), torch.randn(batch, KD, L, device=dev)
+    A = -torch.rand(KD, N, device=dev) * 4 - 0.1
+    Dp, bias = torch.randn(KD, device=dev), torch.randn(KD, device=dev) - 2
+    Bv, Cv, dt_x = x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:], x_dbl[:, :, :R]
+    delta = torch.matmul(dt_w.unsqueeze(0), dt_x).view(batch, KD, L)
+    res = []
+    for fused in (False, True):
+        out = torch.empty(batch, KD, L, device=dev)
+        ck = torch.empty(max(ops.ckpt_elems(batch, KD, L, N), 4), device=dev)
+        du, dd = torch.empty_like(out), torch.empty_like(out)
+        nbc = batch * K * N * L
+        flat = torch.zeros(2 * nbc + KD * N + 2 * KD, device=dev)
+        dB, dC = flat[:nbc].view(batch, K, N, L), flat[nbc:2 * nbc].view(batch, K, N, L)
+        dA = flat[2 * nbc:2 * nbc + KD * N].view(KD, N)
+        dD, db = flat[2 * nbc + KD * N:2 * nbc + KD * N + KD], flat[2 * nbc + KD * N + KD:]
+        kw = dict(dt_w=dt_w.view(KD, R), dt_x=dt_x) if fused else {}
+        ops.launch_fwd(u, None if fused else delta, A, Bv, Cv, Dp, None, bias, True, out, None, None, ck, None, **kw)
+        ops.launch_bwd(u, None if fused else delta, A, Bv, Cv, Dp, None, bias, dout, None, ck, True, du, dd, dA, dB, dC, dD, None, db, **kw)
+        torch.cuda.synchronize()
+        res.append(dict(out=out, ck=ck, du=du, ddelta=dd, flat=flat))
+    for k in res[0]:
+        a, b = res[1][k], res[0][k]
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a, b, rtol=1e-4 if k in ("out", "ck") else 1e-3, atol=(1e-5 if k in ("out", "ck") else 1e-4) * scale,
+                                   msg=lambda m: f"{k}: {m}")
+    assert not ops.dt_fusable(batch, KD, L, N, K, 13) and not ops.dt_fusable(batch, KD, L + 1, N, K, R)
+
+
+@pytest.mark.parametrize("B,d_model,H,W", [(10, 96, 56, 56), (4, 192, 28, 28)])
+def test_ss2d_block_with_and_without_fused_dt_proj(B, d_model, H, W, monkeypatch):
+    """The SS2D block (SS2DFusedFn) allocates no (B, 4D, L) step tensor at stages 1 and 2 and computes the same thing."""
+    from selscan_b200 import ss2d
+    from selscan_b200.vssm import SS2D
+
+    _fp32()
+    torch.manual_seed(d_model)
+    blk = SS2D(d_model).cuda()
+    x = torch.randn(B, H, W, d_model, device="cuda")
+    g = torch.randn(B, H, W, d_model, device="cuda")
+    res = []
+    monkeypatch.setattr(ss2d, "FUSE_DT_MAX_RANK", 12)
+    for fuse in (True, False):
+        monkeypatch.setattr(ss2d, "FUSE_DT", fuse)
+        blk.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_()
+        out = blk(xi)
+        out.backward(g)
+        res.append((out.detach(), xi.grad, {k: p.grad.clone() for k, p in blk.named_parameters()}))
+    _close(res[0][0], res[1][0], 1e-4, 1e-5, "out")
+    _close(res[0][1], res[1][1], 1e-3, 1e-4, "dx")
+    for k in res[1][2]:
+        _close(res[0][2][k], res[1][2][k], 2e-3, 2e-4, k)

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "selscan_kernels.h"
+#include "selscan_tma_host.h"
 
 namespace selscan {
 
@@ -146,7 +147,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
 
 int ln_grid(int64_t rows, int rows_per_cta) {
   const int64_t want = (rows + rows_per_cta - 1) / rows_per_cta;
-  const int64_t cap = 148 * 8;
+  const int64_t cap = (int64_t)sm_count() * 8;   // same helper as every other grid heuristic: the partial-buffer query and the launcher agree
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

@@ -15,6 +15,8 @@
 //               accumulators, commits to the stage's empty barrier and, after a tile's last k-block, to acc_full
 //   warps 6-9   epilogue of tile j while tile j+1 is being multiplied: tcgen05.ld 32 lanes x 32 columns -> swizzled staging
 //               tile -> TMA store, or TMA reduce-add for C += and for split-K (weight gradients: K = batch * L)
+#include <atomic>
+
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -319,8 +321,9 @@ cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B,
   // split K when the tiles alone cannot fill the GPU and the reduction is long (weight gradients: K = batch * L)
   int splits = 1;
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles * batch;
-  if (tiles < 148 && p.kb_total >= 16) {
-    splits = (int)((2 * 148 + tiles - 1) / tiles);
+  const int n_sm = sm_count();
+  if (tiles < n_sm && p.kb_total >= 16) {
+    splits = (int)((2 * n_sm + tiles - 1) / tiles);
     if (splits > p.kb_total / 4) splits = p.kb_total / 4;
     if (splits < 1) splits = 1;
   }
@@ -351,10 +354,18 @@ cudaError_t launch_tcgemm(const float* A, int64_t lda, int a_mn, const float* B,
   p.stages = (int)((kTcSmemMax - kTcHeader) / p.stage_bytes);
   if (p.stages > kTcMaxStages) p.stages = kTcMaxStages;
   const int smem = (int)(kTcHeader + (uint32_t)p.stages * p.stage_bytes + 1024u);
-  cudaError_t e = cudaFuncSetAttribute(tcgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
+  {   // opt in to the largest dynamic shared-memory size seen so far, once per size increase and device instead of per launch
+    static std::atomic<int> configured[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (configured[dev].load(std::memory_order_acquire) < smem) {
+      const cudaError_t e = cudaFuncSetAttribute(tcgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      configured[dev].store(smem, std::memory_order_release);
+    }
+  }
   const int64_t n_work = tiles * p.splits;
-  const unsigned grid = (unsigned)(n_work < 148 ? n_work : 148);
+  const unsigned grid = (unsigned)(n_work < n_sm ? n_work : n_sm);
   tcgemm_3xtf32_kernel<<<grid, kTcThreads, smem, stream>>>(ma, mb, mc, p);
   return cudaGetLastError();
 }

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SELSCAN_B200_ABI_VERSION 6
+#define SELSCAN_B200_ABI_VERSION 7
 /* distance (in sequence positions) between two saved scan states; also the backward's chunk length */
 #define SELSCAN_B200_CKPT_INTERVAL 8
 /* states are padded to this count inside the kernels and in the checkpoint buffer */
@@ -76,6 +76,13 @@ typedef struct selscan_fwd_args {
   int64_t dt_w_d_stride;
   int64_t dt_x_batch_stride, dt_x_group_stride, dt_x_r_stride;
   int32_t dt_rank;
+  /* Mirrored direction pairs (the reversed half of SS2D's CrossScan / CrossMerge inside the scan kernels; code/networks/mamba_sys.py:
+   * 404, 429).  When mirror_pairs != 0 the groups come in pairs (2j, 2j+1): the odd group scans the SAME rows of `u` as the even
+   * one, back to front (scan position l <-> source index seqlen-1-l).  `u` and `out` then have dim/2 rows per batch (row of channel c
+   * of group g: (g / 2) * (dim / ngroups) + c), `out` must be ZERO-INITIALISED and receives the SUM of both groups of a pair, each in
+   * source order (out_pair[l] = y_even[l] + y_odd[seqlen-1-l]); delta / dt_x, B and C stay per group, in SOURCE order (the kernels
+   * read them back to front for odd groups).  Needs ngroups even, z == NULL, the tiled kernels: ask selscan_b200_mirror_ok(). */
+  int32_t mirror_pairs;
 } selscan_fwd_args;
 
 /* replaces selective_scan_cuda.bwd(u, delta, A, B, C, D_, z_, delta_bias_, dout, x_, out_, dz_,
@@ -122,6 +129,13 @@ typedef struct selscan_bwd_args {
   int64_t dt_w_d_stride;
   int64_t dt_x_batch_stride, dt_x_group_stride, dt_x_r_stride;
   int32_t dt_rank;
+  /* Mirrored direction pairs (the reversed half of SS2D's CrossScan / CrossMerge inside the scan kernels; code/networks/mamba_sys.py:
+   * 404, 429).  When mirror_pairs != 0 the groups come in pairs (2j, 2j+1): the odd group scans the SAME rows of `u` as the even
+   * one, back to front (scan position l <-> source index seqlen-1-l).  `u`, `dout` and `du` then have dim/2 rows per batch (row of channel c
+   * of group g: (g / 2) * (dim / ngroups) + c), `du` must be ZERO-INITIALISED and receives the SUM of both groups' gradients
+   * in source order; ddelta, dB, dC are per group, in source order; delta / dt_x, B and C stay per group, in SOURCE order (the kernels
+   * read them back to front for odd groups).  Needs ngroups even, z == NULL, the tiled kernels: ask selscan_b200_mirror_ok(). */
+  int32_t mirror_pairs;
 } selscan_bwd_args;
 
 int selscan_b200_abi_version(void);
@@ -138,6 +152,10 @@ int64_t selscan_b200_ckpt_elems(int32_t batch, int32_t dim, int32_t seqlen, int3
 /* 1 when a call of these sizes can take dt_w / dt_x (fused dt_proj): dt_rank <= 12, dstate <= 16, channels per group a multiple of
  * 64, seqlen > 8 and a multiple of 4, enough work to run unsegmented, and a device that runs the tiled kernels; else 0 */
 int selscan_b200_dt_fusable(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups, int32_t dt_rank);
+
+/* 1 when a call of these sizes can use mirror_pairs: ngroups even, dstate <= 16, channels per group a multiple of 64, seqlen > 8 and
+ * a multiple of 4, enough work to run unsegmented, and a device that runs the tiled kernels; else 0 */
+int selscan_b200_mirror_ok(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups);
 
 /* floats of forward `workspace` that make the segmented small-batch path available; 0 when the call fills the chip anyway */
 int64_t selscan_b200_fwd_workspace_elems(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups);

@@ -31,6 +31,12 @@ int check_common(const Args& a, const char* who) {
   if (a.dstate > 256) return fail("%s: selective_scan only supports state dimension <= 256 (got %d)", who, a.dstate);
   if (a.ngroups < 1 || a.dim % a.ngroups != 0) return fail("%s: dim (%d) must be divisible by ngroups (%d)", who, a.dim, a.ngroups);
   if (!a.u || (!a.delta && !a.dt_w) || !a.A || !a.B || !a.C) return fail("%s: u, delta (or dt_w / dt_x), A, B, C must not be NULL", who);
+  if (a.mirror_pairs) {   // the odd group of every pair walks the even group's rows back to front (tiled kernels only)
+    if (a.ngroups % 2 != 0) return fail("%s: mirror_pairs needs an even number of groups (got %d)", who, a.ngroups);
+    if (a.z) return fail("%s: mirror_pairs is not available with z", who);
+    if (!selscan_b200_mirror_ok(a.batch, a.dim, a.seqlen, a.dstate, a.ngroups))
+      return fail("%s: mirror_pairs needs sizes accepted by selscan_b200_mirror_ok()", who);
+  }
   if (a.dt_w) {   // fused dt_proj: the raw step is formed inside the tiled kernels
     if (!a.dt_x) return fail("%s: dt_x is required when dt_w is given", who);
     if (a.dt_rank < 1 || a.dt_rank > selscan::kMaxFusedDtRank) return fail("%s: fused dt_proj supports 1 <= dt_rank <= %d (got %d)", who, selscan::kMaxFusedDtRank, a.dt_rank);
@@ -74,6 +80,14 @@ __attribute__((visibility("default"))) int selscan_b200_dt_fusable(int32_t batch
   if (dt_rank < 1 || dt_rank > selscan::kMaxFusedDtRank || dstate > SELSCAN_B200_STATE_PAD) return 0;
   if ((dim / ngroups) % 64 != 0 || seqlen <= SELSCAN_B200_CKPT_INTERVAL || (seqlen & 3)) return 0;
   if (selscan_b200_fwd_workspace_elems(batch, dim, seqlen, dstate, ngroups) > 0) return 0;   // small batches run segmented: not fused
+  return selscan::bwd_ws_usable() && !selscan::force_generic() ? 1 : 0;
+}
+
+__attribute__((visibility("default"))) int selscan_b200_mirror_ok(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t ngroups) {
+  if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0 || ngroups <= 0 || (ngroups & 1) || dim % ngroups) return 0;
+  if (dstate > SELSCAN_B200_STATE_PAD || (dim / ngroups) % 64 != 0 || seqlen <= SELSCAN_B200_CKPT_INTERVAL) return 0;
+  if (seqlen & 3) return 0;   // the mirrored walk keeps its 128-bit accesses only when the partial tile is a whole number of quads
+  if (selscan_b200_fwd_workspace_elems(batch, dim, seqlen, dstate, ngroups) > 0) return 0;   // small batches run segmented
   return selscan::bwd_ws_usable() && !selscan::force_generic() ? 1 : 0;
 }
 

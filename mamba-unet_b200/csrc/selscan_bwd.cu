@@ -272,7 +272,7 @@ cudaError_t launch_bwd(const BwdLaunch& p, cudaStream_t stream) {
     if (e != cudaErrorNotSupported) return e;
     (void)cudaGetLastError();   // tensor map not encodable for this layout: the generic kernel takes any strides
   }
-  if (p.a.dt_w != nullptr) return cudaErrorNotSupported;   // fused dt_proj exists on the tiled kernels only (selscan_b200_dt_fusable)
+  if (p.a.dt_w != nullptr || p.a.mirror_pairs) return cudaErrorNotSupported;   // fused dt_proj / mirrored pairs: tiled kernels only
   static_assert(sizeof(BwdSmem) <= 110 * 1024, "two CTAs per SM");
   const int smem = (int)sizeof(BwdSmem);
   const unsigned grid = (unsigned)((int64_t)p.a.batch * p.a.ngroups * p.tiles_per_group);

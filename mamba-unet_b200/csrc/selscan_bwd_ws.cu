@@ -105,7 +105,10 @@ __device__ __forceinline__ u64 mul2v(u64 a, u64 b) {
 }
 __device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-template <bool kHasZ, int kDt>
+// kMir: mirrored direction pairs (selscan_b200.h: mirror_pairs) -- odd groups read u / dout of the even group of their pair back to
+// front and add their du into the same rows.  Only the helper warps know: they put the tiles into scan order before anyone else
+// reads them and reverse the outputs on the way out.
+template <bool kHasZ, int kDt, bool kMir>
 __global__ void __launch_bounds__(kThr, 2)
 selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                       const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
@@ -126,6 +129,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
   const int b = bid / a.ngroups;
   const int d0 = g * p.dim_per_group + tile_g * kR;
   const int n_tiles = (L + kC - 1) / kC;
+  const bool rev = kMir && (g & 1);                                           // CTA-uniform
+  const int ds0 = kMir ? (g >> 1) * p.dim_per_group + tile_g * kR : d0;       // first row of the u / dout / du tensors
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -176,10 +181,17 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     }
     const uint32_t my16 = (uint32_t)row * (kC * 4) + (uint32_t)((hf ^ ((row >> 2) & 1)) << 4);   // my 4 elements in every [row][8] tile
     const uint32_t out16 = (uint32_t)hf * (kR * 16) + (uint32_t)row * 16;    // ... and in the [half][row][4] output tiles
+    // Mirrored groups: the TMA box of a chunk holds the chunk's SOURCE positions, i.e. my 4 scan positions sit in the other half,
+    // reversed.  TMA coordinates are kept non-negative: the partial chunk (seqlen % 8 == 4, the first one processed) loads source
+    // positions 0..7, of which 3..0 are scan half 0 -- the same half, reversed.
+    const bool part_first = rev && (L & 4);
+    auto src16_of = [&](int j) { return (rev && !(part_first && j == 0)) ? (my16 ^ 16u) : my16; };
+    auto srchalf_of = [&](int j) { return (rev && !(part_first && j == 0)) ? 1 - hf : hf; };
+    auto unrev = [&](float4 v) { return rev ? make_float4(v.w, v.z, v.y, v.x) : v; };
 
     // ---- B/C gather: elements htid and htid + 128 of a chunk's [8 positions][32 values] tile; the pointers walk backwards ----
     // (B and C have the same position stride on this path: bwd_ws_eligible)
-    const int64_t bc_step = (int64_t)kC * a.B_l_stride;
+    const int64_t bc_step = (rev ? -(int64_t)kC : (int64_t)kC) * a.B_l_stride;
     const bool along_l = a.B_l_stride == 1;   // (.., N, L) layout: 8 consecutive threads read 8 consecutive positions of a state row;
                                               // l-major x_dbl layout: a warp reads the 16 B and 16 C values of one position
     const int bc_e1 = htid + kGroupThr;
@@ -189,7 +201,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       const int n = val & 15;
       const float* base = (val >= 16) ? (a.C + (int64_t)b * a.C_batch_stride + (int64_t)g * a.C_group_stride + (int64_t)n * a.C_n_stride)
                                       : (a.B + (int64_t)b * a.B_batch_stride + (int64_t)g * a.B_group_stride + (int64_t)n * a.B_n_stride);
-      return base + (int64_t)((n_tiles - 1) * kC + pos) * a.B_l_stride;   // first chunk processed = last of the sequence
+      const int sp = (n_tiles - 1) * kC + pos;                           // scan position; first chunk processed = last of the sequence
+      return base + (int64_t)(rev ? L - 1 - sp : sp) * a.B_l_stride;
     };
     const float* bcp0 = bc_src(bc_pos0, bc_val0);
     const float* bcp1 = bc_src(bc_pos1, bc_val1);
@@ -200,7 +213,9 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     const int c_n = (c_c & 3) * 4 + 2 * (c_q >> 1) + (c_q & 1);   // the state whose sum this lane ends up with
     const bool c_ok = c_n < N;
     // address of my (state, position hw of half 0) in the chunk being processed; walks backwards by one chunk per iteration
-    float* dbc = ((c_c >= 4) ? a.dC : a.dB) + (((int64_t)b * a.ngroups + g) * N + (c_ok ? c_n : 0)) * (int64_t)L + (n_tiles - 1) * kC + hw;
+    const int dbc_sgn = rev ? -1 : 1;        // mirrored groups: dB / dC in source order, i.e. at seqlen-1-position
+    float* dbc = ((c_c >= 4) ? a.dC : a.dB) + (((int64_t)b * a.ngroups + g) * N + (c_ok ? c_n : 0)) * (int64_t)L +
+                 (rev ? L - 1 - ((n_tiles - 1) * kC + hw) : (n_tiles - 1) * kC + hw);
 
     auto issue_tma = [&](int j) {            // chunk j (processing order) -> stage j % kStg
       const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC;
@@ -213,10 +228,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         tma_load_3d(smem_u32(sm.Z[s]), &map_z, l0, d0, b, full);
         tma_load_3d(smem_u32(sm.O[s]), &map_o, l0, d0, b, full);
       }
-      tma_load_3d(smem_u32(sm.U[s]), &map_u, l0, d0, b, full);
-      if (kDt > 0) tma_load_4d(smem_u32(sm.XDT[s]), &map_dt, l0, 0, g, b, full);   // ranks >= dt_rank / positions >= seqlen: zero fill
-      else tma_load_3d(smem_u32(sm.DT[s]), &map_dt, l0, d0, b, full);
-      tma_load_3d(smem_u32(sm.DY[s]), &map_dy, l0, d0, b, full);
+      const int lc = rev ? max(L - l0 - kC, 0) : l0;    // mirrored groups: the chunk's source positions
+      tma_load_3d(smem_u32(sm.U[s]), &map_u, lc, ds0, b, full);
+      if (kDt > 0) tma_load_4d(smem_u32(sm.XDT[s]), &map_dt, lc, 0, g, b, full);   // ranks >= dt_rank / positions outside: zero fill
+      else tma_load_3d(smem_u32(sm.DT[s]), &map_dt, lc, d0, b, full);
+      tma_load_3d(smem_u32(sm.DY[s]), &map_dy, lc, ds0, b, full);
       // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
       tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, b * a.dim + d0, full);
     };
@@ -224,18 +240,33 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     auto prep = [&](int j, float cb0, float cb1, float4& sg_out) {
       const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC + hf * kHP;
       mbar_wait(smem_u32(&sm.tma_full[s]), (uint32_t)((j / kStg) & 1));
-      const float4 u4 = lds_f4(smem_u32(sm.U[s]) + my16);
+      const uint32_t src16 = src16_of(j);
+      const float4 u4 = unrev(lds_f4(smem_u32(sm.U[s]) + src16));
       float4 t4;
       if (kDt > 0) {   // raw step of my 4 positions: dt_w[d, :] . dt_x[:, l]  (all rows of a warp read the same 16 bytes: broadcast)
         t4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kDt; ++r) {
-          const float4 x4 = lds_f4(smem_u32(sm.XDT[s]) + (uint32_t)(r * (kC * 4) + hf * 16));
+          const float4 x4 = unrev(lds_f4(smem_u32(sm.XDT[s]) + (uint32_t)(r * (kC * 4) + srchalf_of(j) * 16)));
           t4.x = fmaf(Wd[r], x4.x, t4.x); t4.y = fmaf(Wd[r], x4.y, t4.y);
           t4.z = fmaf(Wd[r], x4.z, t4.z); t4.w = fmaf(Wd[r], x4.w, t4.w);
         }
       } else {
-        t4 = lds_f4(smem_u32(sm.DT[s]) + my16);
+        t4 = unrev(lds_f4(smem_u32(sm.DT[s]) + src16));
+      }
+      if (kMir && rev) {   // put u and dout of the stage into scan order, in place, before anyone else reads them: every thread reads
+                           // the half its partner writes, hence the barrier between the reads and the writes
+        float4 y4 = unrev(lds_f4(smem_u32(sm.DY[s]) + src16));
+        float4 uz = u4;
+        const int lp = (n_tiles - 1 - j) * kC + hf * kHP;   // past the end the box holds other positions' data, not zero fill: clear
+        if (lp + 0 >= L) { uz.x = 0.f; y4.x = 0.f; }
+        if (lp + 1 >= L) { uz.y = 0.f; y4.y = 0.f; }
+        if (lp + 2 >= L) { uz.z = 0.f; y4.z = 0.f; }
+        if (lp + 3 >= L) { uz.w = 0.f; y4.w = 0.f; }
+        named_bar_sync(1, kGroupThr);
+        sts_f4(smem_u32(sm.U[s]) + my16, uz);
+        sts_f4(smem_u32(sm.DY[s]) + my16, y4);
+        fence_proxy_async_smem();    // ordered before the TMA load that refills this stage
       }
       const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
       float v[4], vu[4], sg[4];
@@ -337,7 +368,7 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           k1 += __shfl_xor_sync(0xffffffffu, q1 ? o1 : o3, 16);
           float kk = q0 ? k1 : k0;
           kk += __shfl_xor_sync(0xffffffffu, q0 ? k0 : k1, 8);
-          if (c_ok && (i > 0 || c0 + h * kHP + hw < L)) atomicAdd(dbc + h * kHP, kk);
+          if (c_ok && (i > 0 || c0 + h * kHP + hw < L)) atomicAdd(dbc + dbc_sgn * (h * kHP), kk);
         }
         // ---------------- du / ddelta of my (row, half): sum the 4 lanes' partials, finalise ----------------
         if (hf == h) {
@@ -365,8 +396,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           // positions past the end contribute exact zeros (delta forced to 0, u / dout / B / C zero fill), so no masking is needed
           dbias_acc += (o_dd.x + o_dd.y) + (o_dd.z + o_dd.w);
           dD_acc = fmaf(y4.x, u4.x, fmaf(y4.y, u4.y, fmaf(y4.z, u4.z, fmaf(y4.w, u4.w, dD_acc))));   // :213
-          sts_f4(smem_u32(sm.DU[ob]) + out16, o_du);
-          sts_f4(smem_u32(sm.DDT[ob]) + out16, o_dd);
+          sts_f4(smem_u32(sm.DU[ob]) + out16, unrev(o_du));     // mirrored groups: back into source order
+          sts_f4(smem_u32(sm.DDT[ob]) + out16, unrev(o_dd));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sm.half_free[h]));
@@ -376,15 +407,19 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           if ((htid & 63) == 0) tma_store_wait_read<0>();   // my store of chunk i-1 has read its tiles: buffer ob^1 is free for chunk i+1
           named_bar_sync(2 + h, 64);
           if ((htid & 63) == 0) {
-            tma_store_3d(&map_du, smem_u32(sm.DU[ob]) + h * (kR * 16), c0 + kHP * h, d0, b);
-            tma_store_3d(&map_ddt, smem_u32(sm.DDT[ob]) + h * (kR * 16), c0 + kHP * h, d0, b);
+            const int lo = rev ? L - (c0 + kHP * h) - kHP : c0 + kHP * h;   // mirrored: a half past the end (lo < 0) has nothing to store
+            if (lo >= 0) {
+              if (kMir) tma_reduce_add_3d(&map_du, smem_u32(sm.DU[ob]) + h * (kR * 16), lo, ds0, b);   // both groups of a pair add
+              else tma_store_3d(&map_du, smem_u32(sm.DU[ob]) + h * (kR * 16), lo, d0, b);
+              tma_store_3d(&map_ddt, smem_u32(sm.DDT[ob]) + h * (kR * 16), lo, d0, b);
+            }
             tma_store_commit();
           }
         } else if (hh == 1 && lane == 0) {
           mbar_arrive(smem_u32(&sm.stage_free[s]));                             //  ... and the warps of half 1 after contracting half 0)
         }
       }
-      dbc -= kC;
+      dbc -= dbc_sgn * kC;
       sg_cur = sg_nxt;
       cb0 = nb0;
       cb1 = nb1;
@@ -562,15 +597,20 @@ inline bool make_ckpt_map(CUtensorMap* map, const float* base, int64_t rows, int
 // arithmetic assumes (otherwise setmaxnreg.inc could wait for registers that never come).
 bool bwd_ws_usable() {
   static const bool ok = [] {
-    cudaFuncAttributes fa[4];
-    if (cudaFuncGetAttributes(&fa[0], selscan_bwd_ws_kernel<false, 0>) != cudaSuccess ||
-        cudaFuncGetAttributes(&fa[1], selscan_bwd_ws_kernel<true, 0>) != cudaSuccess ||
-        cudaFuncGetAttributes(&fa[2], selscan_bwd_ws_kernel<false, 6>) != cudaSuccess ||
-        cudaFuncGetAttributes(&fa[3], selscan_bwd_ws_kernel<false, kMaxFusedDtRank>) != cudaSuccess) {
+    cudaFuncAttributes fa[7];
+    if (cudaFuncGetAttributes(&fa[0], selscan_bwd_ws_kernel<false, 0, false>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[1], selscan_bwd_ws_kernel<true, 0, false>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[2], selscan_bwd_ws_kernel<false, 6, false>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[3], selscan_bwd_ws_kernel<false, kMaxFusedDtRank, false>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[4], selscan_bwd_ws_kernel<false, 0, true>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[5], selscan_bwd_ws_kernel<false, 6, true>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa[6], selscan_bwd_ws_kernel<false, kMaxFusedDtRank, true>) != cudaSuccess) {
       (void)cudaGetLastError();
       return false;
     }
-    return fa[0].numRegs == kLaunchRegs && fa[1].numRegs == kLaunchRegs && fa[2].numRegs == kLaunchRegs && fa[3].numRegs == kLaunchRegs;
+    for (int i = 0; i < 7; ++i)
+      if (fa[i].numRegs != kLaunchRegs) return false;
+    return true;
   }();
   return ok;
 }
@@ -610,14 +650,14 @@ inline bool make_dtx_map_bwd(CUtensorMap* map, const selscan_bwd_args& a, int bo
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool kHasZ, int kDt>
+template <bool kHasZ, int kDt, bool kMir = false>
 cudaError_t launch_ws_variant(const CUtensorMap (&m)[9], const BwdLaunch& p, unsigned grid, cudaStream_t stream) {
   constexpr int smem = (int)sizeof(WsSmemT<kHasZ, kDt>) + 256;
   static_assert(kHasZ || sizeof(WsSmemT<kHasZ, kDt>) + 256 + 1024 <= 116736, "two CTAs per SM");
   static_assert(sizeof(WsSmemT<kHasZ, kDt>) + 256 <= 232448, "fits one CTA per SM");
   static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
-  if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<kHasZ, kDt>, smem)) return e;
-  selscan_bwd_ws_kernel<kHasZ, kDt><<<grid, kThr, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], p);
+  if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<kHasZ, kDt, kMir>, smem)) return e;
+  selscan_bwd_ws_kernel<kHasZ, kDt, kMir><<<grid, kThr, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], p);
   return cudaGetLastError();
 }
 
@@ -626,23 +666,29 @@ cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
   CUtensorMap m[9];   // u, delta (or dt_x), dout, saved states, du, ddelta, z, out, dz
   const int dt_box = a.dt_w == nullptr ? 0 : (a.dt_rank <= 6 ? 6 : kMaxFusedDtRank);
-  if (!make_row_map_sw(&m[0], a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+  const int src_rows = a.mirror_pairs ? a.dim / 2 : a.dim;   // rows per batch of u / dout / du
+  if (!make_row_map_sw(&m[0], a.u, a.seqlen, src_rows, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
       !(dt_box ? make_dtx_map_bwd(&m[1], a, dt_box)
                : make_row_map_sw(&m[1], a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B)) ||
-      !make_row_map_sw(&m[2], a.dout, a.seqlen, a.dim, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
+      !make_row_map_sw(&m[2], a.dout, a.seqlen, src_rows, a.batch, a.dout_d_stride, a.dout_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
       !make_ckpt_map(&m[3], a.ckpt, (int64_t)a.batch * a.dim, p.n_ckpt) ||
-      !make_row_map(&m[4], a.du, a.seqlen, a.dim, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
+      !make_row_map(&m[4], a.du, a.seqlen, src_rows, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
       !make_row_map(&m[5], a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR))
     return cudaErrorNotSupported;
   m[6] = m[7] = m[8] = m[0];
   const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kR));
   if (a.z != nullptr) {
-    if (dt_box) return cudaErrorNotSupported;   // (the C ABI rejects the combination earlier)
+    if (dt_box || a.mirror_pairs) return cudaErrorNotSupported;   // (the C ABI rejects the combinations earlier)
     if (!make_row_map_sw(&m[6], a.z, a.seqlen, a.dim, a.batch, a.z_d_stride, a.z_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
         !make_row_map_sw(&m[7], a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
         !make_row_map_sw(&m[8], a.dz, a.seqlen, a.dim, a.batch, a.dz_d_stride, a.dz_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B))
       return cudaErrorNotSupported;
     return launch_ws_variant<true, 0>(m, p, grid, stream);
+  }
+  if (a.mirror_pairs) {
+    if (dt_box == 6) return launch_ws_variant<false, 6, true>(m, p, grid, stream);
+    if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank, true>(m, p, grid, stream);
+    return launch_ws_variant<false, 0, true>(m, p, grid, stream);
   }
   if (dt_box == 6) return launch_ws_variant<false, 6>(m, p, grid, stream);
   if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank>(m, p, grid, stream);

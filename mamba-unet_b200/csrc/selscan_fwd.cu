@@ -120,7 +120,7 @@ cudaError_t launch_fwd(const FwdLaunch& p, cudaStream_t stream) {
     const cudaError_t e = launch_fwd_tma(p, stream);
     if (e != cudaErrorNotSupported) return e;   // a tensor map could not be encoded for this layout: generic kernel below
   }
-  if (p.a.dt_w != nullptr) return cudaErrorNotSupported;   // fused dt_proj exists on the tiled kernels only (selscan_b200_dt_fusable)
+  if (p.a.dt_w != nullptr || p.a.mirror_pairs) return cudaErrorNotSupported;   // fused dt_proj / mirrored pairs: tiled kernels only
   const unsigned grid = (unsigned)((rows + kFwdThreads - 1) / kFwdThreads);
   if (p.a.z != nullptr)
     selscan_fwd_rowserial_kernel<true><<<grid, kFwdThreads, 0, stream>>>(p);

@@ -74,6 +74,8 @@ struct Lay {
 
 struct Item {
   int b, g, d0, seg, t_begin, n_tiles;
+  int ds0;    // first row of this item in u / out (mirrored pairs: the even group's rows)
+  bool rev;   // mirrored pairs: odd group, walks the rows back to front
 };
 
 template <int kMode>
@@ -91,6 +93,8 @@ __device__ __forceinline__ Item decode_item(const FwdLaunch& p, int item) {
   it.g = bid % p.a.ngroups;
   it.b = bid / p.a.ngroups;
   it.d0 = it.g * p.dim_per_group + tile_g * kRows;
+  it.rev = p.a.mirror_pairs != 0 && (it.g & 1);
+  it.ds0 = p.a.mirror_pairs != 0 ? (it.g >> 1) * p.dim_per_group + tile_g * kRows : it.d0;
   const int n_tiles_all = (p.a.seqlen + kTL - 1) / kTL;
   it.t_begin = (kMode == 0) ? 0 : it.seg * p.seg_tiles;
   const int t_end = (kMode == 0) ? n_tiles_all : min(n_tiles_all, it.t_begin + p.seg_tiles);
@@ -99,7 +103,9 @@ __device__ __forceinline__ Item decode_item(const FwdLaunch& p, int item) {
 }
 
 // kMode 0: whole sequence per item.  1: segment aggregates only (no outputs).  2: segment with an initial state.
-template <int kMode, bool kHasZ, int kDt>
+// kMir: mirrored direction pairs (selscan_b200.h: mirror_pairs): odd groups read the even group's u rows back to front -- mirrored
+// TMA coordinates, mirrored tile columns in the consumers -- and both groups of a pair ADD their outputs into the same rows
+template <int kMode, bool kHasZ, int kDt, bool kMir>
 __global__ void __launch_bounds__(kThreads, Lay<kHasZ, kDt>::kCtas)
 selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                        const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
@@ -145,16 +151,20 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         const uint32_t k = it / kStages;
         if (k > 0) mbar_wait(empty_bar(s), (k - 1) & 1);
         const int l0 = (w.t_begin + t) * kTL;
+        const bool rev = kMir && w.rev;
+        // mirrored: the tile's source positions.  TMA coordinates are kept non-negative: the partial tile of a mirrored item loads the
+        // row's first 32 positions and the consumers shift their columns by the missing count (a multiple of 4: seqlen % 4 == 0)
+        const int lc = rev ? max(L - l0 - kTL, 0) : l0;
         const uint32_t full = full_bar(s);
         if (lane == 0) {
           if (kDt > 0) {
             mbar_expect_tx(full, (uint32_t)kTileBytes + LY::kDtBytes);
-            tma_load_3d(in_tile(s, 0), &map_u, l0, w.d0, w.b, full);
-            tma_load_4d(sm0 + LY::oDt + (uint32_t)s * LY::kDtBytes, &map_dt, l0, 0, w.g, w.b, full);   // ranks >= dt_rank: zero fill
+            tma_load_3d(in_tile(s, 0), &map_u, lc, kMir ? w.ds0 : w.d0, w.b, full);
+            tma_load_4d(sm0 + LY::oDt + (uint32_t)s * LY::kDtBytes, &map_dt, lc, 0, w.g, w.b, full);   // ranks >= dt_rank: zero fill
           } else {
             mbar_expect_tx(full, (uint32_t)((kHasZ && kMode != 1) ? 3 : 2) * kTileBytes);
-            tma_load_3d(in_tile(s, 0), &map_u, l0, w.d0, w.b, full);
-            tma_load_3d(in_tile(s, 1), &map_dt, l0, w.d0, w.b, full);
+            tma_load_3d(in_tile(s, 0), &map_u, lc, kMir ? w.ds0 : w.d0, w.b, full);
+            tma_load_3d(in_tile(s, 1), &map_dt, lc, w.d0, w.b, full);
           }
           if (kHasZ && kMode != 1) tma_load_3d(in_tile(s, 2), &map_z, l0, w.d0, w.b, full);
         }
@@ -166,7 +176,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
           for (int i = 0; i < 32; ++i) {
             const int n = i & 15;
             const float* src = (i < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
-            v[i] = (n < N && l < L) ? __ldg(src + l) : 0.f;
+            v[i] = (n < N && l < L) ? __ldg(src + (rev ? L - 1 - l : l)) : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
@@ -176,7 +186,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
           const float* src = (lane < 16) ? (Bg + (int64_t)n * a.B_n_stride) : (Cg + (int64_t)n * a.C_n_stride);
           const int64_t ls = (lane < 16) ? a.B_l_stride : a.C_l_stride;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(l0 + j) * ls) : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = (n < N && l0 + j < L) ? __ldg(src + (int64_t)(rev ? L - 1 - (l0 + j) : l0 + j) * ls) : 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(bc + (uint32_t)(j * kBCPitch + lane) * 4), "f"(v[j]) : "memory");
@@ -228,6 +238,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
 
   uint32_t it = 0;        // tiles consumed by this CTA: ring position
   uint32_t n_out = 0;     // output tiles written by this warp: double-buffer index
+  auto out_tile_of = [&](int wp, uint32_t n) { return sm0 + LY::oOut + (uint32_t)((wp * 2 + (n & 1)) * LY::kOut) * kOutBytes; };
   Params cur, nxt;
   Item w = decode_item<kMode>(p, blockIdx.x < n_items ? blockIdx.x : 0);
   if (blockIdx.x < n_items) load_params(w, cur);
@@ -265,31 +276,42 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       const uint32_t dt_row = in_tile(s, 1) + rr * (kTL * 4);
       const uint32_t z_row = in_tile(s, kHasZ ? 2 : 0) + rr * (kTL * 4) + h * 8;
       const uint32_t bc_base = sm0 + LY::oBC + (uint32_t)s * (kTL * kBCPitch * 4) + h * (kLaneStates * 4);
-      const uint32_t xdt_base = sm0 + LY::oDt + (uint32_t)s * LY::kDtBytes + h * 8;   // my two positions of a quad in every rank row
-      const uint32_t out_tile = sm0 + LY::oOut + (uint32_t)((warp * 2 + (n_out & 1)) * LY::kOut) * kOutBytes;
+      const uint32_t xdt_base = sm0 + LY::oDt + (uint32_t)s * LY::kDtBytes;
+      const bool rev = kMir && w.rev;          // mirrored item: scan position p of the tile sits in column 31 - p - miss
+      const int miss = rev ? max(kTL - (L - l0), 0) : 0;   // positions the (last, partial) tile lacks; its box starts at source 0
+      const int qmiss = miss >> 2;
+      if (kMir && miss > 0) {                  // columns of the out tile past the sequence must add zeros: clear the tile first
+#pragma unroll
+        for (int i = 0; i < kOutBytes / (32 * 16); ++i) sts_f4(out_tile_of(warp, n_out) + (uint32_t)(lane + 32 * i) * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+        __syncwarp();
+      }
+      const uint32_t out_tile = out_tile_of(warp, n_out);
       const uint32_t out_row = out_tile + ch * (kTL * 4) + h * 8;
+      const uint32_t out_row_rev = out_tile + ch * (kTL * 4) + (1 - h) * 8;
       // Software pipeline over the 8 quads of the tile: while quad q's recurrence runs, quad q+1's row data is loaded,
       // discretised and exchanged, and quad q-1's partial sums are reduce-scattered and stored.
       float uv_n[4], dl_n[4];              // quad q+1 (prefetched)
       float yp[4], up0 = 0.f, up1 = 0.f;   // quad q-1: partial sums and my two u values
       auto prefetch = [&](int q, float (&uv)[4], float (&dl)[4]) {
-        const float4 u4 = lds_f4(u_row + (((uint32_t)q << 4) ^ swz));
-        uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w;
+        const uint32_t qsrc = (uint32_t)(rev ? max(7 - q - qmiss, 0) : q) << 4;   // (clamped: a partial tile prefetches one quad past its end)
+        const float4 u4 = lds_f4(u_row + (qsrc ^ swz));
+        uv[0] = rev ? u4.w : u4.x; uv[1] = rev ? u4.z : u4.y; uv[2] = rev ? u4.y : u4.z; uv[3] = rev ? u4.x : u4.w;
         // my two positions of the quad: discretise delta once per element, then exchange with the partner lane
         float m0, m1;
         if (kDt > 0) {   // delta = dt_w[d, :] . dt_x[:, l] + bias: rank-R expansion in registers, no (batch, dim, seqlen) step tensor
           m0 = m1 = bias;
 #pragma unroll
           for (int r = 0; r < kDt; ++r) {
-            float x0, x1;
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(xdt_base + (uint32_t)(r * (kTL * 4) + q * 16)));
-            m0 = fmaf(cur.Wd[r], x0, m0);
-            m1 = fmaf(cur.Wd[r], x1, m1);
+            float x0, x1;   // my two positions of the quad (mirrored: columns 30 - p, 31 - p, swapped)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1)
+                         : "r"(xdt_base + (uint32_t)(r * (kTL * 4)) + (rev ? (uint32_t)max(120 - 16 * q - 8 * h - 4 * miss, 0) : (uint32_t)(16 * q + 8 * h))));
+            m0 = fmaf(cur.Wd[r], rev ? x1 : x0, m0);
+            m1 = fmaf(cur.Wd[r], rev ? x0 : x1, m1);
           }
         } else {
-          const float4 d4 = lds_f4(dt_row + (((uint32_t)q << 4) ^ swz));
-          m0 = (hi ? d4.z : d4.x) + bias;
-          m1 = (hi ? d4.w : d4.y) + bias;
+          const float4 d4 = lds_f4(dt_row + (qsrc ^ swz));
+          m0 = (rev ? (hi ? d4.y : d4.w) : (hi ? d4.z : d4.x)) + bias;
+          m1 = (rev ? (hi ? d4.x : d4.z) : (hi ? d4.w : d4.y)) + bias;
         }
         {   // branch-free on the (uniform) softplus flag: a branch here would split the tile into basic blocks and
             // serialise this latency chain (LDS -> EX2 -> RCP -> polynomial -> SHFL) against the recurrence
@@ -312,7 +334,11 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         k1 += __shfl_xor_sync(0xffffffffu, hi ? y[1] : y[3], 16);
         const float o0 = fmaf(Dv, um0, k0), o1 = fmaf(Dv, um1, k1);
         const uint32_t off = ((uint32_t)q << 4) ^ swz;
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(out_row + off), "f"(o0), "f"(o1) : "memory");
+        if (rev) {   // back into source order: positions p, p + 1 -> columns 31 - p, 30 - p
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(out_row_rev + (((uint32_t)(7 - q - qmiss) << 4) ^ swz)), "f"(o1), "f"(o0) : "memory");
+        } else {
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(out_row + off), "f"(o0), "f"(o1) : "memory");
+        }
         if (kHasZ) {   // out_z = out * silu(z)   (fwd_kernel.cuh:293)
           float z0, z1;
           asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(z0), "=f"(z1) : "r"(z_row + off));
@@ -392,7 +418,8 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(empty_bar(s));   // the warp is done reading stage s
-        tma_store_3d(&map_out, out_tile, l0, w.d0 + warp * kWarpRows, w.b);
+        if (kMir) tma_reduce_add_3d(&map_out, out_tile, rev ? max(L - l0 - kTL, 0) : l0, w.ds0 + warp * kWarpRows, w.b);   // both groups of a pair add
+        else tma_store_3d(&map_out, out_tile, l0, w.d0 + warp * kWarpRows, w.b);
         if (kHasZ) tma_store_3d(&map_outz, out_tile + kOutBytes, l0, w.d0 + warp * kWarpRows, w.b);
         tma_store_commit();
         tma_store_wait_read<1>();    // the other OUT buffer (previous tile) has been read: free for the next tile
@@ -442,15 +469,15 @@ __global__ void selscan_fwd_combine_kernel(const FwdLaunch p) {
   }
 }
 
-template <int kMode, bool kHasZ, int kDt = 0>
+template <int kMode, bool kHasZ, int kDt = 0, bool kMir = false>
 cudaError_t launch_one(const CUtensorMap& mu, const CUtensorMap& mdt, const CUtensorMap& mz, const CUtensorMap& mout,
                        const CUtensorMap& moutz, const FwdLaunch& p, int n_items, cudaStream_t stream) {
   constexpr int smem = (int)Lay<kHasZ, kDt>::kBytes + 1024;
   static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
-  if (const cudaError_t e = set_smem_once(configured, selscan_fwd_tma_kernel<kMode, kHasZ, kDt>, smem)) return e;
+  if (const cudaError_t e = set_smem_once(configured, selscan_fwd_tma_kernel<kMode, kHasZ, kDt, kMir>, smem)) return e;
   const int slots = sm_count() * Lay<kHasZ, kDt>::kCtas;
   const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);
-  selscan_fwd_tma_kernel<kMode, kHasZ, kDt><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, p, n_items);
+  selscan_fwd_tma_kernel<kMode, kHasZ, kDt, kMir><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, p, n_items);
   return cudaGetLastError();
 }
 
@@ -510,10 +537,11 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   const selscan_fwd_args& a = p.a;
   CUtensorMap mu, mdt, mout, mz, moutz;
   const int dt_box = a.dt_w == nullptr ? 0 : (a.dt_rank <= 6 ? 6 : kMaxFusedDtRank);
-  if (!make_row_map(&mu, a.u, a.seqlen, a.dim, a.batch, a.u_d_stride, a.u_batch_stride, kTL, kRows) ||
+  const int src_rows = a.mirror_pairs ? a.dim / 2 : a.dim;   // rows per batch of u / out
+  if (!make_row_map(&mu, a.u, a.seqlen, src_rows, a.batch, a.u_d_stride, a.u_batch_stride, kTL, kRows) ||
       !(dt_box ? make_dtx_map(&mdt, a, kTL, dt_box)
                : make_row_map(&mdt, a.delta, a.seqlen, a.dim, a.batch, a.delta_d_stride, a.delta_batch_stride, kTL, kRows)) ||
-      !make_row_map(&mout, a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kTL, kWarpRows))
+      !make_row_map(&mout, a.out, a.seqlen, src_rows, a.batch, a.out_d_stride, a.out_batch_stride, kTL, kWarpRows))
     return cudaErrorNotSupported;
   const bool has_z = a.z != nullptr;
   if (has_z) {
@@ -528,6 +556,13 @@ cudaError_t launch_fwd_tma(const FwdLaunch& p, cudaStream_t stream) {
   FwdLaunch q = p;
   q.n_segs = 1;
   fwd_plan_segments(a.batch, a.dim, a.seqlen, a.ngroups, &q.n_segs, &q.seg_tiles);
+  if (a.mirror_pairs) {   // mirrored pairs: whole sequences only (selscan_b200_mirror_ok), no z
+    q.n_segs = 1;
+    if (has_z) return cudaErrorNotSupported;
+    if (dt_box == 6) return launch_one<0, false, 6, true>(mu, mdt, mz, mout, moutz, q, n_base, stream);
+    if (dt_box) return launch_one<0, false, kMaxFusedDtRank, true>(mu, mdt, mz, mout, moutz, q, n_base, stream);
+    return launch_one<0, false, 0, true>(mu, mdt, mz, mout, moutz, q, n_base, stream);
+  }
   if (dt_box) {   // fused dt_proj: whole sequences only (selscan_b200_dt_fusable excludes the segmented sizes), no z
     q.n_segs = 1;
     return dt_box == 6 ? launch_one<0, false, 6>(mu, mdt, mz, mout, moutz, q, n_base, stream)

@@ -160,6 +160,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// same, accumulating (fp32 add in L2) instead of overwriting
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

@@ -10,7 +10,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # SELSCAN_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
 LIB_PATH = os.environ.get("SELSCAN_B200_LIB") or os.path.join(_PKG, "lib", "libselscan_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 CKPT_INTERVAL = 8
 STATE_PAD = 16
 
@@ -19,7 +19,7 @@ _i32, _i64, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
 
 # fused dt_proj inputs, the tail of both argument structs
 _DT_FIELDS = [("dt_w", _ptr), ("dt_x", _ptr), ("dt_w_d_stride", _i64), ("dt_x_batch_stride", _i64), ("dt_x_group_stride", _i64),
-              ("dt_x_r_stride", _i64), ("dt_rank", _i32)]
+              ("dt_x_r_stride", _i64), ("dt_rank", _i32), ("mirror_pairs", _i32)]
 
 
 class FwdArgs(ctypes.Structure):
@@ -85,6 +85,8 @@ def load():
         lib.selscan_b200_fwd_workspace_elems.argtypes = [_i32] * 5
         lib.selscan_b200_dt_fusable.restype = ctypes.c_int
         lib.selscan_b200_dt_fusable.argtypes = [_i32] * 6
+        lib.selscan_b200_mirror_ok.restype = ctypes.c_int
+        lib.selscan_b200_mirror_ok.argtypes = [_i32] * 5
         lib.selscan_b200_fwd.restype = ctypes.c_int
         lib.selscan_b200_fwd.argtypes = [ctypes.POINTER(FwdArgs), _ptr]
         lib.selscan_b200_bwd.restype = ctypes.c_int

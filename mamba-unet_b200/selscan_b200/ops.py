@@ -104,8 +104,13 @@ def _require_f32_cuda(**tensors):
             raise RuntimeError(f"selscan_b200: {name} is on {t.device}, expected {dev}")
 
 
-def _dt_fields(dt_w, dt_x):
-    """Tail of both argument structs: the fused dt_proj inputs (dt_w (dim, R) rows, dt_x (batch, G, R, L) unit stride along L)."""
+def _dt_fields(dt_w, dt_x, mirror_pairs=False):
+    """Tail of both argument structs: the fused dt_proj inputs (dt_w (dim, R) rows, dt_x (batch, G, R, L) unit stride along L) and
+    the mirrored-pairs flag."""
+    return dict(_dt_only(dt_w, dt_x), mirror_pairs=int(bool(mirror_pairs)))
+
+
+def _dt_only(dt_w, dt_x):
     if dt_w is None:
         return dict(dt_w=None, dt_x=None, dt_w_d_stride=0, dt_x_batch_stride=0, dt_x_group_stride=0, dt_x_r_stride=0, dt_rank=0)
     if dt_w.dim() != 2 or dt_w.stride(1) != 1 or dt_x.dim() != 4 or dt_x.stride(3) != 1 or dt_x.shape[2] != dt_w.shape[1]:
@@ -119,15 +124,24 @@ def dt_fusable(batch, dim, seqlen, dstate, ngroups, dt_rank):
     return bool(_lib.load().selscan_b200_dt_fusable(batch, dim, seqlen, dstate, ngroups, dt_rank))
 
 
+def mirror_ok(batch, dim, seqlen, dstate, ngroups):
+    """True when calls of these sizes may use mirror_pairs (selscan_b200_mirror_ok)."""
+    return bool(_lib.load().selscan_b200_mirror_ok(batch, dim, seqlen, dstate, ngroups))
+
+
 def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=None, last_state=None, ckpt=None,
-               workspace=None, dt_w=None, dt_x=None):
+               workspace=None, dt_w=None, dt_x=None, mirror_pairs=False):
     """One selscan_b200_fwd call on the current stream.  All tensors fp32 CUDA; B, C 4-D (batch, G, N, L);
     u/delta/z/out unit-stride along seqlen; outputs preallocated by the caller (the library never allocates).
-    dt_w / dt_x: fused dt_proj (delta may then be None; see dt_fusable)."""
+    dt_w / dt_x: fused dt_proj (delta may then be None; see dt_fusable).
+    mirror_pairs: groups (2j, 2j+1) share the rows of `u` / `out` (which then have dim / 2 rows); the odd group walks them back to
+    front and both ADD their outputs into `out`, which the caller zero-initialises (see include/selscan_b200.h, mirror_ok)."""
     lib = _lib.load()
     _require_f32_cuda(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=delta_bias, out=out, out_z=out_z,
                       last_state=last_state, ckpt=ckpt, workspace=workspace, dt_w=dt_w, dt_x=dt_x)
     batch, dim, seqlen = u.shape
+    if mirror_pairs:
+        dim *= 2                                   # `dim` counts the channels of all groups; u / out carry one row per pair
     if delta is None:
         delta = u if dt_w is not None else None   # strides only; the pointer is passed as NULL below
     a = _lib.FwdArgs(
@@ -142,19 +156,22 @@ def launch_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, out, out_z=N
         z_batch_stride=_strides2(z)[0], z_d_stride=_strides2(z)[1],
         out=_p(out), out_batch_stride=out.stride(0), out_d_stride=out.stride(1),
         out_z=_p(out_z), out_z_batch_stride=_strides2(out_z)[0], out_z_d_stride=_strides2(out_z)[1],
-        last_state=_p(last_state), ckpt=_p(ckpt), workspace=_p(workspace), **_dt_fields(dt_w, dt_x))
+        last_state=_p(last_state), ckpt=_p(ckpt), workspace=_p(workspace), **_dt_fields(dt_w, dt_x, mirror_pairs))
     with torch.cuda.device(u.device):
         _lib.check(lib.selscan_b200_fwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_fwd")
 
 
 def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softplus,
-               du, ddelta, dA, dB, dC, dD=None, dz=None, ddelta_bias=None, dt_w=None, dt_x=None):
+               du, ddelta, dA, dB, dC, dD=None, dz=None, ddelta_bias=None, dt_w=None, dt_x=None, mirror_pairs=False):
     """One selscan_b200_bwd call on the current stream.  dA, dB, dC, dD, ddelta_bias must be zero-initialised.
-    dt_w / dt_x: fused dt_proj, as in launch_fwd; ddelta is then the gradient w.r.t. the raw step dt_w . dt_x."""
+    dt_w / dt_x: fused dt_proj, as in launch_fwd; ddelta is then the gradient w.r.t. the raw step dt_w . dt_x.
+    mirror_pairs: as in launch_fwd; u / dout / du have one row per pair and du must be zero-initialised too."""
     lib = _lib.load()
     _require_f32_cuda(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=delta_bias, dout=dout, out=out, ckpt=ckpt, du=du,
                       ddelta=ddelta, dA=dA, dB=dB, dC=dC, dD=dD, dz=dz, ddelta_bias=ddelta_bias, dt_w=dt_w, dt_x=dt_x)
     batch, dim, seqlen = u.shape
+    if mirror_pairs:
+        dim *= 2
     if delta is None:
         delta = u if dt_w is not None else None
     a = _lib.BwdArgs(
@@ -174,7 +191,7 @@ def launch_bwd(u, delta, A, B, C, D, z, delta_bias, dout, out, ckpt, delta_softp
         ddelta_batch_stride=ddelta.stride(0), ddelta_d_stride=ddelta.stride(1),
         dz_batch_stride=_strides2(dz)[0], dz_d_stride=_strides2(dz)[1],
         du=_p(du), ddelta=_p(ddelta), dz=_p(dz), dA=_p(dA), dB=_p(dB), dC=_p(dC), dD=_p(dD),
-        ddelta_bias=_p(ddelta_bias), **_dt_fields(dt_w, dt_x))
+        ddelta_bias=_p(ddelta_bias), **_dt_fields(dt_w, dt_x, mirror_pairs))
     with torch.cuda.device(u.device):
         _lib.check(lib.selscan_b200_bwd(a, torch.cuda.current_stream(u.device).cuda_stream), "selscan_b200_bwd")
 

@@ -175,6 +175,9 @@ int selscan_b200_cross_merge(const float* ys, float* y, int32_t batch, int32_t d
  * "channels-last" tensors are (batch, H, W, channels) with a free POSITION stride (floats between two pixels), so the x and z
  * halves of in_proj's output (mamba_sys.py:530-531, `xz.chunk(2, dim=-1)`) are read, and their gradients written, in place.
  *
+ * n_planes = 4: xs / ys / dxs / dys hold all four scan orders, (batch, 4, dim, H*W): row-major, column-major and both reversed.
+ * n_planes = 2: only the row-major and the column-major plane, (batch, 2, dim, H*W) -- the reversed orders are then walked by the scan
+ *              kernels themselves (mirror_pairs above): ys is the per-pair sum they accumulated, dys / xs are read by both groups.
  * ss2d_in_fwd : x (batch,H,W,dim) channels-last -> permute (:533) -> depthwise 3x3 conv, padding 1, + bias (:534; conv_w is
  *               (dim,1,3,3) contiguous, conv_b (dim) or NULL) -> SiLU (:534) -> CrossScan (:403-404) -> xs (batch,4,dim,H*W), row
  *               pitch `row_pitch` floats (k=0 row-major, 1 column-major, 2/3 reversed)
@@ -186,17 +189,17 @@ int selscan_b200_cross_merge(const float* ys, float* y, int32_t batch, int32_t d
  * ss2d_out_bwd: dout (batch,H,W,dim) contiguous -> dz (channels-last, stride dz_pos_stride; iff z), dys (layout of ys), and
  *               dln_part: selscan_b200_ss2d_out_partial_elems() floats = (n_tiles, 2, dim) per-tile sums for d ln_weight, d ln_bias */
 int selscan_b200_ss2d_in_fwd(const float* x, int64_t x_pos_stride, const float* conv_w, const float* conv_b, float* xs,
-                             int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream);
+                             int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, int32_t n_planes, void* stream);
 int selscan_b200_ss2d_in_bwd(const float* dxs, const float* x, int64_t x_pos_stride, const float* conv_w, const float* conv_b,
                              float* dx, int64_t dx_pos_stride, float* dconv_part, int32_t batch, int32_t dim, int32_t H, int32_t W,
-                             int64_t row_pitch, void* stream);
+                             int64_t row_pitch, int32_t n_planes, void* stream);
 int64_t selscan_b200_ss2d_out_partial_elems(int32_t batch, int32_t dim, int32_t H, int32_t W);
 int selscan_b200_ss2d_out_fwd(const float* ys, int64_t row_pitch, const float* z, int64_t z_pos_stride, const float* ln_weight,
                               const float* ln_bias, float eps, float* out, float* xhat, float* rstd, int32_t batch, int32_t dim,
-                              int32_t H, int32_t W, void* stream);
+                              int32_t H, int32_t W, int32_t n_planes, void* stream);
 int selscan_b200_ss2d_out_bwd(const float* dout, const float* z, int64_t z_pos_stride, const float* xhat, const float* rstd,
                               const float* ln_weight, const float* ln_bias, float* dz, int64_t dz_pos_stride, float* dys,
-                              int64_t row_pitch, float* dln_part, int32_t batch, int32_t dim, int32_t H, int32_t W, void* stream);
+                              int64_t row_pitch, float* dln_part, int32_t batch, int32_t dim, int32_t H, int32_t W, int32_t n_planes, void* stream);
 
 /* LayerNorm over the last dimension of a contiguous (rows, dim) fp32 tensor: the op on the caller side of every SS2D block
  * (VSSBlock.ln_1, code/networks/mamba_sys.py:552,559; PatchMerging2D.norm :205; PatchExpand.norm :242; VSSM.norm / norm_up).

@@ -191,6 +191,11 @@ __attribute__((visibility("default"))) int selscan_b200_cross_merge(const float*
   return cross_common(false, ys, y, batch, dim, H, W, row_pitch, stream);
 }
 
+static int edge_planes(const char* who, int32_t n_planes) {
+  if (n_planes != 4 && n_planes != 2) return fail("%s: n_planes must be 4 (all scan orders) or 2 (row- and column-major only), got %d", who, n_planes);
+  return 0;
+}
+
 static int edge_sizes(const char* who, int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t pitch) {
   if (batch < 0 || dim <= 0 || H <= 0 || W <= 0) return fail("%s: bad sizes batch=%d dim=%d H=%d W=%d", who, batch, dim, H, W);
   if (pitch < (int64_t)H * W) return fail("%s: row_pitch (%lld) must be >= H*W (%d)", who, (long long)pitch, H * W);
@@ -206,26 +211,26 @@ static int edge_done(const char* who, cudaError_t e) {
 #define SELSCAN_EXPORT __attribute__((visibility("default")))
 
 SELSCAN_EXPORT int selscan_b200_ss2d_in_fwd(const float* x, int64_t x_pos_stride, const float* conv_w, const float* conv_b, float* xs,
-                                            int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream) {
+                                            int32_t batch, int32_t dim, int32_t H, int32_t W, int64_t row_pitch, int32_t n_planes, void* stream) {
   const char* who = "selscan_b200_ss2d_in_fwd";
   if (!x || !conv_w || !xs) return fail("%s: x, conv_w, xs must not be NULL", who);
-  if (edge_sizes(who, batch, dim, H, W, row_pitch)) return -1;
+  if (edge_sizes(who, batch, dim, H, W, row_pitch) || edge_planes(who, n_planes)) return -1;
   if (x_pos_stride < dim) return fail("%s: x_pos_stride (%lld) must be >= dim (%d)", who, (long long)x_pos_stride, dim);
   if (!selscan::ss2d_in_supported(H, W)) return fail("%s: image plane of %dx%d does not fit in shared memory", who, H, W);
   return edge_done(who, selscan::launch_ss2d_in_fwd(x, x_pos_stride, conv_w, conv_b, xs, batch, dim, H, W, row_pitch,
-                                                    static_cast<cudaStream_t>(stream)));
+                                                    n_planes, static_cast<cudaStream_t>(stream)));
 }
 
 SELSCAN_EXPORT int selscan_b200_ss2d_in_bwd(const float* dxs, const float* x, int64_t x_pos_stride, const float* conv_w,
                                             const float* conv_b, float* dx, int64_t dx_pos_stride, float* dconv_part, int32_t batch,
-                                            int32_t dim, int32_t H, int32_t W, int64_t row_pitch, void* stream) {
+                                            int32_t dim, int32_t H, int32_t W, int64_t row_pitch, int32_t n_planes, void* stream) {
   const char* who = "selscan_b200_ss2d_in_bwd";
   if (!dxs || !x || !conv_w || !dx || !dconv_part) return fail("%s: dxs, x, conv_w, dx, dconv_part must not be NULL", who);
-  if (edge_sizes(who, batch, dim, H, W, row_pitch)) return -1;
+  if (edge_sizes(who, batch, dim, H, W, row_pitch) || edge_planes(who, n_planes)) return -1;
   if (x_pos_stride < dim || dx_pos_stride < dim) return fail("%s: position strides must be >= dim (%d)", who, dim);
   if (!selscan::ss2d_in_supported(H, W)) return fail("%s: image plane of %dx%d does not fit in shared memory", who, H, W);
   return edge_done(who, selscan::launch_ss2d_in_bwd(dxs, x, x_pos_stride, conv_w, conv_b, dx, dx_pos_stride, dconv_part, batch, dim, H,
-                                                    W, row_pitch, static_cast<cudaStream_t>(stream)));
+                                                    W, row_pitch, n_planes, static_cast<cudaStream_t>(stream)));
 }
 
 SELSCAN_EXPORT int64_t selscan_b200_ss2d_out_partial_elems(int32_t batch, int32_t dim, int32_t H, int32_t W) {
@@ -234,30 +239,30 @@ SELSCAN_EXPORT int64_t selscan_b200_ss2d_out_partial_elems(int32_t batch, int32_
 
 SELSCAN_EXPORT int selscan_b200_ss2d_out_fwd(const float* ys, int64_t row_pitch, const float* z, int64_t z_pos_stride,
                                              const float* ln_weight, const float* ln_bias, float eps, float* out, float* xhat,
-                                             float* rstd, int32_t batch, int32_t dim, int32_t H, int32_t W, void* stream) {
+                                             float* rstd, int32_t batch, int32_t dim, int32_t H, int32_t W, int32_t n_planes, void* stream) {
   const char* who = "selscan_b200_ss2d_out_fwd";
   if (!ys || !ln_weight || !ln_bias || !out) return fail("%s: ys, ln_weight, ln_bias, out must not be NULL", who);
   if ((xhat == nullptr) != (rstd == nullptr)) return fail("%s: xhat and rstd are saved together (both or neither)", who);
-  if (edge_sizes(who, batch, dim, H, W, row_pitch)) return -1;
+  if (edge_sizes(who, batch, dim, H, W, row_pitch) || edge_planes(who, n_planes)) return -1;
   if (z && z_pos_stride < dim) return fail("%s: z_pos_stride must be >= dim (%d)", who, dim);
   if (!selscan::ss2d_out_supported(dim)) return fail("%s: dim=%d does not fit a shared-memory tile", who, dim);
   return edge_done(who, selscan::launch_ss2d_out_fwd(ys, row_pitch, z, z_pos_stride, ln_weight, ln_bias, eps, out, xhat, rstd, batch,
-                                                     dim, H, W, static_cast<cudaStream_t>(stream)));
+                                                     dim, H, W, n_planes, static_cast<cudaStream_t>(stream)));
 }
 
 SELSCAN_EXPORT int selscan_b200_ss2d_out_bwd(const float* dout, const float* z, int64_t z_pos_stride, const float* xhat,
                                              const float* rstd, const float* ln_weight, const float* ln_bias, float* dz,
                                              int64_t dz_pos_stride, float* dys, int64_t row_pitch, float* dln_part, int32_t batch,
-                                             int32_t dim, int32_t H, int32_t W, void* stream) {
+                                             int32_t dim, int32_t H, int32_t W, int32_t n_planes, void* stream) {
   const char* who = "selscan_b200_ss2d_out_bwd";
   if (!dout || !xhat || !rstd || !ln_weight || !ln_bias || !dys || !dln_part)
     return fail("%s: dout, xhat, rstd, ln_weight, ln_bias, dys, dln_part must not be NULL", who);
   if (z && !dz) return fail("%s: dz is required when z is given", who);
-  if (edge_sizes(who, batch, dim, H, W, row_pitch)) return -1;
+  if (edge_sizes(who, batch, dim, H, W, row_pitch) || edge_planes(who, n_planes)) return -1;
   if (z && (z_pos_stride < dim || dz_pos_stride < dim)) return fail("%s: position strides must be >= dim (%d)", who, dim);
   if (!selscan::ss2d_out_supported(dim)) return fail("%s: dim=%d does not fit a shared-memory tile", who, dim);
   return edge_done(who, selscan::launch_ss2d_out_bwd(dout, z, z_pos_stride, xhat, rstd, ln_weight, ln_bias, dz, dz_pos_stride, dys,
-                                                     row_pitch, dln_part, batch, dim, H, W, static_cast<cudaStream_t>(stream)));
+                                                     row_pitch, dln_part, batch, dim, H, W, n_planes, static_cast<cudaStream_t>(stream)));
 }
 
 SELSCAN_EXPORT int selscan_b200_layernorm_supported(int32_t dim) { return dim > 0 && selscan::ln_nv(dim) != 0; }

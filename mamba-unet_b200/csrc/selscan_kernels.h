@@ -54,14 +54,14 @@ bool ss2d_in_supported(int H, int W);
 bool ss2d_out_supported(int D);
 int64_t ss2d_out_ctas(int B, int D, int H, int W);
 cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, const float* cb, float* xs, int B, int D, int H, int W,
-                               int64_t pitch, cudaStream_t stream);
+                               int64_t pitch, int n_planes, cudaStream_t stream);
 cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, const float* cw, const float* cb, float* dx, int64_t dld,
-                               float* wpart, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream);
+                               float* wpart, int B, int D, int H, int W, int64_t pitch, int n_planes, cudaStream_t stream);
 cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, int64_t zld, const float* gamma, const float* beta,
-                                float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, cudaStream_t stream);
+                                float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, int n_planes, cudaStream_t stream);
 cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, const float* xhat, const float* rstd,
                                 const float* gamma, const float* beta, float* dz, int64_t dzld, float* dys, int64_t pitch,
-                                float* part, int B, int D, int H, int W, cudaStream_t stream);
+                                float* part, int B, int D, int H, int W, int n_planes, cudaStream_t stream);
 
 // LayerNorm over short rows (selscan_ln.cu): ln_nv(dim) == 0 means the row length is not instantiated
 int ln_nv(int D);

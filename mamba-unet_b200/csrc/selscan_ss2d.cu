@@ -66,6 +66,8 @@ struct InGeom {
   int64_t pitch;
   int vec;                        // channels-last rows can be moved as float4
   int vec4;                       // scan-order rows can be moved as float4 (H, W, pitch multiples of 4, aligned base)
+  int ndir;                       // scan-order planes per image: 4 (row, column, and both reversed) or 2 (the reversed orders are
+                                  // walked by the scan kernels themselves: selscan_b200.h, mirror_pairs)
 };
 
 template <int kCT>
@@ -170,15 +172,16 @@ ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restr
       a1 = fmaf(t[6 + s], r3[s], a1);
     }
     const float v0 = a0 * sigmoid_fast(a0), v1 = a1 * sigmoid_fast(a1);
-    float* o = xs + ((int64_t)b * 4 * g.D + c0 + c) * g.pitch;
+    float* o = xs + ((int64_t)b * g.ndir * g.D + c0 + c) * g.pitch;
     float* o2 = o + 2 * g.D * g.pitch;
+    const bool has_rev = g.ndir == 4;
     const int p = h * W + w;
     o[p] = v0;
-    o2[L - 1 - p] = v0;
+    if (has_rev) o2[L - 1 - p] = v0;
     V[c * g.VPP + h * g.VP + w] = v0;
     if (h + 1 < H) {
       o[p + W] = v1;
-      o2[L - 1 - p - W] = v1;
+      if (has_rev) o2[L - 1 - p - W] = v1;
       V[c * g.VPP + (h + 1) * g.VP + w] = v1;
     }
   }
@@ -188,9 +191,9 @@ ss2d_in_fwd_kernel(const float* __restrict__ x, int64_t ld, const float* __restr
     const int c = fdiv(i, g.dL), p = i - c * L;
     const int w = fdiv(p, g.dH), h = p - w * H;
     const float v = V[c * g.VPP + h * g.VP + w];
-    float* o = xs + (((int64_t)b * 4 + 1) * g.D + c0 + c) * g.pitch;
+    float* o = xs + (((int64_t)b * g.ndir + 1) * g.D + c0 + c) * g.pitch;
     o[p] = v;
-    o[2 * g.D * g.pitch + (L - 1 - p)] = v;
+    if (g.ndir == 4) o[2 * g.D * g.pitch + (L - 1 - p)] = v;
   }
 }
 
@@ -215,6 +218,8 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
   load_planes<kCT>(X, x + (int64_t)b * L * ld + c0, ld, c0, g);
   const int nvalid = (D - c0 < kCT ? D - c0 : kCT) * L;
   const int64_t dir2 = 2 * (int64_t)D * g.pitch;
+  const bool has_rev = g.ndir == 4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (g.vec4) {
     // CrossScan backward with 16-byte loads: a thread takes 4 consecutive positions of an order and of its reverse
     const int Lq = L >> 2, nq = nvalid >> 2;
@@ -225,9 +230,9 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
         const int q = q0 + u * nthr;
         if (q < nq) {
           const int c = fdiv(q, g.dLq), p = (q - c * Lq) << 2;
-          const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
+          const float* g0 = dxs + ((int64_t)b * g.ndir * D + c0 + c) * g.pitch;
           a[u] = __ldg(reinterpret_cast<const float4*>(g0 + p));
-          r[u] = __ldg(reinterpret_cast<const float4*>(g0 + dir2 + (L - 4 - p)));
+          r[u] = has_rev ? __ldg(reinterpret_cast<const float4*>(g0 + dir2 + (L - 4 - p))) : zero4;
         }
       }
 #pragma unroll
@@ -252,9 +257,9 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
         const int q = q0 + u * nthr;
         if (q < nq) {
           const int c = fdiv(q, g.dLq), p = (q - c * Lq) << 2;
-          const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
+          const float* g1 = dxs + (((int64_t)b * g.ndir + 1) * D + c0 + c) * g.pitch;
           a[u] = __ldg(reinterpret_cast<const float4*>(g1 + p));
-          r[u] = __ldg(reinterpret_cast<const float4*>(g1 + dir2 + (L - 4 - p)));
+          r[u] = has_rev ? __ldg(reinterpret_cast<const float4*>(g1 + dir2 + (L - 4 - p))) : zero4;
         }
       }
 #pragma unroll
@@ -280,8 +285,8 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
         const int i = i0 + u * nthr;
         if (i < nvalid) {
           const int c = fdiv(i, g.dL), p = i - c * L;
-          const float* g0 = dxs + ((int64_t)b * 4 * D + c0 + c) * g.pitch;
-          v[u] = __ldg(g0 + p) + __ldg(g0 + dir2 + (L - 1 - p));
+          const float* g0 = dxs + ((int64_t)b * g.ndir * D + c0 + c) * g.pitch;
+          v[u] = __ldg(g0 + p) + (has_rev ? __ldg(g0 + dir2 + (L - 1 - p)) : 0.f);
         }
       }
   #pragma unroll
@@ -302,8 +307,8 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
         const int i = i0 + u * nthr;
         if (i < nvalid) {
           const int c = fdiv(i, g.dL), p = i - c * L;
-          const float* g1 = dxs + (((int64_t)b * 4 + 1) * D + c0 + c) * g.pitch;
-          v[u] = __ldg(g1 + p) + __ldg(g1 + dir2 + (L - 1 - p));
+          const float* g1 = dxs + (((int64_t)b * g.ndir + 1) * D + c0 + c) * g.pitch;
+          v[u] = __ldg(g1 + p) + (has_rev ? __ldg(g1 + dir2 + (L - 1 - p)) : 0.f);
         }
       }
   #pragma unroll
@@ -406,6 +411,7 @@ ss2d_in_bwd_kernel(const float* __restrict__ dxs, const float* __restrict__ x, i
 // ------------------------------------------------------------------------------------------------------------------
 struct OutGeom {
   int D, H, W, L, tiles_h, tiles_w, DP;
+  int ndir;                      // scan-order planes per image: 4, or 2 (no reversed orders)
   FastDiv dDb;                   // by the number of 32-channel blocks
   int64_t pitch;
 };
@@ -498,17 +504,20 @@ ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, i
   const int tiles = g.tiles_h * g.tiles_w;
   const int b = blockIdx.x / tiles, t = blockIdx.x - b * tiles;
   const int h0 = (t / g.tiles_w) * TH, w0 = (t % g.tiles_w) * TW;
-  const float* yb = ys + (int64_t)b * 4 * g.D * g.pitch;
+  const float* yb = ys + (int64_t)b * g.ndir * g.D * g.pitch;
   const int64_t dir = (int64_t)g.D * g.pitch;
   const int L = g.L, D = g.D;
+  const bool has_rev = g.ndir == 4;
   for_each_run<TH, TW, false, VEC>(
       g, h0, w0,
       [&](int d, int gp, int, int) {
         const float* r = yb + (int64_t)d * g.pitch;
         Run<VEC> a = ld_run<VEC>(r + gp);
-        const Run<VEC> c = ld_run_rev<VEC>(r + 2 * dir, L, gp);
+        if (has_rev) {
+          const Run<VEC> c = ld_run_rev<VEC>(r + 2 * dir, L, gp);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) a.a[k] += c.a[k];
+          for (int k = 0; k < VEC; ++k) a.a[k] += c.a[k];
+        }
         return a;
       },
       [&](int slot, int step, const Run<VEC>& v) {
@@ -521,9 +530,11 @@ ss2d_out_fwd_kernel(const float* __restrict__ ys, const float* __restrict__ z, i
       [&](int d, int gp, int, int) {
         const float* r = yb + dir + (int64_t)d * g.pitch;
         Run<VEC> a = ld_run<VEC>(r + gp);
-        const Run<VEC> c = ld_run_rev<VEC>(r + 2 * dir, L, gp);
+        if (has_rev) {
+          const Run<VEC> c = ld_run_rev<VEC>(r + 2 * dir, L, gp);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) a.a[k] += c.a[k];
+          for (int k = 0; k < VEC; ++k) a.a[k] += c.a[k];
+        }
         return a;
       },
       [&](int slot, int step, const Run<VEC>& v) {
@@ -655,8 +666,9 @@ ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z,
     for (int d = lane; d < D; d += 32) row[d] = rs * (fmaf(row[d], __ldg(gamma + d), -c1) - __ldg(xr + d) * c2);
   }
   __syncthreads();
-  float* db = dys + (int64_t)b * 4 * D * g.pitch;
+  float* db = dys + (int64_t)b * g.ndir * D * g.pitch;
   const int64_t dir = (int64_t)D * g.pitch;
+  const bool has_rev = g.ndir == 4;
   // CrossMerge backward: every order receives the same value (the global stores need d and gp, so they sit in the first functor)
   for_each_run<TH, TW, false, VEC>(
       g, h0, w0,
@@ -666,7 +678,7 @@ ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z,
         for (int k = 0; k < VEC; ++k) v.a[k] = T[slot + k * step];
         float* r = db + (int64_t)d * g.pitch;
         st_run<VEC>(r + gp, v);
-        st_run_rev<VEC>(r + 2 * dir, L, gp, v);
+        if (has_rev) st_run_rev<VEC>(r + 2 * dir, L, gp, v);
         return v;
       },
       [&](int, int, const Run<VEC>&) {});
@@ -678,7 +690,7 @@ ss2d_out_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ z,
         for (int k = 0; k < VEC; ++k) v.a[k] = T[slot + k * step];
         float* r = db + dir + (int64_t)d * g.pitch;
         st_run<VEC>(r + gp, v);
-        st_run_rev<VEC>(r + 2 * dir, L, gp, v);
+        if (has_rev) st_run_rev<VEC>(r + 2 * dir, L, gp, v);
         return v;
       },
       [&](int, int, const Run<VEC>&) {});
@@ -695,7 +707,7 @@ struct InPlan {
 InPlan plan_in(int D, int H, int W, int64_t pitch, bool bwd) {
   InPlan p;
   InGeom& g = p.g;
-  g.D = D; g.H = H; g.W = W; g.L = H * W; g.pitch = pitch;
+  g.D = D; g.H = H; g.W = W; g.L = H * W; g.pitch = pitch; g.ndir = 4;
   g.RP = (W + 2) | 1;
   g.VP = W | 1;
   g.VPP = H * g.VP;
@@ -723,7 +735,7 @@ bool out_fits(int DP, size_t* smem) {
 
 // tile shape index: 0 = 8x8, 1 = 8x4, 2 = 4x4, 3 = 4x2, 4 = 2x2, 5 = 1x1 (any D up to ~55K)
 int plan_out(int D, int H, int W, int64_t pitch, OutGeom* g, size_t* smem) {
-  g->D = D; g->H = H; g->W = W; g->L = H * W; g->pitch = pitch;
+  g->D = D; g->H = H; g->W = W; g->L = H * W; g->pitch = pitch; g->ndir = 4;
   g->DP = D + ((1 - D % 32) + 32) % 32;
   g->dDb = make_fastdiv((D + 31) / 32);
   int shape, th, tw;
@@ -764,9 +776,10 @@ bool ss2d_in_supported(int H, int W) {
 }
 
 cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, const float* cb, float* xs, int B, int D, int H, int W,
-                               int64_t pitch, cudaStream_t stream) {
+                               int64_t pitch, int n_planes, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   InPlan p = plan_in(D, H, W, pitch, false);
+  p.g.ndir = n_planes;
   p.g.vec = al16(x) && ld % 4 == 0;
   const unsigned grid = (unsigned)((int64_t)B * ((D + p.ct - 1) / p.ct));
   cudaError_t e;
@@ -781,9 +794,10 @@ cudaError_t launch_ss2d_in_fwd(const float* x, int64_t ld, const float* cw, cons
 }
 
 cudaError_t launch_ss2d_in_bwd(const float* dxs, const float* x, int64_t ld, const float* cw, const float* cb, float* dx, int64_t dld,
-                               float* wpart, int B, int D, int H, int W, int64_t pitch, cudaStream_t stream) {
+                               float* wpart, int B, int D, int H, int W, int64_t pitch, int n_planes, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   InPlan p = plan_in(D, H, W, pitch, true);
+  p.g.ndir = n_planes;
   p.g.vec = al16(x) && ld % 4 == 0;
   p.g.vec4 = al16(dxs) && H % 4 == 0 && W % 4 == 0 && pitch % 4 == 0;
   const unsigned grid = (unsigned)((int64_t)B * ((D + p.ct - 1) / p.ct));
@@ -837,12 +851,13 @@ bool out_vec2(const float* p, int H, int W, int64_t pitch) {
 }
 
 cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, int64_t zld, const float* gamma, const float* beta,
-                                float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, cudaStream_t stream) {
+                                float eps, float* out, float* xhat, float* rstd, int B, int D, int H, int W, int n_planes, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   OutGeom g;
   size_t smem;
   const int shape = plan_out(D, H, W, pitch, &g, &smem);
   if (shape < 0) return cudaErrorInvalidValue;
+  g.ndir = n_planes;
   const unsigned grid = (unsigned)((int64_t)B * g.tiles_h * g.tiles_w);
   cudaError_t e = cudaSuccess;
   const bool vec2 = out_vec2(ys, H, W, pitch);
@@ -852,12 +867,13 @@ cudaError_t launch_ss2d_out_fwd(const float* ys, int64_t pitch, const float* z, 
 
 cudaError_t launch_ss2d_out_bwd(const float* gout, const float* z, int64_t zld, const float* xhat, const float* rstd,
                                 const float* gamma, const float* beta, float* dz, int64_t dzld, float* dys, int64_t pitch,
-                                float* part, int B, int D, int H, int W, cudaStream_t stream) {
+                                float* part, int B, int D, int H, int W, int n_planes, cudaStream_t stream) {
   if (B == 0 || D == 0 || H * W == 0) return cudaSuccess;
   OutGeom g;
   size_t smem;
   const int shape = plan_out(D, H, W, pitch, &g, &smem);
   if (shape < 0) return cudaErrorInvalidValue;
+  g.ndir = n_planes;
   const unsigned grid = (unsigned)((int64_t)B * g.tiles_h * g.tiles_w);
   cudaError_t e = cudaSuccess;
   const bool vec2 = out_vec2(dys, H, W, pitch);

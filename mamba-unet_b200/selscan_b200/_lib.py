@@ -96,17 +96,17 @@ def load():
             fn.argtypes = [_ptr, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
         _f32 = ctypes.c_float
         lib.selscan_b200_ss2d_in_fwd.restype = ctypes.c_int
-        lib.selscan_b200_ss2d_in_fwd.argtypes = [_ptr, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
+        lib.selscan_b200_ss2d_in_fwd.argtypes = [_ptr, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i64, _i32, _ptr]
         lib.selscan_b200_ss2d_in_bwd.restype = ctypes.c_int
-        lib.selscan_b200_ss2d_in_bwd.argtypes = [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i32, _i32, _i32, _i32, _i64, _ptr]
+        lib.selscan_b200_ss2d_in_bwd.argtypes = [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr, _i32, _i32, _i32, _i32, _i64, _i32, _ptr]
         lib.selscan_b200_ss2d_out_partial_elems.restype = ctypes.c_int64
         lib.selscan_b200_ss2d_out_partial_elems.argtypes = [_i32] * 4
         lib.selscan_b200_ss2d_out_fwd.restype = ctypes.c_int
         lib.selscan_b200_ss2d_out_fwd.argtypes = [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _f32, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32,
-                                                  _ptr]
+                                                  _i32, _ptr]
         lib.selscan_b200_ss2d_out_bwd.restype = ctypes.c_int
         lib.selscan_b200_ss2d_out_bwd.argtypes = [_ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr, _i32, _i32,
-                                                  _i32, _i32, _ptr]
+                                                  _i32, _i32, _i32, _ptr]
         lib.selscan_b200_layernorm_supported.restype = ctypes.c_int
         lib.selscan_b200_layernorm_supported.argtypes = [_i32]
         lib.selscan_b200_layernorm_partial_elems.restype = ctypes.c_int64

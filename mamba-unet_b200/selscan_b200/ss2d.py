@@ -29,10 +29,10 @@ def _plane_fits(H, W):
     return H * (W + 1) * 4 <= _PLANE_SMEM_BYTES
 
 
-def _empty_dirs(ref, B, D, L):
-    """(B, 4, D, L) fp32 whose rows are 16-byte aligned for any L (pitch rounded up to 4 floats, cf. ops.empty_rows)."""
+def _empty_dirs(ref, B, D, L, n=4):
+    """(B, n, D, L) fp32 whose rows are 16-byte aligned for any L (pitch rounded up to 4 floats, cf. ops.empty_rows)."""
     pitch = (L + 3) // 4 * 4
-    buf = ref.new_empty((B, 4, D, pitch))
+    buf = ref.new_empty((B, n, D, pitch))
     return buf if pitch == L else buf[..., :L]
 
 
@@ -150,14 +150,15 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def edge_in_fwd(xz, D, conv_w, conv_b):
-    """x half of xz (B, H, W, >= D) channels-last -> conv3x3 + bias + SiLU -> the four scan orders (B, 4, D, L)."""
+def edge_in_fwd(xz, D, conv_w, conv_b, n_planes=4):
+    """x half of xz (B, H, W, >= D) channels-last -> conv3x3 + bias + SiLU -> the scan orders (B, n_planes, D, L): 4 = row-major,
+    column-major and both reversed; 2 = row- and column-major only (the scan kernels walk the reversed ones themselves)."""
     B, H, W, ld = xz.shape
-    xs = _empty_dirs(xz, B, D, H * W)
+    xs = _empty_dirs(xz, B, D, H * W, n_planes)
     lib = _lib.load()
     with torch.cuda.device(xz.device):
         _lib.check(lib.selscan_b200_ss2d_in_fwd(xz.data_ptr(), ld, conv_w.data_ptr(), ops._p(conv_b), xs.data_ptr(), B, D, H, W,
-                                                xs.stride(2), _stream(xz)), "selscan_b200_ss2d_in_fwd")
+                                                xs.stride(2), n_planes, _stream(xz)), "selscan_b200_ss2d_in_fwd")
     return xs
 
 
@@ -169,13 +170,13 @@ def edge_in_bwd(d_xs, xz, D, conv_w, conv_b, d_xz):
     with torch.cuda.device(xz.device):
         _lib.check(lib.selscan_b200_ss2d_in_bwd(d_xs.data_ptr(), xz.data_ptr(), ld, conv_w.data_ptr(), ops._p(conv_b),
                                                 d_xz.data_ptr(), d_xz.shape[-1], part.data_ptr(), B, D, H, W, d_xs.stride(2),
-                                                _stream(xz)), "selscan_b200_ss2d_in_bwd")
+                                                d_xs.shape[1], _stream(xz)), "selscan_b200_ss2d_in_bwd")
     part = part.sum(0)
     return part[:, :9].reshape(D, 1, 3, 3), part[:, 9]
 
 
 def edge_out_fwd(ys, H, W, z, zld, ln_w, ln_b, eps, save):
-    """ys (B, 4, D, L) -> merge -> LayerNorm(D) -> * silu(z) -> (B, H, W, D); z is a data pointer (or None) + position stride."""
+    """ys (B, 4 or 2, D, L) -> merge -> LayerNorm(D) -> * silu(z) -> (B, H, W, D); z is a data pointer (or None) + position stride."""
     B, _, D, L = ys.shape
     out = ys.new_empty((B, H, W, D))
     xhat = ys.new_empty((B * L, D)) if save else None
@@ -183,22 +184,22 @@ def edge_out_fwd(ys, H, W, z, zld, ln_w, ln_b, eps, save):
     lib = _lib.load()
     with torch.cuda.device(ys.device):
         _lib.check(lib.selscan_b200_ss2d_out_fwd(ys.data_ptr(), ys.stride(2), z, zld, ln_w.data_ptr(), ln_b.data_ptr(), float(eps),
-                                                 out.data_ptr(), ops._p(xhat), ops._p(rstd), B, D, H, W, _stream(ys)),
+                                                 out.data_ptr(), ops._p(xhat), ops._p(rstd), B, D, H, W, ys.shape[1], _stream(ys)),
                    "selscan_b200_ss2d_out_fwd")
     return out, xhat, rstd
 
 
-def edge_out_bwd(g, H, W, z, zld, xhat, rstd, ln_w, ln_b, dz, dzld):
-    """Backward of edge_out_fwd: returns (d ys (B, 4, D, L), d ln_w, d ln_b); writes dz through the pointer `dz` when gated."""
+def edge_out_bwd(g, H, W, z, zld, xhat, rstd, ln_w, ln_b, dz, dzld, n_planes=4):
+    """Backward of edge_out_fwd: returns (d ys (B, n_planes, D, L), d ln_w, d ln_b); writes dz through the pointer `dz` when gated."""
     B, D = g.shape[0], g.shape[-1]
     L = H * W
-    d_ys = _empty_dirs(g, B, D, L)
+    d_ys = _empty_dirs(g, B, D, L, n_planes)
     lib = _lib.load()
     part = g.new_empty((int(lib.selscan_b200_ss2d_out_partial_elems(B, D, H, W)),))
     with torch.cuda.device(g.device):
         _lib.check(lib.selscan_b200_ss2d_out_bwd(g.data_ptr(), z, zld, xhat.data_ptr(), rstd.data_ptr(), ln_w.data_ptr(),
                                                  ln_b.data_ptr(), dz, dzld, d_ys.data_ptr(), d_ys.stride(2), part.data_ptr(), B, D,
-                                                 H, W, _stream(g)), "selscan_b200_ss2d_out_bwd")
+                                                 H, W, n_planes, _stream(g)), "selscan_b200_ss2d_out_bwd")
     part = part.view(-1, 2, D).sum(0)
     return d_ys, part[0], part[1]
 
@@ -233,12 +234,32 @@ def _pad_dt_weight(dt_w):
     return w, R4
 
 
+# The reversed half of CrossScan / CrossMerge inside the scan kernels (mamba_sys.py:404, :429; include/selscan_b200.h: mirror_pairs): the
+# prologue writes, and the epilogue reads, only the row-major and the column-major plane; the scan kernels walk each plane forwards for
+# one direction and backwards for the other, and accumulate both outputs (and both du) in source order.  `xs`, `out_y` and their
+# gradients shrink from (B, 4, D, L) to (B, 2, D, L).  Internally the four directions are then ordered (row, row reversed, column,
+# column reversed) = _MIRROR_PERM of the reference's (row, column, row reversed, column reversed); parameters and their gradients are
+# permuted on the way in and out.  Taken when MIRROR and ops.mirror_ok() (L % 4 == 0, enough work to run unsegmented).
+# OFF by default -- measured on B200 at batch 24 (profiles/r02_mirror.json): the edge kernels get 16 % (stage 1) to 33 % (stage 3)
+# faster with two planes, but the accumulating TMA stores, the in-place reordering in the backward's helper warps and the two
+# memsets cost the scan kernels 7 % + 0.02-0.04 ms, and the per-direction GEMMs split in two: stage 1 is a wash, stages 2 / 3 gain
+# 0.06 ms per block, and the whole training step LOSES 3 ms (44.4 vs 41.0 ms) to the extra small launches.
+MIRROR = False
+_MIRROR_PERM = (0, 2, 1, 3)    # its own inverse
+
+
+def _perm_dirs(t):
+    """Reorder the leading (direction) axis by _MIRROR_PERM with device-side ops only (no index tensor: CUDA-graph capturable)."""
+    return torch.stack([t[k] for k in _MIRROR_PERM])
+
+
 class SS2DFusedFn(torch.autograd.Function):
     """xz = in_proj(x) (B, H, W, 2*D)  ->  LayerNorm(merge(scan(...))) * silu(z)  (B, H, W, D)  (mamba_sys.py:530-537).
 
-    One autograd node with a hand-written backward: prologue kernel, the two projections as batched GEMMs (cuBLAS), the scan,
-    epilogue kernel.  d(xz) is ONE buffer whose halves are written in place by the two edge kernels; d(xs) is the scan's du
-    with the projection's contribution accumulated by the GEMM itself (beta = 1)."""
+    One autograd node with a hand-written backward: prologue kernel, the two projections as batched GEMMs, the scan, epilogue kernel.
+    d(xz) is ONE buffer whose halves are written in place by the two edge kernels; d(xs) is the scan's du with the projection's
+    contribution accumulated by the GEMM itself (beta = 1).  P = scan-order planes held in memory (4, or 2 with MIRROR), M = K / P
+    directions per plane."""
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)   # autocast is off inside: every matmul below stays fp32
@@ -246,49 +267,58 @@ class SS2DFusedFn(torch.autograd.Function):
         B, H, W, D2 = xz.shape
         D, L, K = D2 // 2, H * W, 4
         R, N = dt_w.shape[2], A_logs.shape[1]
+        C = R + 2 * N
         xz = xz.contiguous()
         conv_w, ln_w, ln_b = conv_w.contiguous(), ln_w.contiguous(), ln_b.contiguous()
         conv_b = conv_b.contiguous() if conv_b is not None else None
         needs_grad = any(ctx.needs_input_grad)
-        xs = edge_in_fwd(xz, D, conv_w, conv_b)                                          # (B, K, D, L)
+        mir = MIRROR and ops.mirror_ok(B, K * D, L, N, K)
+        P = 2 if mir else 4
+        M = K // P
+        A_k, Ds_k, dtb_k = A_logs.float().view(K, D, N), Ds.float().view(K, D), dt_b.float().view(K, D)
+        if mir:   # directions in (plane, mirror) order
+            x_proj_w, dt_w, A_k, Ds_k, dtb_k = (_perm_dirs(t) for t in (x_proj_w, dt_w, A_k, Ds_k, dtb_k))
+        x_proj_w, dt_w = x_proj_w.contiguous(), dt_w.contiguous()
+        xs = edge_in_fwd(xz, D, conv_w, conv_b, P)                                       # (B, P, D, L)
         tc = _tc_proj_ok(D, L, N, R)
         fuse_dt = FUSE_DT and R <= FUSE_DT_MAX_RANK and ops.dt_fusable(B, K * D, L, N, K, R)   # :409-412 inside the scan kernels
         dts = None
         if tc:
             from . import tcgemm
-            C = R + 2 * N
-            x_proj_w = x_proj_w.contiguous()
             x_dbl = xz.new_empty((B, K, C, L))
-            tcgemm.bgemm(x_proj_w, xs.view(B * K, D, L), x_dbl.view(B * K, C, L), b_mn=True)          # W (C, D) x xs (D, L)
-            if not fuse_dt:
-                dtw_pad, R4 = _pad_dt_weight(dt_w)
-                dts = xz.new_empty((B, K, D, L))
-                tcgemm.bgemm(dtw_pad, x_dbl.view(B * K, C, L)[:, :R4], dts.view(B * K, D, L), b_mn=True)  # padded columns are zero
+            dts = None if fuse_dt else xz.new_empty((B, K, D, L))
+            dtw_pad, R4 = _pad_dt_weight(dt_w)
+            for m in range(M):   # direction (p, m) reads plane p: one batched GEMM per m, weights shared cyclically over the images
+                xd_m = x_dbl.view(B * P, M, C, L)[:, m]
+                tcgemm.bgemm(x_proj_w.view(P, M, C, D)[:, m].contiguous(), xs.view(B * P, D, L), xd_m, b_mn=True)   # W (C, D) x xs (D, L)
+                if not fuse_dt:
+                    tcgemm.bgemm(dtw_pad.view(P, M, D, R4)[:, m].contiguous(), xd_m[:, :R4], dts.view(B * P, M, D, L)[:, m], b_mn=True)
         else:
-            x_dbl = torch.matmul(x_proj_w.unsqueeze(0), xs)                              # (B, K, R+2N, L)   :406
+            x_dbl = torch.matmul(x_proj_w.view(1, P, M, C, D), xs.unsqueeze(2)).view(B, K, C, L)          # (B, K, R+2N, L)   :406
             if not fuse_dt:
                 dts = torch.matmul(dt_w.unsqueeze(0), x_dbl[:, :, :R])                   # (B, K, D, L)      :409
                 if L % 4:                                                                # rows must stay 16-byte aligned
                     dts = _empty_dirs(xz, B, D, L).copy_(dts)
-        dt_w = dt_w.contiguous()
         dt_args = dict(dt_w=dt_w.view(K * D, R), dt_x=x_dbl[:, :, :R]) if fuse_dt else {}
-        As = -torch.exp(A_logs.float()).view(K * D, N)                                   # :417
-        Dsf, dtb = Ds.float().reshape(-1).contiguous(), dt_b.float().reshape(-1).contiguous()
-        out_y = _empty_dirs(xz, B, D, L)
+        As = -torch.exp(A_k).reshape(K * D, N).contiguous()                              # :417
+        Dsf, dtb = Ds_k.reshape(-1).contiguous(), dtb_k.reshape(-1).contiguous()
+        # with MIRROR both directions of a plane ADD their outputs into its rows: zero-initialised
+        out_y = _empty_dirs(xz, B, D, L, P).zero_() if mir else _empty_dirs(xz, B, D, L)
         ckpt = ws = None
         if needs_grad:
             ckpt = xz.new_empty((max(ops.ckpt_elems(B, K * D, L, N), 4),))
         n_ws = ops.fwd_workspace_elems(B, K * D, L, N, K)
         if n_ws > 0:
             ws = xz.new_empty((n_ws,))
-        ops.launch_fwd(xs.view(B, K * D, L), None if fuse_dt else dts.view(B, K * D, L), As, x_dbl[:, :, R:R + N],
-                       x_dbl[:, :, R + N:], Dsf, None, dtb, True, out_y.view(B, K * D, L), None, None, ckpt, ws, **dt_args)   # :420-426
+        ops.launch_fwd(xs.view(B, P * D, L), None if fuse_dt else dts.view(B, K * D, L), As, x_dbl[:, :, R:R + N],
+                       x_dbl[:, :, R + N:], Dsf, None, dtb, True, out_y.view(B, P * D, L), None, None, ckpt, ws, mirror_pairs=mir,
+                       **dt_args)                                                        # :420-426
         zptr = xz.data_ptr() + D * xz.element_size()
         y, xhat, rstd = edge_out_fwd(out_y, H, W, zptr, D2, ln_w, ln_b, eps, needs_grad)  # :429-434, :536
         if needs_grad:
             ctx.save_for_backward(xz, xs, x_dbl, dts, As, ckpt, xhat, rstd, conv_w, conv_b, x_proj_w, dt_w, Dsf, dtb, ln_w, ln_b)
             ctx.shape_A, ctx.shape_D, ctx.shape_dtb = A_logs.shape, Ds.shape, dt_b.shape
-            ctx.tc, ctx.fuse_dt = tc, fuse_dt
+            ctx.tc, ctx.fuse_dt, ctx.mir = tc, fuse_dt, mir
         return y
 
     @staticmethod
@@ -298,41 +328,49 @@ class SS2DFusedFn(torch.autograd.Function):
         B, H, W, D2 = xz.shape
         D, L, K = D2 // 2, H * W, 4
         R, N = dt_w.shape[2], As.shape[1]
-        KD = K * D
+        KD, C = K * D, R + 2 * N
+        mir = ctx.mir
+        P = 2 if mir else 4
+        M = K // P
         g = g.float().contiguous()
         d_xz = torch.empty_like(xz)
         esz = xz.element_size()
         d_ys, d_ln_w, d_ln_b = edge_out_bwd(g, H, W, xz.data_ptr() + D * esz, D2, xhat, rstd, ln_w, ln_b,
-                                            d_xz.data_ptr() + D * esz, D2)
-        du, ddelta = _empty_dirs(xz, B, D, L), _empty_dirs(xz, B, D, L)
+                                            d_xz.data_ptr() + D * esz, D2, P)            # (B, P, D, L)
+        du = _empty_dirs(xz, B, D, L, P).zero_() if mir else _empty_dirs(xz, B, D, L)    # MIRROR: both directions of a plane add
+        ddelta = _empty_dirs(xz, B, D, L)
         nbc = B * K * N * L
         flat = xz.new_zeros((2 * nbc + KD * N + 2 * KD,))
         dB, dC = flat[:nbc].view(B, K, N, L), flat[nbc:2 * nbc].view(B, K, N, L)
         dA = flat[2 * nbc:2 * nbc + KD * N].view(KD, N)
         dD, dbias = flat[2 * nbc + KD * N:2 * nbc + KD * N + KD], flat[2 * nbc + KD * N + KD:]
         dt_args = dict(dt_w=dt_w.view(KD, R), dt_x=x_dbl[:, :, :R]) if ctx.fuse_dt else {}
-        ops.launch_bwd(xs.view(B, KD, L), None if ctx.fuse_dt else dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
-                       Dsf, None, dtb, d_ys.view(B, KD, L), None, ckpt, True, du.view(B, KD, L), ddelta.view(B, KD, L), dA, dB, dC,
-                       dD, None, dbias, **dt_args)
+        ops.launch_bwd(xs.view(B, P * D, L), None if ctx.fuse_dt else dts.view(B, KD, L), As, x_dbl[:, :, R:R + N], x_dbl[:, :, R + N:],
+                       Dsf, None, dtb, d_ys.view(B, P * D, L), None, ckpt, True, du.view(B, P * D, L), ddelta.view(B, KD, L), dA, dB, dC,
+                       dD, None, dbias, mirror_pairs=mir, **dt_args)
         # The three small-output products (reductions over L with a 6..56-row result) stay on cuBLAS: a 128-row tensor-core
         # tile is mostly padding there and the 3xTF32 operand split makes them shared-memory bound (scripts/bench_tcproj.py).
         x_dt = x_dbl[:, :, :R]
         d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                      # (K, D, R)
         d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)                 # (B, K, R, L)
         d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                       # (B, K, R+2N, L)
-        d_x_proj_w = torch.matmul(d_x_dbl, xs.transpose(-1, -2)).sum(0)                   # (K, R+2N, D)
-        if ctx.tc:
-            from . import tcgemm
-            tcgemm.bgemm(x_proj_w, d_x_dbl.view(B * K, R + 2 * N, L), du.view(B * K, D, L), a_mn=True, b_mn=True,
-                         accumulate=True)                                                 # du += W^T d(x_dbl), TMA reduce-add
-        else:
-            wT = x_proj_w.transpose(-1, -2).unsqueeze(0).expand(B, K, D, R + 2 * N).reshape(B * K, D, R + 2 * N)
-            d_xs = du.view(B * K, D, L)
-            d_xs.baddbmm_(wT, d_x_dbl.view(B * K, R + 2 * N, L))                          # du + W^T d(x_dbl), no extra pass
+        d_x_proj_w = torch.matmul(d_x_dbl.view(B, P, M, C, L), xs.transpose(-1, -2).unsqueeze(2)).sum(0).view(K, C, D)   # (K, R+2N, D)
+        for m in range(M):       # du[plane p] += W_(p,m)^T d(x_dbl)_(p,m)
+            w_m = x_proj_w.view(P, M, C, D)[:, m]
+            dxd_m = d_x_dbl.view(B * P, M, C, L)[:, m]
+            if ctx.tc:
+                from . import tcgemm
+                tcgemm.bgemm(w_m.contiguous(), dxd_m, du.view(B * P, D, L), a_mn=True, b_mn=True, accumulate=True)   # TMA reduce-add
+            else:
+                wT = w_m.transpose(-1, -2).unsqueeze(0).expand(B, P, D, C).reshape(B * P, D, C)
+                du.view(B * P, D, L).baddbmm_(wT, dxd_m)                                  # du + W^T d(x_dbl), no extra pass
         d_conv_w, d_conv_b = edge_in_bwd(du, xz, D, conv_w, conv_b, d_xz)
-        d_A_logs = (dA * As).view(ctx.shape_A)
-        return (d_xz, d_conv_w, d_conv_b if conv_b is not None else None, d_x_proj_w, d_dt_w, dbias.view(ctx.shape_dtb), d_A_logs,
-                dD.view(ctx.shape_D), d_ln_w, d_ln_b, None)
+        d_A = (dA * As).view(K, D, N)
+        d_D, d_dtb = dD.view(K, D), dbias.view(K, D)
+        if mir:   # back to the reference's direction order
+            d_x_proj_w, d_dt_w, d_A, d_D, d_dtb = (_perm_dirs(t) for t in (d_x_proj_w, d_dt_w, d_A, d_D, d_dtb))
+        return (d_xz, d_conv_w, d_conv_b if conv_b is not None else None, d_x_proj_w, d_dt_w, d_dtb.reshape(ctx.shape_dtb),
+                d_A.reshape(ctx.shape_A), d_D.reshape(ctx.shape_D), d_ln_w, d_ln_b, None)
 
 
 def ss2d_inner_b200(self, xz):

@@ -262,3 +262,36 @@ def test_ss2d_block_with_and_without_fused_dt_proj(B, d_model, H, W, monkeypatch
     _close(res[0][1], res[1][1], 1e-3, 1e-4, "dx")
     for k in res[1][2]:
         _close(res[0][2][k], res[1][2][k], 2e-3, 2e-4, k)
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("B,d_model,H,W", [(10, 96, 56, 56), (4, 192, 28, 28), (3, 384, 14, 14), (24, 32, 12, 20)])
+def test_ss2d_block_with_and_without_mirrored_scan_directions(B, d_model, H, W, tc, monkeypatch):
+    """MIRROR: the prologue / epilogue move two scan-order planes instead of four and the scan kernels walk the reversed directions
+    themselves (mamba_sys.py:404, :429 inside the kernels).  Same outputs, same gradients for every parameter (which come back in the
+    reference's direction order)."""
+    from selscan_b200 import ops, ss2d
+    from selscan_b200.vssm import SS2D
+
+    _fp32()
+    monkeypatch.setattr(ss2d, "TC_PROJ", tc)
+    torch.manual_seed(d_model + W)
+    blk = SS2D(d_model).cuda()
+    with torch.no_grad():   # make the four directions differ in every parameter
+        for p in (blk.A_logs, blk.Ds, blk.dt_projs_bias, blk.out_norm.weight, blk.out_norm.bias):
+            p.add_(0.2 * torch.randn_like(p))
+    assert ops.mirror_ok(B, 8 * d_model, H * W, 16, 4)
+    x = torch.randn(B, H, W, d_model, device="cuda")
+    g = torch.randn(B, H, W, d_model, device="cuda")
+    res = []
+    for mir in (True, False):
+        monkeypatch.setattr(ss2d, "MIRROR", mir)
+        blk.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_()
+        out = blk(xi)
+        out.backward(g)
+        res.append((out.detach(), xi.grad, {k: p.grad.clone() for k, p in blk.named_parameters()}))
+    _close(res[0][0], res[1][0], 1e-4, 1e-5, "out")
+    _close(res[0][1], res[1][1], 1e-3, 1e-4, "dx")
+    for k in res[1][2]:
+        _close(res[0][2][k], res[1][2][k], 2e-3, 2e-4, k)

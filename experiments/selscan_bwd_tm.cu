@@ -36,6 +36,10 @@
 
 namespace selscan {
 
+// not declared in the product headers: this kernel is not part of the library (experiments/README.md)
+bool bwd_tm_usable();
+cudaError_t launch_bwd_tm(const BwdLaunch& p, cudaStream_t stream);
+
 namespace {
 
 constexpr int kR = 64;            // channels per unit

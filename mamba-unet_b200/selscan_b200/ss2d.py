@@ -239,11 +239,14 @@ def _pad_dt_weight(dt_w):
 # one direction and backwards for the other, and accumulate both outputs (and both du) in source order.  `xs`, `out_y` and their
 # gradients shrink from (B, 4, D, L) to (B, 2, D, L).  Internally the four directions are then ordered (row, row reversed, column,
 # column reversed) = _MIRROR_PERM of the reference's (row, column, row reversed, column reversed); parameters and their gradients are
-# permuted on the way in and out.  Taken when MIRROR and ops.mirror_ok() (L % 4 == 0, enough work to run unsegmented).
-# OFF by default -- measured on B200 at batch 24 (profiles/r02_mirror.json): the edge kernels get 16 % (stage 1) to 33 % (stage 3)
-# faster with two planes, but the accumulating TMA stores, the in-place reordering in the backward's helper warps and the two
-# memsets cost the scan kernels 7 % + 0.02-0.04 ms, and the per-direction GEMMs split in two: stage 1 is a wash, stages 2 / 3 gain
-# 0.06 ms per block, and the whole training step LOSES 3 ms (44.4 vs 41.0 ms) to the extra small launches.
+# permuted on the way in and out.  Taken when MIRROR says so and ops.mirror_ok() (L % 4 == 0, enough work to run unsegmented).
+# Measured on B200 at batch 24 (profiles/r02_mirror.json, scripts/profile_mirror.py): with two planes the edge kernels get 16 %
+# (stage 1) to 33 % (stage 3) faster, while the accumulating TMA stores, the in-place reordering in the backward's helper warps and
+# the two memsets cost the scan kernels 5-8 % + 0.02-0.04 ms -- and 20 % where dt_proj is fused into the forward as well (stage 1: its
+# time follows its instruction count).  MIRROR = "auto" mirrors only the blocks whose dt_proj is NOT fused (stages 2 and 3 of
+# Mamba-UNet), True mirrors whenever possible, False never.  Whole training step, same process (profiles/r02_ab_mirror_step.json):
+# False 41.2 ms, "auto" 42.5 ms, True 43.5 ms -- the kernels break even at stages 2-3 but the extra host-side ops (per-direction
+# GEMM calls, parameter permutations) cost the eager step more than the edge kernels save.  Hence off.
 MIRROR = False
 _MIRROR_PERM = (0, 2, 1, 3)    # its own inverse
 
@@ -272,7 +275,8 @@ class SS2DFusedFn(torch.autograd.Function):
         conv_w, ln_w, ln_b = conv_w.contiguous(), ln_w.contiguous(), ln_b.contiguous()
         conv_b = conv_b.contiguous() if conv_b is not None else None
         needs_grad = any(ctx.needs_input_grad)
-        mir = MIRROR and ops.mirror_ok(B, K * D, L, N, K)
+        fuse_dt = FUSE_DT and R <= FUSE_DT_MAX_RANK and ops.dt_fusable(B, K * D, L, N, K, R)   # :409-412 inside the scan kernels
+        mir = bool(MIRROR) and (MIRROR != "auto" or not fuse_dt) and ops.mirror_ok(B, K * D, L, N, K)
         P = 2 if mir else 4
         M = K // P
         A_k, Ds_k, dtb_k = A_logs.float().view(K, D, N), Ds.float().view(K, D), dt_b.float().view(K, D)
@@ -281,7 +285,6 @@ class SS2DFusedFn(torch.autograd.Function):
         x_proj_w, dt_w = x_proj_w.contiguous(), dt_w.contiguous()
         xs = edge_in_fwd(xz, D, conv_w, conv_b, P)                                       # (B, P, D, L)
         tc = _tc_proj_ok(D, L, N, R)
-        fuse_dt = FUSE_DT and R <= FUSE_DT_MAX_RANK and ops.dt_fusable(B, K * D, L, N, K, R)   # :409-412 inside the scan kernels
         dts = None
         if tc:
             from . import tcgemm
@@ -354,7 +357,9 @@ class SS2DFusedFn(torch.autograd.Function):
         d_dt_w = torch.matmul(ddelta, x_dt.transpose(-1, -2)).sum(0)                      # (K, D, R)
         d_dtr = torch.matmul(dt_w.transpose(-1, -2).unsqueeze(0), ddelta)                 # (B, K, R, L)
         d_x_dbl = torch.cat([d_dtr, dB, dC], dim=2)                                       # (B, K, R+2N, L)
-        d_x_proj_w = torch.matmul(d_x_dbl.view(B, P, M, C, L), xs.transpose(-1, -2).unsqueeze(2)).sum(0).view(K, C, D)   # (K, R+2N, D)
+        xsT = xs.transpose(-1, -2)                                                        # (B, P, L, D)
+        d_x_proj_w = torch.stack([torch.matmul(d_x_dbl.view(B, P, M, C, L)[:, :, m], xsT).sum(0) for m in range(M)],
+                                 dim=1).view(K, C, D)                                     # (K, R+2N, D); strided slices, no copies
         for m in range(M):       # du[plane p] += W_(p,m)^T d(x_dbl)_(p,m)
             w_m = x_proj_w.view(P, M, C, D)[:, m]
             dxd_m = d_x_dbl.view(B * P, M, C, L)[:, m]

@@ -284,7 +284,7 @@ def test_ss2d_block_with_and_without_mirrored_scan_directions(B, d_model, H, W, 
     x = torch.randn(B, H, W, d_model, device="cuda")
     g = torch.randn(B, H, W, d_model, device="cuda")
     res = []
-    for mir in (True, False):
+    for mir in (True, False):      # (the default "auto" picks one of the two per block)
         monkeypatch.setattr(ss2d, "MIRROR", mir)
         blk.zero_grad(set_to_none=True)
         xi = x.clone().requires_grad_()

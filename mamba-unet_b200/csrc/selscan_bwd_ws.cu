@@ -76,6 +76,9 @@ struct WsSmemT {
   float S12[2][kR * kS12P];         // per half chunk: [row][lane 0..3][s1 x4 positions | s2 x4] (compute)
   float DU[2][kR * kC];             // output tiles [half][row][4] (one 64 x 4 TMA store per half), double-buffered by chunk parity (helper)
   float DDT[2][kR * kC];
+  // dB / dC sums of a half chunk, [chunk parity][half][dB | dC][16 states][4 positions]: two 16 x 4 TMA reduce-add boxes per half
+  // instead of 128 scattered global REDs (profiles/r02_bwd_whatif.json: the REDs alone cost 5 % of the kernel)
+  float DBC[2][2][2 * kStatePad * kHP];
   u64 tma_full[kStg];               // TMA transaction bytes of a stage
   u64 prep_done[kStg];              // helper warps: delta / delta*u / B/C tiles of a stage written
   u64 stage_free[kStg];             // compute + helper warps: stage no longer read
@@ -84,6 +87,7 @@ struct WsSmemT {
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
@@ -114,7 +118,9 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
                       const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_ck,
                       const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_ddt,
                       const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_o,
-                      const __grid_constant__ CUtensorMap map_dz, const BwdLaunch p) {
+                      const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_db,
+                      const __grid_constant__ CUtensorMap map_dc, const int tma_bc, const BwdLaunch p) {
+  // tma_bc (kernel-uniform): dB / dC leave as TMA reduce-adds of staged tiles (map_db / map_dc: (seqlen, 16, batch * groups), box 4 x 16)
   // kDt > 0: map_dt is the 4-D map over dt_x (seqlen, rank, group, batch); the helpers form the raw step themselves
   using WsSmem = WsSmemT<kHasZ, kDt>;
   extern __shared__ unsigned char smem_raw[];
@@ -155,6 +161,10 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       tma_prefetch_desc(&map_z);
       tma_prefetch_desc(&map_o);
       tma_prefetch_desc(&map_dz);
+    }
+    if (tma_bc) {
+      tma_prefetch_desc(&map_db);
+      tma_prefetch_desc(&map_dc);
     }
   }
   __syncthreads();
@@ -212,6 +222,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     const int c_c = lane & 7, c_q = lane >> 3;
     const int c_n = (c_c & 3) * 4 + 2 * (c_q >> 1) + (c_q & 1);   // the state whose sum this lane ends up with
     const bool c_ok = c_n < N;
+    const bool tbc = !kMir && tma_bc != 0;
+    const uint32_t tbc_off = (uint32_t)(((c_c >= 4) ? kStatePad * kHP : 0) + c_n * kHP + hw) * 4;   // my (tensor, state, position) in a DBC tile
     // address of my (state, position hw of half 0) in the chunk being processed; walks backwards by one chunk per iteration
     const int dbc_sgn = rev ? -1 : 1;        // mirrored groups: dB / dC in source order, i.e. at seqlen-1-position
     float* dbc = ((c_c >= 4) ? a.dC : a.dB) + (((int64_t)b * a.ngroups + g) * N + (c_ok ? c_n : 0)) * (int64_t)L +
@@ -368,7 +380,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           k1 += __shfl_xor_sync(0xffffffffu, q1 ? o1 : o3, 16);
           float kk = q0 ? k1 : k0;
           kk += __shfl_xor_sync(0xffffffffu, q0 ? k0 : k1, 8);
-          if (c_ok && (i > 0 || c0 + h * kHP + hw < L)) atomicAdd(dbc + dbc_sgn * (h * kHP), kk);
+          if (tbc) sts_f1(smem_u32(sm.DBC[ob][h]) + tbc_off, kk);    // positions past the end are clipped by the tensor map
+          else if (c_ok && (i > 0 || c0 + h * kHP + hw < L)) atomicAdd(dbc + dbc_sgn * (h * kHP), kk);
         }
         // ---------------- du / ddelta of my (row, half): sum the 4 lanes' partials, finalise ----------------
         if (hf == h) {
@@ -400,13 +413,25 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           sts_f4(smem_u32(sm.DDT[ob]) + out16, unrev(o_dd));
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.half_free[h]));
+        // With staged dB / dC tiles all four warps feed the store of a half: the other half's warps only arrive at its barrier,
+        // and P / S12 of this half are handed back to the compute warps AFTER the barrier -- the next chunk's arrivals cannot mix
+        // with this one's, and the owner's wait_read below (store of chunk i-1) is ordered before anyone's DBC writes of chunk i+1.
+        if (!tbc && lane == 0) mbar_arrive(smem_u32(&sm.half_free[h]));
         if (hf == h) {                       // the two warps of this half hand their tiles to the TMA store
           if (hh == 1 && lane == 0) mbar_arrive(smem_u32(&sm.stage_free[s]));   // (warps of half 0 are done with the stage here ...
-          fence_proxy_async_smem();          // my du / ddelta writes -> visible to the async proxy
+          fence_proxy_async_smem();          // my du / ddelta (/ dB / dC) writes -> visible to the async proxy
           if ((htid & 63) == 0) tma_store_wait_read<0>();   // my store of chunk i-1 has read its tiles: buffer ob^1 is free for chunk i+1
-          named_bar_sync(2 + h, 64);
+          if (tbc) {
+            named_bar_sync(2 + h, kGroupThr);
+            if (lane == 0) mbar_arrive(smem_u32(&sm.half_free[h]));
+          } else {
+            named_bar_sync(2 + h, 64);
+          }
           if ((htid & 63) == 0) {
+            if (tbc) {
+              tma_reduce_add_3d(&map_db, smem_u32(sm.DBC[ob][h]), c0 + kHP * h, 0, b * a.ngroups + g);
+              tma_reduce_add_3d(&map_dc, smem_u32(sm.DBC[ob][h]) + kStatePad * kHP * 4, c0 + kHP * h, 0, b * a.ngroups + g);
+            }
             const int lo = rev ? L - (c0 + kHP * h) - kHP : c0 + kHP * h;   // mirrored: a half past the end (lo < 0) has nothing to store
             if (lo >= 0) {
               if (kMir) tma_reduce_add_3d(&map_du, smem_u32(sm.DU[ob]) + h * (kR * 16), lo, ds0, b);   // both groups of a pair add
@@ -415,8 +440,13 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
             }
             tma_store_commit();
           }
-        } else if (hh == 1 && lane == 0) {
-          mbar_arrive(smem_u32(&sm.stage_free[s]));                             //  ... and the warps of half 1 after contracting half 0)
+        } else {
+          if (tbc) {
+            fence_proxy_async_smem();
+            named_bar_arrive(2 + h, kGroupThr);
+            if (lane == 0) mbar_arrive(smem_u32(&sm.half_free[h]));
+          }
+          if (hh == 1 && lane == 0) mbar_arrive(smem_u32(&sm.stage_free[s]));   //  ... and the warps of half 1 after contracting half 0)
         }
       }
       dbc -= dbc_sgn * kC;
@@ -651,20 +681,21 @@ inline bool make_dtx_map_bwd(CUtensorMap* map, const selscan_bwd_args& a, int bo
 }
 
 template <bool kHasZ, int kDt, bool kMir = false>
-cudaError_t launch_ws_variant(const CUtensorMap (&m)[9], const BwdLaunch& p, unsigned grid, cudaStream_t stream) {
+cudaError_t launch_ws_variant(const CUtensorMap (&m)[11], int tma_bc, const BwdLaunch& p, unsigned grid, cudaStream_t stream) {
   constexpr int smem = (int)sizeof(WsSmemT<kHasZ, kDt>) + 256;
   static_assert(kHasZ || sizeof(WsSmemT<kHasZ, kDt>) + 256 + 1024 <= 116736, "two CTAs per SM");
   static_assert(sizeof(WsSmemT<kHasZ, kDt>) + 256 <= 232448, "fits one CTA per SM");
   static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
   if (const cudaError_t e = set_smem_once(configured, selscan_bwd_ws_kernel<kHasZ, kDt, kMir>, smem)) return e;
-  selscan_bwd_ws_kernel<kHasZ, kDt, kMir><<<grid, kThr, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], p);
+  selscan_bwd_ws_kernel<kHasZ, kDt, kMir><<<grid, kThr, smem, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10],
+                                                                        tma_bc, p);
   return cudaGetLastError();
 }
 
 // Returns cudaErrorNotSupported when a tensor map cannot be encoded for this layout: the caller then takes the generic kernel.
 cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
   const selscan_bwd_args& a = p.a;
-  CUtensorMap m[9];   // u, delta (or dt_x), dout, saved states, du, ddelta, z, out, dz
+  CUtensorMap m[11];  // u, delta (or dt_x), dout, saved states, du, ddelta, z, out, dz, dB, dC
   const int dt_box = a.dt_w == nullptr ? 0 : (a.dt_rank <= 6 ? 6 : kMaxFusedDtRank);
   const int src_rows = a.mirror_pairs ? a.dim / 2 : a.dim;   // rows per batch of u / dout / du
   if (!make_row_map_sw(&m[0], a.u, a.seqlen, src_rows, a.batch, a.u_d_stride, a.u_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
@@ -675,7 +706,11 @@ cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
       !make_row_map(&m[4], a.du, a.seqlen, src_rows, a.batch, a.du_d_stride, a.du_batch_stride, kHP, kR) ||
       !make_row_map(&m[5], a.ddelta, a.seqlen, a.dim, a.batch, a.ddelta_d_stride, a.ddelta_batch_stride, kHP, kR))
     return cudaErrorNotSupported;
-  m[6] = m[7] = m[8] = m[0];
+  m[6] = m[7] = m[8] = m[9] = m[10] = m[0];
+  // dB / dC as TMA reduce-adds: 16 states, rows of seqlen floats 16-byte aligned, source-order positions (not the mirrored groups)
+  const int tma_bc = !a.mirror_pairs && a.dstate == kStatePad && a.seqlen % 4 == 0 && ((reinterpret_cast<uintptr_t>(a.dB) | reinterpret_cast<uintptr_t>(a.dC)) & 15u) == 0 &&
+                     make_row_map(&m[9], a.dB, a.seqlen, a.dstate, a.batch * a.ngroups, a.seqlen, (int64_t)a.dstate * a.seqlen, kHP, kStatePad, false) &&
+                     make_row_map(&m[10], a.dC, a.seqlen, a.dstate, a.batch * a.ngroups, a.seqlen, (int64_t)a.dstate * a.seqlen, kHP, kStatePad, false);
   const unsigned grid = (unsigned)((int64_t)a.batch * a.ngroups * (p.dim_per_group / kR));
   if (a.z != nullptr) {
     if (dt_box || a.mirror_pairs) return cudaErrorNotSupported;   // (the C ABI rejects the combinations earlier)
@@ -683,16 +718,16 @@ cudaError_t launch_bwd_ws(const BwdLaunch& p, cudaStream_t stream) {
         !make_row_map_sw(&m[7], a.out, a.seqlen, a.dim, a.batch, a.out_d_stride, a.out_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B) ||
         !make_row_map_sw(&m[8], a.dz, a.seqlen, a.dim, a.batch, a.dz_d_stride, a.dz_batch_stride, kC, kR, CU_TENSOR_MAP_SWIZZLE_32B))
       return cudaErrorNotSupported;
-    return launch_ws_variant<true, 0>(m, p, grid, stream);
+    return launch_ws_variant<true, 0>(m, tma_bc, p, grid, stream);
   }
   if (a.mirror_pairs) {
-    if (dt_box == 6) return launch_ws_variant<false, 6, true>(m, p, grid, stream);
-    if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank, true>(m, p, grid, stream);
-    return launch_ws_variant<false, 0, true>(m, p, grid, stream);
+    if (dt_box == 6) return launch_ws_variant<false, 6, true>(m, tma_bc, p, grid, stream);
+    if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank, true>(m, tma_bc, p, grid, stream);
+    return launch_ws_variant<false, 0, true>(m, tma_bc, p, grid, stream);
   }
-  if (dt_box == 6) return launch_ws_variant<false, 6>(m, p, grid, stream);
-  if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank>(m, p, grid, stream);
-  return launch_ws_variant<false, 0>(m, p, grid, stream);
+  if (dt_box == 6) return launch_ws_variant<false, 6>(m, tma_bc, p, grid, stream);
+  if (dt_box) return launch_ws_variant<false, kMaxFusedDtRank>(m, tma_bc, p, grid, stream);
+  return launch_ws_variant<false, 0>(m, tma_bc, p, grid, stream);
 }
 
 }  // namespace selscan

@@ -127,7 +127,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
   WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 255) & ~(uintptr_t)255);   // 32B-swizzle atom = 256 B
   const selscan_bwd_args& a = p.a;
   const int L = a.seqlen, N = a.dstate;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // One volatile read of %tid.x: with 72 registers the compiler otherwise re-reads the special register inside the helper loop
+  // (S2R + a short-scoreboard wait, 6 % of the helper warps' time in profiles/r02_ncu_scan_summary.txt's source view)
+  int tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  const int warp = tid >> 5, lane = tid & 31;
   const int tiles_per_group = p.dim_per_group / kR;
   int bid = blockIdx.x;
   const int tile_g = bid % tiles_per_group; bid /= tiles_per_group;
@@ -138,7 +142,7 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
   const bool rev = kMir && (g & 1);                                           // CTA-uniform
   const int ds0 = kMir ? (g >> 1) * p.dim_per_group + tile_g * kR : d0;       // first row of the u / dout / du tensors
 
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStg; ++s) {
       mbar_init(smem_u32(&sm.tma_full[s]), 1);
@@ -176,7 +180,7 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
   if (warp >= 4) {
     // =========================================== helper warpgroup ===========================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelpRegs));
-    const int htid = threadIdx.x - kGroupThr;
+    const int htid = tid - kGroupThr;
     const int hw = warp - 4;
     const int row = htid & (kR - 1);        // my channel inside the CTA ...
     const int hf = htid >> 6;               // ... and my half of every chunk (warp-uniform)
@@ -280,21 +284,44 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         sts_f4(smem_u32(sm.DY[s]) + my16, y4);
         fence_proxy_async_smem();    // ordered before the TMA load that refills this stage
       }
+      // Two elements per instruction wherever a packed form exists (FMUL2 / FADD2 / FFMA2): this role is issue-bound like the other,
+      // and softplus + its derivative are 2/5 of its instructions (profiles/r02_bwd_whatif.json).  Same arithmetic as softplus_fast /
+      // sigmoid_from_w (selscan_common.cuh), element by element.
       const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
       float v[4], vu[4], sg[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float xb = tt[e] + bias;
-        float dv = xb, sgm = 1.f;
+      for (int e = 0; e < 4; e += 2) {
+        const float x0 = tt[e] + bias, x1 = tt[e + 1] + bias;
+        float d0v = x0, d1v = x1, g0 = 1.f, g1 = 1.f;
         if (softplus) {
-          float wexp;
-          dv = softplus_fast(xb, wexp);
-          sgm = sigmoid_from_w(xb, wexp);   // softplus' (bwd_kernel.cuh:446-450; == 1 to rounding for x > 20)
+          float w0, w1, r0, r1, q0, q1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w0) : "f"(-fabsf(x0) * 1.4426950408889634f));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w1) : "f"(-fabsf(x1) * 1.4426950408889634f));
+          const u64 w2 = pk2(w0, w1);
+          float a0, a1, b0, b1;
+          upk2(add2(w2, pk2(2.f, 2.f)), a0, a1);
+          upk2(add2(w2, pk2(1.f, 1.f)), b0, b1);
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(a0));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(a1));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(b0));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(b1));
+          const u64 t = mul2(w2, pk2(r0, r1));                 // w / (2 + w)
+          const u64 t2 = mul2(t, t);
+          u64 pl = fma2(t2, pk2(kAtanhC4, kAtanhC4), pk2(kAtanhC3, kAtanhC3));
+          pl = fma2(pl, t2, pk2(kAtanhC2, kAtanhC2));
+          pl = fma2(pl, t2, pk2(kAtanhC1, kAtanhC1));
+          pl = fma2(pl, t2, pk2(1.f, 1.f));
+          upk2(fma2(add2(t, t), pl, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f))), d0v, d1v);
+          float wq0, wq1;
+          upk2(mul2(w2, pk2(q0, q1)), wq0, wq1);               // softplus' (bwd_kernel.cuh:446-450; == 1 to rounding for x > 20)
+          g0 = x0 >= 0.f ? q0 : wq0;
+          g1 = x1 >= 0.f ? q1 : wq1;
         }
-        dv = (l0 + e < L) ? dv : 0.f;       // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
-        v[e] = dv;
-        vu[e] = dv * uu[e];
-        sg[e] = sgm;
+        d0v = (l0 + e < L) ? d0v : 0.f;       // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
+        d1v = (l0 + e + 1 < L) ? d1v : 0.f;
+        v[e] = d0v; v[e + 1] = d1v;
+        upk2(mul2(pk2(d0v, d1v), pk2(uu[e], uu[e + 1])), vu[e], vu[e + 1]);
+        sg[e] = g0; sg[e + 1] = g1;
       }
       sts_f4(smem_u32(sm.SD[s]) + my16, make_float4(v[0], v[1], v[2], v[3]));
       sts_f4(smem_u32(sm.SDU[s]) + my16, make_float4(vu[0], vu[1], vu[2], vu[3]));

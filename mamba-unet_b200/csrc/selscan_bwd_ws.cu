@@ -181,6 +181,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     // =========================================== helper warpgroup ===========================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHelpRegs));
     const int htid = tid - kGroupThr;
+    constexpr int kLoadThr = 32;            // the thread that issues the TMA loads (and the dz stores): lane 0 of the second helper warp --
+                                            // threads 0 and 64 issue the output stores of their halves, so three warps share the issue work
     const int hw = warp - 4;
     const int row = htid & (kR - 1);        // my channel inside the CTA ...
     const int hf = htid >> 6;               // ... and my half of every chunk (warp-uniform)
@@ -317,8 +319,10 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           g0 = x0 >= 0.f ? q0 : wq0;
           g1 = x1 >= 0.f ? q1 : wq1;
         }
-        d0v = (l0 + e < L) ? d0v : 0.f;       // past the end: a = 1, b = 0 (u and dout are TMA zero fill there)
-        d1v = (l0 + e + 1 < L) ? d1v : 0.f;
+        if (j == 0) {                         // only the first chunk processed can reach past the end: a = 1, b = 0 there
+          d0v = (l0 + e < L) ? d0v : 0.f;     // (u and dout are TMA zero fill)
+          d1v = (l0 + e + 1 < L) ? d1v : 0.f;
+        }
         v[e] = d0v; v[e + 1] = d1v;
         upk2(mul2(pk2(d0v, d1v), pk2(uu[e], uu[e + 1])), vu[e], vu[e + 1]);
         sg[e] = g0; sg[e + 1] = g1;
@@ -342,7 +346,7 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         sts_f4(smem_u32(sm.DY[s]) + my16, make_float4(dyg[0], dyg[1], dyg[2], dyg[3]));    // in place: the gated dout everyone else reads
         fence_proxy_async_smem();            // generic writes -> visible to the TMA store below, ordered before the stage's next TMA load
         named_bar_sync(1, kGroupThr);        // the whole dz tile is written
-        if (htid == 0) {
+        if (htid == kLoadThr) {
           tma_store_3d(&map_dz, smem_u32(sm.O[s]), t * kC, d0, b);      // positions past the end are clipped by the tensor map
           tma_store_commit();
         }
@@ -353,11 +357,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       if (lane == 0) mbar_arrive(smem_u32(&sm.prep_done[s]));
     };
 
-    float dD_acc = 0.f, dbias_acc = 0.f;
+    u64 dD2 = pk2(0.f, 0.f), dbias2 = pk2(0.f, 0.f);   // packed partial sums of dD / ddelta_bias
     float cb0, cb1;
     float4 sg_cur, sg_nxt = make_float4(0.f, 0.f, 0.f, 0.f);   // softplus' of my 4 elements: chunk being finalised / prepared ahead
     {
-      if (htid == 0) {
+      if (htid == kLoadThr) {
         issue_tma(0);
         if (n_tiles > 1) issue_tma(1);
       }
@@ -384,7 +388,7 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       // first the discretisation the compute warps wait for next (its TMA data landed an iteration ago), then the TMA loads of
       // chunk i+2, whose stage must first be released by every warp's work on chunk i-1
       if (i + 1 < n_tiles) prep(i + 1, cb0, cb1, sg_nxt);
-      if (htid == 0 && i + 2 < n_tiles) issue_tma(i + 2);
+      if (htid == kLoadThr && i + 2 < n_tiles) issue_tma(i + 2);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int h = 1 - hh;
@@ -413,29 +417,31 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         // ---------------- du / ddelta of my (row, half): sum the 4 lanes' partials, finalise ----------------
         if (hf == h) {
           const uint32_t srow = smem_u32(sm.S12[h]) + (uint32_t)row * (kS12P * 4);
-          float4 s1 = lds_f4(srow), s2 = lds_f4(srow + 16);
+          u64 s1a, s1b, s2a, s2b;           // s1 / s2 of my 4 positions as two packed pairs each
+          lds_2x64(srow, s1a, s1b);
+          lds_2x64(srow + 16, s2a, s2b);
 #pragma unroll
           for (int q = 1; q < 4; ++q) {
-            const float4 x1 = lds_f4(srow + q * 32), x2 = lds_f4(srow + q * 32 + 16);
-            s1.x += x1.x; s1.y += x1.y; s1.z += x1.z; s1.w += x1.w;
-            s2.x += x2.x; s2.y += x2.y; s2.z += x2.z; s2.w += x2.w;
+            u64 xa, xb, ya, yb;
+            lds_2x64(srow + q * 32, xa, xb);
+            lds_2x64(srow + q * 32 + 16, ya, yb);
+            s1a = add2(s1a, xa); s1b = add2(s1b, xb);
+            s2a = add2(s2a, ya); s2b = add2(s2b, yb);
           }
-          const float4 u4 = lds_f4(smem_u32(sm.U[s]) + my16);
-          const float4 y4 = lds_f4(smem_u32(sm.DY[s]) + my16);
-          const float4 l4 = lds_f4(smem_u32(sm.SD[s]) + my16);
-          const float4 g4 = sg_cur;
-          float4 o_du, o_dd;
-          o_du.x = fmaf(l4.x, s1.x, Dv * y4.x);                               // bwd_kernel.cuh:211, :280
-          o_du.y = fmaf(l4.y, s1.y, Dv * y4.y);
-          o_du.z = fmaf(l4.z, s1.z, Dv * y4.z);
-          o_du.w = fmaf(l4.w, s1.w, Dv * y4.w);
-          o_dd.x = fmaf(u4.x, s1.x, s2.x * kLn2) * g4.x;                      // :281-284, :446-450 (s2 in units of log2 e)
-          o_dd.y = fmaf(u4.y, s1.y, s2.y * kLn2) * g4.y;
-          o_dd.z = fmaf(u4.z, s1.z, s2.z * kLn2) * g4.z;
-          o_dd.w = fmaf(u4.w, s1.w, s2.w * kLn2) * g4.w;
+          u64 ua, ub, ya, yb, la, lb;
+          lds_2x64(smem_u32(sm.U[s]) + my16, ua, ub);
+          lds_2x64(smem_u32(sm.DY[s]) + my16, ya, yb);
+          lds_2x64(smem_u32(sm.SD[s]) + my16, la, lb);
+          const u64 Dv2 = pk2(Dv, Dv), ln2 = pk2(kLn2, kLn2);
+          const u64 dua = fma2(la, s1a, mul2(Dv2, ya)), dub = fma2(lb, s1b, mul2(Dv2, yb));      // bwd_kernel.cuh:211, :280
+          const u64 dda = mul2(fma2(ua, s1a, mul2(s2a, ln2)), pk2(sg_cur.x, sg_cur.y));          // :281-284, :446-450 (s2 in units of log2 e)
+          const u64 ddb = mul2(fma2(ub, s1b, mul2(s2b, ln2)), pk2(sg_cur.z, sg_cur.w));
           // positions past the end contribute exact zeros (delta forced to 0, u / dout / B / C zero fill), so no masking is needed
-          dbias_acc += (o_dd.x + o_dd.y) + (o_dd.z + o_dd.w);
-          dD_acc = fmaf(y4.x, u4.x, fmaf(y4.y, u4.y, fmaf(y4.z, u4.z, fmaf(y4.w, u4.w, dD_acc))));   // :213
+          dbias2 = add2(dbias2, add2(dda, ddb));
+          dD2 = fma2(ya, ua, fma2(yb, ub, dD2));                                                 // :213
+          float4 o_du, o_dd;
+          upk2(dua, o_du.x, o_du.y); upk2(dub, o_du.z, o_du.w);
+          upk2(dda, o_dd.x, o_dd.y); upk2(ddb, o_dd.z, o_dd.w);
           sts_f4(smem_u32(sm.DU[ob]) + out16, unrev(o_du));     // mirrored groups: back into source order
           sts_f4(smem_u32(sm.DDT[ob]) + out16, unrev(o_dd));
         }
@@ -482,8 +488,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       cb1 = nb1;
     }
     if ((htid & 63) == 0) tma_store_wait_all<0>();
-    if (a.dD != nullptr) atomicAdd(a.dD + d, dD_acc);                      // two threads (halves) per channel, summed over batch
-    if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, dbias_acc);
+    if (a.dD != nullptr) atomicAdd(a.dD + d, hsum2(dD2));                  // two threads (halves) per channel, summed over batch
+    if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, hsum2(dbias2));
     return;
   }
 

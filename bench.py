@@ -612,8 +612,9 @@ def main():
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": table[dom]["bwd_ms"],
                 "share_of_step": round(dict((s[0], s[3]) for s in stages)[dom] * table[dom]["bwd_ms"] /
                                        sum(s[3] * (table[s[0]]["fwd_ms"] + table[s[0]]["bwd_ms"]) for s in stages), 4),
-                "note": "not HBM-bound: SM-side limits bound this kernel (shared-memory/shuffle pipe ~79% busy, issue slots 54%, MUFU 48% "
-                        "at once, profiles/r02_ncu_scan_summary.txt); see DESIGN.md section 4"}
+                "note": "not HBM-bound: both warp roles of this kernel run dependent instruction chains ~85-90% of the time "
+                        "(shared-memory pipe 71% busy, issue slots 54%, MUFU 51% at once: profiles/r02_ncu_scan_summary.txt; what each "
+                        "cost is worth: profiles/r02_bwd_whatif.json); see DESIGN.md section 4"}
 
     # ---- e2e: public op from pinned host buffers ---------------------------------------------------------------
     e2e = None

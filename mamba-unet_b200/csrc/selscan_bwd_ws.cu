@@ -20,13 +20,16 @@
 //              ahead and publishes delta and delta*u; gathers B/C (any strides, loaded two chunks ahead) into the
 //              [position][B0..15 C0..15] tile; one lane issues the TMA loads two chunks ahead (u, delta, dout: 64 x 8 boxes with the
 //              32-byte swizzle; saved state: 64 x 16) into a 3-stage ring; after the compute warps finish a half chunk it sums P
-//              over the 32 channel pairs (one atomic per (state, position) per CTA -- the reference issues one per (channel, state,
+//              over the 32 channel pairs (one sum per (state, position) per CTA, sent as 16 x 4 TMA reduce-add boxes where the rows
+//              of dB / dC are 16-byte aligned, as scalar atomics otherwise -- the reference issues one atomic per (channel, state,
 //              position), bwd_kernel.cuh:298-316), sums the S12 partials over the 4 lanes of a channel and finalises du, ddelta
 //              (through softplus'), dD, ddelta_bias; du / ddelta leave by per-half TMA stores.
 // Hand-over is by mbarriers only (full/empty per stage and per half chunk); the two roles drift by up to a chunk.  All waits are
 // bounded (trap instead of hang).  16 warps per SM (2 CTAs): 8 dense compute warps + 8 helper warps that fill their stalls.
-// Measured (stage 1, batch 24): 0.925 ms against 0.98 ms; issue slots 54 % busy, shared-memory pipe 79 % -- the kernel now sits on
-// that pipe; one CTA per SM (batch <= 8): 0.69 against 0.85 ms.
+// Measured (stage 1, batch 24): 0.888 ms (single-role kernel: 0.98); issue slots 54 % busy, shared-memory pipe 71 %, MUFU 51 %.
+// No pipe is the limit by itself: what-if builds (profiles/r02_bwd_whatif.json) show that the time follows the HELPER warps' chain
+// of dependent instructions (busy ~90 % of the time; the compute warps wait 10 % for prep_done) -- hence dB / dC as TMA reduce-adds
+// of staged tiles and packed f32x2 helper math.  One CTA per SM (batch <= 8): 0.69 against 0.85 ms.
 #include <atomic>
 #include <type_traits>
 

@@ -59,12 +59,22 @@ constexpr int kPP = kHP * 32 + 16;   // floats per channel pair in a P half: 4 p
                                      // a quarter-warp store to disjoint banks and readers need no swizzle
 constexpr int kS12P = 36;            // floats per row in an S12 half (32 + 16 bytes: conflict-free STS.128 by (row, lane), LDS.128 by row)
 
+// One stage of the ring: every per-stage tile in ONE block, so that a stage costs one base address per thread (the tiles used to be
+// separate [kStg] arrays: one multiply-add each, ~15 instructions per chunk and warp).  Multiples of 256 bytes throughout.
+struct WsStage {
+  float CK[kR * kStatePad];         // [row][16 states]                                    (TMA)
+  float U[kR * kC];                 // [row][8 positions] (one 64 x 8 box)                  (TMA)
+  float DT[kR * kC];                //   raw delta
+  float DY[kR * kC];
+  float SD[kR * kC];                // delta   [row][8]                                     (helper)
+  float SDU[kR * kC];               // delta*u
+  float BC[kC * kPitch + 32];       // [position][B0..15 C0..15]                            (helper)   (+ 128 bytes: block size % 256 == 0)
+};
+static_assert(sizeof(WsStage) % 256 == 0, "stage tiles keep their 256-byte alignment");
+
 template <bool kHasZ, int kDt>
 struct WsSmemT {
-  float CK[kStg][kR * kStatePad];   // [row][16 states]                                    (TMA)
-  float U[kStg][kR * kC];           // [row][8 positions] (one 64 x 8 box)                  (TMA)
-  float DT[kStg][kR * kC];          //   raw delta
-  float DY[kStg][kR * kC];
+  WsStage st[kStg];
   // gated calls only (bwd_kernel.cuh:171-207): z and the ungated forward output, [row][8] like U (TMA: the hardware swizzle is a
   // function of the shared-memory ADDRESS, so these tiles sit with the other TMA tiles at multiples of 256 bytes); the helpers
   // overwrite dout with dout * silu(z) and `out` with dz in place, and dz leaves by a TMA store of the whole stage tile
@@ -72,9 +82,6 @@ struct WsSmemT {
   float O[kHasZ ? kStg : 1][kHasZ ? kR * kC : 64];
   // fused dt_proj only (mamba_sys.py:409): the dt rows of x_dbl, [rank][8 positions] dense (TMA), instead of the DT tile
   float XDT[kStg][kDt > 0 ? (kDt * kC + 31) / 32 * 32 : 32];   // (multiples of 128 bytes: TMA tiles before and after stay aligned)
-  float BC[kStg][kC * kPitch];      // [position][B0..15 C0..15]                            (helper)
-  float SD[kStg][kR * kC];          // delta   [row][8]                                     (helper)
-  float SDU[kStg][kR * kC];         // delta*u
   float P[2][kNP * kPP];            // per half chunk: [pair][position][dB 0..15 | dC 0..15]   (compute)
   float S12[2][kR * kS12P];         // per half chunk: [row][lane 0..3][s1 x4 positions | s2 x4] (compute)
   float DU[2][kR * kC];             // output tiles [half][row][4] (one 64 x 4 TMA store per half), double-buffered by chunk parity (helper)
@@ -250,19 +257,19 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         tma_load_3d(smem_u32(sm.O[s]), &map_o, l0, d0, b, full);
       }
       const int lc = rev ? max(L - l0 - kC, 0) : l0;    // mirrored groups: the chunk's source positions
-      tma_load_3d(smem_u32(sm.U[s]), &map_u, lc, ds0, b, full);
+      tma_load_3d(smem_u32(sm.st[s].U), &map_u, lc, ds0, b, full);
       if (kDt > 0) tma_load_4d(smem_u32(sm.XDT[s]), &map_dt, lc, 0, g, b, full);   // ranks >= dt_rank / positions outside: zero fill
-      else tma_load_3d(smem_u32(sm.DT[s]), &map_dt, lc, d0, b, full);
-      tma_load_3d(smem_u32(sm.DY[s]), &map_dy, lc, ds0, b, full);
+      else tma_load_3d(smem_u32(sm.st[s].DT), &map_dt, lc, d0, b, full);
+      tma_load_3d(smem_u32(sm.st[s].DY), &map_dy, lc, ds0, b, full);
       // saved state t-1 = state before the chunk's first position; state "-1" is out of bounds -> zeros
-      tma_load_2d(smem_u32(sm.CK[s]), &map_ck, (t - 1) * kStatePad, b * a.dim + d0, full);
+      tma_load_2d(smem_u32(sm.st[s].CK), &map_ck, (t - 1) * kStatePad, b * a.dim + d0, full);
     };
     // discretise my 4 elements of chunk j, publish delta, delta*u, softplus' and the chunk's B/C values (loaded one iteration earlier)
     auto prep = [&](int j, float cb0, float cb1, float4& sg_out) {
       const int t = n_tiles - 1 - j, s = j % kStg, l0 = t * kC + hf * kHP;
       mbar_wait(smem_u32(&sm.tma_full[s]), (uint32_t)((j / kStg) & 1));
       const uint32_t src16 = src16_of(j);
-      const float4 u4 = unrev(lds_f4(smem_u32(sm.U[s]) + src16));
+      const float4 u4 = unrev(lds_f4(smem_u32(sm.st[s].U) + src16));
       float4 t4;
       if (kDt > 0) {   // raw step of my 4 positions: dt_w[d, :] . dt_x[:, l]  (all rows of a warp read the same 16 bytes: broadcast)
         t4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -273,11 +280,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           t4.z = fmaf(Wd[r], x4.z, t4.z); t4.w = fmaf(Wd[r], x4.w, t4.w);
         }
       } else {
-        t4 = unrev(lds_f4(smem_u32(sm.DT[s]) + src16));
+        t4 = unrev(lds_f4(smem_u32(sm.st[s].DT) + src16));
       }
       if (kMir && rev) {   // put u and dout of the stage into scan order, in place, before anyone else reads them: every thread reads
                            // the half its partner writes, hence the barrier between the reads and the writes
-        float4 y4 = unrev(lds_f4(smem_u32(sm.DY[s]) + src16));
+        float4 y4 = unrev(lds_f4(smem_u32(sm.st[s].DY) + src16));
         float4 uz = u4;
         const int lp = (n_tiles - 1 - j) * kC + hf * kHP;   // past the end the box holds other positions' data, not zero fill: clear
         if (lp + 0 >= L) { uz.x = 0.f; y4.x = 0.f; }
@@ -285,8 +292,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         if (lp + 2 >= L) { uz.z = 0.f; y4.z = 0.f; }
         if (lp + 3 >= L) { uz.w = 0.f; y4.w = 0.f; }
         named_bar_sync(1, kGroupThr);
-        sts_f4(smem_u32(sm.U[s]) + my16, uz);
-        sts_f4(smem_u32(sm.DY[s]) + my16, y4);
+        sts_f4(smem_u32(sm.st[s].U) + my16, uz);
+        sts_f4(smem_u32(sm.st[s].DY) + my16, y4);
         fence_proxy_async_smem();    // ordered before the TMA load that refills this stage
       }
       // Two elements per instruction wherever a packed form exists (FMUL2 / FADD2 / FFMA2): this role is issue-bound like the other,
@@ -330,13 +337,13 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
         upk2(mul2(pk2(d0v, d1v), pk2(uu[e], uu[e + 1])), vu[e], vu[e + 1]);
         sg[e] = g0; sg[e + 1] = g1;
       }
-      sts_f4(smem_u32(sm.SD[s]) + my16, make_float4(v[0], v[1], v[2], v[3]));
-      sts_f4(smem_u32(sm.SDU[s]) + my16, make_float4(vu[0], vu[1], vu[2], vu[3]));
+      sts_f4(smem_u32(sm.st[s].SD) + my16, make_float4(v[0], v[1], v[2], v[3]));
+      sts_f4(smem_u32(sm.st[s].SDU) + my16, make_float4(vu[0], vu[1], vu[2], vu[3]));
       sg_out = make_float4(sg[0], sg[1], sg[2], sg[3]);
       if (kHasZ) {   // bwd_kernel.cuh:186-191: dz = dout * out * sigmoid(z) * (1 + z * (1 - sigmoid(z))), then dout <- dout * silu(z)
         const float4 z4 = lds_f4(smem_u32(sm.Z[s]) + my16);
         const float4 o4 = lds_f4(smem_u32(sm.O[s]) + my16);
-        const float4 y4 = lds_f4(smem_u32(sm.DY[s]) + my16);
+        const float4 y4 = lds_f4(smem_u32(sm.st[s].DY) + my16);
         const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, oo[4] = {o4.x, o4.y, o4.z, o4.w}, yy[4] = {y4.x, y4.y, y4.z, y4.w};
         float dzv[4], dyg[4];
 #pragma unroll
@@ -346,7 +353,7 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           dyg[e] = yy[e] * zz[e] * sz;
         }
         sts_f4(smem_u32(sm.O[s]) + my16, make_float4(dzv[0], dzv[1], dzv[2], dzv[3]));     // in place: dz
-        sts_f4(smem_u32(sm.DY[s]) + my16, make_float4(dyg[0], dyg[1], dyg[2], dyg[3]));    // in place: the gated dout everyone else reads
+        sts_f4(smem_u32(sm.st[s].DY) + my16, make_float4(dyg[0], dyg[1], dyg[2], dyg[3]));    // in place: the gated dout everyone else reads
         fence_proxy_async_smem();            // generic writes -> visible to the TMA store below, ordered before the stage's next TMA load
         named_bar_sync(1, kGroupThr);        // the whole dz tile is written
         if (htid == kLoadThr) {
@@ -354,8 +361,8 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
           tma_store_commit();
         }
       }
-      sts_f1(smem_u32(sm.BC[s]) + bc_i0, cb0);
-      sts_f1(smem_u32(sm.BC[s]) + bc_i1, cb1);
+      sts_f1(smem_u32(sm.st[s].BC) + bc_i0, cb0);
+      sts_f1(smem_u32(sm.st[s].BC) + bc_i1, cb1);
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sm.prep_done[s]));
     };
@@ -432,9 +439,9 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
             s2a = add2(s2a, ya); s2b = add2(s2b, yb);
           }
           u64 ua, ub, ya, yb, la, lb;
-          lds_2x64(smem_u32(sm.U[s]) + my16, ua, ub);
-          lds_2x64(smem_u32(sm.DY[s]) + my16, ya, yb);
-          lds_2x64(smem_u32(sm.SD[s]) + my16, la, lb);
+          lds_2x64(smem_u32(sm.st[s].U) + my16, ua, ub);
+          lds_2x64(smem_u32(sm.st[s].DY) + my16, ya, yb);
+          lds_2x64(smem_u32(sm.st[s].SD) + my16, la, lb);
           const u64 Dv2 = pk2(Dv, Dv), ln2 = pk2(kLn2, kLn2);
           const u64 dua = fma2(la, s1a, mul2(Dv2, ya)), dub = fma2(lb, s1b, mul2(Dv2, yb));      // bwd_kernel.cuh:211, :280
           const u64 dda = mul2(fma2(ua, s1a, mul2(s2a, ln2)), pk2(sg_cur.x, sg_cur.y));          // :281-284, :446-450 (s2 in units of log2 e)
@@ -524,11 +531,11 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
     const uint32_t par = (uint32_t)((i / kStg) & 1);
     mbar_wait(smem_u32(&sm.prep_done[s]), par);
     mbar_wait(smem_u32(&sm.tma_full[s]), par);     // completed long ago: makes the TMA-written dout / state tiles visible to me
-    const uint32_t dy_row = smem_u32(sm.DY[s]) + pp * (kC * 4);   // + hoff[half] + c * kCT
-    const uint32_t ck_row = smem_u32(sm.CK[s]) + pp * (kStatePad * 4) + sq * 16;
-    const uint32_t bc_base = smem_u32(sm.BC[s]) + sq * (kLS * 4);
-    const uint32_t sd_row = smem_u32(sm.SD[s]) + pp * (kC * 4);
-    const uint32_t sdu_row = smem_u32(sm.SDU[s]) + pp * (kC * 4);
+    const uint32_t dy_row = smem_u32(sm.st[s].DY) + pp * (kC * 4);   // + hoff[half] + c * kCT
+    const uint32_t ck_row = smem_u32(sm.st[s].CK) + pp * (kStatePad * 4) + sq * 16;
+    const uint32_t bc_base = smem_u32(sm.st[s].BC) + sq * (kLS * 4);
+    const uint32_t sd_row = smem_u32(sm.st[s].SD) + pp * (kC * 4);
+    const uint32_t sdu_row = smem_u32(sm.st[s].SDU) + pp * (kC * 4);
 
     float dl[2][kC];
 #pragma unroll

@@ -272,13 +272,18 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       const float4 u4 = unrev(lds_f4(smem_u32(sm.st[s].U) + src16));
       float4 t4;
       if (kDt > 0) {   // raw step of my 4 positions: dt_w[d, :] . dt_x[:, l]  (all rows of a warp read the same 16 bytes: broadcast)
-        t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        u64 ta = pk2(0.f, 0.f), tb = ta;   // two positions per FFMA2 (the weight is a broadcast operand)
 #pragma unroll
         for (int r = 0; r < kDt; ++r) {
-          const float4 x4 = unrev(lds_f4(smem_u32(sm.XDT[s]) + (uint32_t)(r * (kC * 4) + srchalf_of(j) * 16)));
-          t4.x = fmaf(Wd[r], x4.x, t4.x); t4.y = fmaf(Wd[r], x4.y, t4.y);
-          t4.z = fmaf(Wd[r], x4.z, t4.z); t4.w = fmaf(Wd[r], x4.w, t4.w);
+          u64 xa, xb;
+          lds_2x64(smem_u32(sm.XDT[s]) + (uint32_t)(r * (kC * 4) + srchalf_of(j) * 16), xa, xb);
+          const u64 w = pk2(Wd[r], Wd[r]);
+          ta = fma2(w, xa, ta);
+          tb = fma2(w, xb, tb);
         }
+        upk2(ta, t4.x, t4.y);
+        upk2(tb, t4.z, t4.w);
+        t4 = unrev(t4);                    // (mirrored groups: the box holds source order)
       } else {
         t4 = unrev(lds_f4(smem_u32(sm.st[s].DT) + src16));
       }

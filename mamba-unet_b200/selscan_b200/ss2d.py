@@ -212,9 +212,11 @@ TC_PROJ = True
 
 # dt_proj (+ bias + softplus) inside the scan kernels: the kernels read the dt rows of x_dbl and this module's
 # dt_projs_weight directly and no (B, 4D, L) step tensor is computed, stored for the backward or read.  The kernels take ranks up to
-# 12; measured on B200 at batch 24 (profiles/r02_fused_dt.json) the rank-6 expansion of stage 1 costs the two scan kernels what the
-# GEMM pass it replaces cost (+0.071 ms vs 0.076 ms per call: the scan is bound on the SM side, not by HBM) and frees 231 MB of saved
-# activations per block, while rank 12 (stage 2) costs twice its GEMM -- so the default fuses up to rank 6.  FUSE_DT = False: never.
+# 12; measured on B200 at batch 24 (profiles/r02_fused_dt.json, scripts/bench_fused_dt.py) the rank-6 expansion of stage 1 costs the
+# two scan kernels +0.10 ms per call against 0.077 ms for the GEMM pass it replaces (the scan is bound on the SM side, by its helper
+# warps' instruction chains, not by HBM), while rank 12 (stage 2) costs 2.5x its GEMM -- so the default fuses up to rank 6 only.
+# Whole training step, same process (profiles/r02_ab_fuse_dt_step.json): 40.86 ms / 9.46 GB peak with, 40.64 ms / 10.32 GB without:
+# half a percent of time for 0.86 GB (8 %) of saved activations.  FUSE_DT = False: never.
 FUSE_DT = True
 FUSE_DT_MAX_RANK = 6
 

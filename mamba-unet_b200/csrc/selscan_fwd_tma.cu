@@ -54,6 +54,11 @@ constexpr int kThreads = (kConsWarps + 1) * 32;
 constexpr int kLaneStates = kStatePad / 2;  // states per lane
 constexpr int kTileBytes = kRows * kTL * 4;          // 8 KB
 constexpr int kOutBytes = kWarpRows * kTL * 4;       // 2 KB
+// Saved states ("checkpoints", one per 8 positions) are staged in shared memory and leave by TMA: 32 scattered 16-byte global stores per
+// warp instruction cost the forward 10-17 % (what-if build without them, round 2).  Two half buffers per warp (saved states 0-1 / 2-3 of
+// a tile), each [16 rows][2 x 16 states] = 128-byte rows with the 128-byte swizzle (a quarter-warp = 8 rows x one 16-byte chunk
+// touches all banks), one 32-float x 16-row box each.
+constexpr int kCkHalfBytes = kWarpRows * 2 * kStatePad * 4;   // 2 KB
 
 // shared-memory carve-up (bytes from a 1024-byte aligned base; every TMA tile is a multiple of 1024 bytes)
 // kDt > 0: fused dt_proj -- the stage carries a [kDt ranks][32 positions] tile of x_dbl's dt rows instead of a delta tile
@@ -65,7 +70,8 @@ struct Lay {
   static constexpr int kOut = kHasZ ? 2 : 1;     // output tiles per buffer: out [, out_z]
   static constexpr uint32_t oIn = 0;                                            // [stage][which]
   static constexpr uint32_t oOut = oIn + kStages * kIn * kTileBytes;           // [warp][buffer][which]
-  static constexpr uint32_t oBC = oOut + kConsWarps * 2 * kOut * kOutBytes;    // [stage][position][36]
+  static constexpr uint32_t oCk = oOut + kConsWarps * 2 * kOut * kOutBytes;    // [warp][half][16 rows][128 bytes]  (TMA, 1024-byte aligned)
+  static constexpr uint32_t oBC = oCk + kConsWarps * 2 * kCkHalfBytes;         // [stage][position][36]
   static constexpr uint32_t oDt = oBC + kStages * kTL * kBCPitch * 4;          // [stage][rank][32 positions] (TMA, dense 128-byte rows)
   static constexpr uint32_t kDtBytes = kDt * kTL * 4;
   static constexpr uint32_t oBar = oDt + kStages * kDtBytes;                   // full[stage], empty[stage]
@@ -109,7 +115,9 @@ template <int kMode, bool kHasZ, int kDt, bool kMir>
 __global__ void __launch_bounds__(kThreads, Lay<kHasZ, kDt>::kCtas)
 selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_dt,
                        const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_out,
-                       const __grid_constant__ CUtensorMap map_outz, const FwdLaunch p, const int n_items) {
+                       const __grid_constant__ CUtensorMap map_outz, const __grid_constant__ CUtensorMap map_ck, const int ck_tma,
+                       const FwdLaunch p, const int n_items) {
+  // ck_tma (kernel-uniform): the saved states leave by TMA (map_ck: (n_ckpt * 16 floats, batch * dim rows), box 32 x 16, 128-byte swizzle)
   // kDt > 0: map_dt is the 4-D map over dt_x (seqlen, rank, group, batch) and the raw step is formed here (mamba_sys.py:409)
   using LY = Lay<kHasZ, kDt>;
   constexpr int kStages = LY::kStages;
@@ -131,6 +139,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     tma_prefetch_desc(&map_u);
     tma_prefetch_desc(&map_dt);
     if (kMode != 1) tma_prefetch_desc(&map_out);
+    if (kMode != 1 && ck_tma) tma_prefetch_desc(&map_ck);
     if (kHasZ) {
       tma_prefetch_desc(&map_z);
       tma_prefetch_desc(&map_outz);
@@ -261,6 +270,10 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     }
     float sum_delta = 0.f;
     float* __restrict__ ck = (kMode != 1 && a.ckpt) ? a.ckpt + row * p.n_ckpt * kStatePad + h * kLaneStates : nullptr;
+    const bool ckt = kMode != 1 && ck_tma != 0;     // saved states through the staging tiles + TMA (else: the global stores below)
+    const uint32_t ck_stage = sm0 + LY::oCk + (uint32_t)warp * (2 * kCkHalfBytes) + (uint32_t)ch * (2 * kStatePad * 4);   // my row; + half * kCkHalfBytes
+    const uint32_t ck_key = (uint32_t)(ch & 7) << 4;   // 128-byte swizzle of the staging tiles
+    const int ck_row0 = (int)((int64_t)w.b * a.dim + w.d0 + warp * kWarpRows);
     const float Dv = cur.Dv, bias = cur.bias;
     const int next_item = item + (int)gridDim.x;
     Item wn = w;
@@ -346,6 +359,10 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(out_row + kOutBytes + off), "f"(o0 * g0), "f"(o1 * g1) : "memory");
         }
       };
+      // saved states 2 hb, 2 hb + 1 of the tile -> rows of the checkpoint tensor (the tensor map clips the interval a sequence ends in)
+      auto send_ck = [&](int hb) {
+        tma_store_2d_if(&map_ck, sm0 + LY::oCk + (uint32_t)(warp * 2 + hb) * kCkHalfBytes, (l0 / kCkptInterval + 2 * hb) * kStatePad, ck_row0, ckt && lane == 0);
+      };
       prefetch(0, uv_n, dl_n);
       // quads of the tile that hold at least one position of the sequence: only the last tile of a sequence can be partial, and it
       // alone takes the instantiation with the early exit.  The full tile is ONE basic block (every condition below is a
@@ -390,6 +407,11 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
             continue;
           }
           if (q > 0) finish(q - 1, yp, up0, up1);
+          if (!kPartial && q == 4) {   // saved states 0-1 of the tile were staged and fenced in quad 3 and the shuffles of finish() put every
+            send_ck(0);                // lane's fence before this point: send them half a tile ahead of the rest
+            tma_store_commit();
+            tma_store_wait_read<1>();  // the group before this one (previous tile: out + saved states 2-3) has been read: half buffer 1 is
+          }                            // free for quads 5 and 7 (the shuffles in between order lane 0's wait before the other lanes' stores)
 #pragma unroll
           for (int j = 0; j < 4; ++j) yp[j] = y[j];
           up0 = hi ? uv[2] : uv[0];
@@ -401,8 +423,13 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
 #pragma unroll
             for (int n = 0; n < 4; ++n) upk2(x2[n], xs[2 * n], xs[2 * n + 1]);
             float* dst = ck + (int64_t)(done / kCkptInterval - 1) * kStatePad;
-            stg_f4_if(dst, xs[0], xs[1], xs[2], xs[3], ck != nullptr && done < L);
-            stg_f4_if(dst + 4, xs[4], xs[5], xs[6], xs[7], ck != nullptr && done < L);
+            stg_f4_if(dst, xs[0], xs[1], xs[2], xs[3], !ckt && ck != nullptr && done < L);
+            stg_f4_if(dst + 4, xs[4], xs[5], xs[6], xs[7], !ckt && ck != nullptr && done < L);
+            const uint32_t cb = ck_stage + (uint32_t)(q >> 2) * kCkHalfBytes;
+            const uint32_t c16 = (uint32_t)((q >> 1) & 1) * (kStatePad * 4) + (uint32_t)h * (kLaneStates * 4);
+            sts_f4(cb + (c16 ^ ck_key), make_float4(xs[0], xs[1], xs[2], xs[3]));
+            sts_f4(cb + ((c16 + 16) ^ ck_key), make_float4(xs[4], xs[5], xs[6], xs[7]));
+            if ((q & 3) == 3) fence_proxy_async_smem();   // both saved states of a half buffer written: visible to the TMA store
           }
         }
       };
@@ -416,13 +443,18 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
       finish(n_q - 1, yp, up0, up1);
       fence_proxy_async_smem();   // my OUT writes -> visible to the TMA store
       __syncwarp();
+      if (n_q != kTL / 4) send_ck(0);   // (a partial tile sends both halves here)
+      send_ck(1);
       if (lane == 0) {
         mbar_arrive(empty_bar(s));   // the warp is done reading stage s
         if (kMir) tma_reduce_add_3d(&map_out, out_tile, rev ? max(L - l0 - kTL, 0) : l0, w.ds0 + warp * kWarpRows, w.b);   // both groups of a pair add
         else tma_store_3d(&map_out, out_tile, l0, w.d0 + warp * kWarpRows, w.b);
         if (kHasZ) tma_store_3d(&map_outz, out_tile + kOutBytes, l0, w.d0 + warp * kWarpRows, w.b);
         tma_store_commit();
-        tma_store_wait_read<1>();    // the other OUT buffer (previous tile) has been read: free for the next tile
+        // the group before this one has been read: the other OUT buffer (previous tile) and half buffer 0 of the saved states (this
+        // tile's quads 0-3) are free for the next tile; a partial tile (the last of a sequence) sent both halves just now: drain
+        if (n_q == kTL / 4) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
       }
       ++n_out;
       __syncwarp();
@@ -472,12 +504,26 @@ __global__ void selscan_fwd_combine_kernel(const FwdLaunch p) {
 template <int kMode, bool kHasZ, int kDt = 0, bool kMir = false>
 cudaError_t launch_one(const CUtensorMap& mu, const CUtensorMap& mdt, const CUtensorMap& mz, const CUtensorMap& mout,
                        const CUtensorMap& moutz, const FwdLaunch& p, int n_items, cudaStream_t stream) {
+  // saved states by TMA: rows of n_ckpt * 16 floats, box = 2 saved states (128 bytes) x 16 rows, 128-byte swizzle (the staging tiles' layout;
+  // with a 64-byte inner box the hardware pads every inner row to the swizzle span)
+  CUtensorMap mck = mu;
+  int ck_tma = 0;
+  if (kMode != 1 && p.a.ckpt != nullptr && p.n_ckpt >= 1 && (reinterpret_cast<uintptr_t>(p.a.ckpt) & 15u) == 0) {
+    if (auto enc = tensor_map_encoder()) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)p.n_ckpt * kStatePad, (cuuint64_t)p.a.batch * (cuuint64_t)p.a.dim};
+      const cuuint64_t gstr[1] = {(cuuint64_t)p.n_ckpt * kStatePad * 4};
+      const cuuint32_t box[2] = {2 * (cuuint32_t)kStatePad, (cuuint32_t)kWarpRows};
+      const cuuint32_t estr[2] = {1, 1};
+      ck_tma = enc(&mck, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.a.ckpt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+  }
   constexpr int smem = (int)Lay<kHasZ, kDt>::kBytes + 1024;
   static std::atomic<unsigned long long> configured{0};   // one cudaFuncSetAttribute per device, not per launch
   if (const cudaError_t e = set_smem_once(configured, selscan_fwd_tma_kernel<kMode, kHasZ, kDt, kMir>, smem)) return e;
   const int slots = sm_count() * Lay<kHasZ, kDt>::kCtas;
   const unsigned grid = (unsigned)(n_items < slots ? n_items : slots);
-  selscan_fwd_tma_kernel<kMode, kHasZ, kDt, kMir><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, p, n_items);
+  selscan_fwd_tma_kernel<kMode, kHasZ, kDt, kMir><<<grid, kThreads, smem, stream>>>(mu, mdt, mz, mout, moutz, mck, ck_tma, p, n_items);
   return cudaGetLastError();
 }
 

@@ -160,6 +160,15 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 2-D store, predicated (no branch in the instruction stream: the caller's tile loop stays one basic block)
+__device__ __forceinline__ void tma_store_2d_if(const CUtensorMap* m, uint32_t src, int c0, int c1, bool ok) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@p cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];\n\t}" ::"l"(reinterpret_cast<uint64_t>(m)),
+      "r"(src), "r"(c0), "r"(c1), "r"((int)ok)
+      : "memory");
+}
 // same, accumulating (fp32 add in L2) instead of overwriting
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(

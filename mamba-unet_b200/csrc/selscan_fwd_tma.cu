@@ -19,6 +19,9 @@
 //       two partial y of a position are reduce-scattered over the pair (one shuffle per position); outputs are staged in a
 //       swizzled 16 x 32 tile per warp and written back by a per-warp TMA store, so HBM only ever sees full 128-byte rows.
 //       The recurrence is thread-serial: per position and state pair one FMUL2, two MUFU.EX2, one FMUL2 and two FFMA2.
+//       The state after every 8th position (what the backward restarts from) is staged in two swizzled half tiles per warp and
+//       leaves as 32-float x 16-row TMA boxes, half a tile apart: as 16-byte global stores, one row per lane, it was 32 distinct
+//       lines per warp instruction and 10-17 % of the kernel (profiles/r02_bwd_whatif.json -> forward).
 // Full/empty mbarriers per stage are the only synchronisation; all waits are bounded (trap instead of hang).
 //
 // Low-parallelism shapes (small batch: the reference validates slice by slice, val_2D.py:35-47) split the SEQUENCE into

@@ -70,12 +70,13 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started BEFORE the warm-up (nvidia-smi needs a few hundred ms to come
+    up, more than a short timed region lasts); summary() keeps the samples that arrived between begin() and end()."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def __enter__(self):
         try:
@@ -90,7 +91,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -100,10 +101,22 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = list(self.lines)
+        if self.t0 is not None and self.t1 is not None:   # samples taken under the timed load (a line arrives up to one period late)
+            inside = [ln for ts, ln in lines if self.t0 <= ts <= self.t1 + 0.06]
+            lines = inside if inside else [ln for ts, ln in lines if self.t0 - 0.25 <= ts <= self.t1 + 0.25]
+        else:
+            lines = [ln for _, ln in lines]
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -474,6 +487,9 @@ def main():
     batch = args.batch
     stages = [s for s in STAGES if not args.stages or s[0] in args.stages.split(",")]
 
+    clk = ClockSampler(local)
+    clk.__enter__()     # nvidia-smi comes up while the inputs are generated; begin() / end() bracket the timed region
+
     # ---- resident inputs / preallocated outputs per stage (model-like distribution M) ----
     gen = torch.Generator(device=dev).manual_seed(1337 + rank)
     bufs = {}
@@ -555,12 +571,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     rec = []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    try:
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        clk.begin()
         t_wall0 = time.perf_counter()
         start.record()
         for _ in range(args.steps):
@@ -568,6 +585,9 @@ def main():
         stop.record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        clk.end()
+    finally:
+        clk.__exit__(None, None, None)
     ms_total = start.elapsed_time(stop)
     if world > 1:
         tt = torch.tensor([ms_total], device=dev)

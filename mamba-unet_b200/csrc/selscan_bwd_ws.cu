@@ -502,7 +502,9 @@ selscan_bwd_ws_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_co
       cb0 = nb0;
       cb1 = nb1;
     }
-    if ((htid & 63) == 0) tma_store_wait_all<0>();
+    // every thread that committed TMA stores: their shared-memory sources have been read (the CTA may exit; the writes themselves
+    // are complete when the grid is -- waiting for them here cost short sequences ~1 us per CTA)
+    if ((htid & 63) == 0 || htid == kLoadThr) tma_store_wait_read<0>();
     if (a.dD != nullptr) atomicAdd(a.dD + d, hsum2(dD2));                  // two threads (halves) per channel, summed over batch
     if (a.ddelta_bias != nullptr) atomicAdd(a.ddelta_bias + d, hsum2(dbias2));
     return;

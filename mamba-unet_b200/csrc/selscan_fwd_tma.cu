@@ -481,7 +481,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
     w = wn;
     cur = nxt;
   }
-  if (kMode != 1 && lane == 0) tma_store_wait_all<0>();
+  if (kMode != 1 && lane == 0) tma_store_wait_read<0>();   // sources read: the CTA may exit (the writes are complete when the grid is)
 }
 
 // Carry combine of the segmented forward: thread = (row, state); sequential over the (few) segments.

@@ -178,3 +178,32 @@ def test_tiled_backward_with_z_gate(oracle, batch, dim, L, G):
     out, last, grads = run_ours(inp, True)
     assert grads["dz"] is not None
     check_all(out, last, grads, *_oracle_refs(oracle, inp))
+
+
+def test_accumulator_alignment_fallback():
+    """dB / dC leave as TMA reduce-adds only where their rows are 16-byte aligned (selscan_bwd_ws.cu `tma_bc`); a caller may hand
+    over accumulators that are not (views at odd offsets; the ABI asks for alignment of `ckpt` only): the kernel then takes scalar
+    REDs, with the same results."""
+    from selscan_b200 import ops
+
+    torch.manual_seed(5)
+    dev, b, kd, L, K, N = "cuda", 2, 256, 200, 4, 16
+    u, delta = torch.randn(b, kd, L, device=dev), torch.randn(b, kd, L, device=dev) * 0.5
+    A = -torch.rand(kd, N, device=dev) - 0.5
+    B, C = torch.randn(b, K, N, L, device=dev), torch.randn(b, K, N, L, device=dev)
+    D, bias, dout = torch.randn(kd, device=dev), torch.randn(kd, device=dev) - 2, torch.randn(b, kd, L, device=dev)
+    nbc, n_ck = b * K * N * L, ops.ckpt_elems(b, kd, L, N)
+    res = []
+    for off in (0, 1):       # element offset of the dB | dC blocks: 0 = aligned, 1 = 4 bytes off
+        out, du, dd = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
+        ck = torch.empty(max(n_ck, 4), device=dev)
+        flat = torch.zeros(2 * nbc + 8, device=dev)
+        dB, dC = flat[off:off + nbc].view(b, K, N, L), flat[off + nbc + 4:off + 2 * nbc + 4].view(b, K, N, L)
+        small = torch.zeros(kd * N + 2 * kd, device=dev)
+        dA, dD, db = small[:kd * N].view(kd, N), small[kd * N:kd * N + kd], small[kd * N + kd:]
+        ops.launch_fwd(u, delta, A, B, C, D, None, bias, True, out, None, None, ck, None)
+        ops.launch_bwd(u, delta, A, B, C, D, None, bias, dout, None, ck, True, du, dd, dA, dB, dC, dD, None, db)
+        res.append([t.clone() for t in (out, du, dd, dA, dB, dC, dD, db)])
+    for name, a, r in zip(("out", "du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias"), res[1], res[0]):
+        scale = max(1.0, float(r.abs().max()))
+        torch.testing.assert_close(a, r, rtol=BWD_RTOL, atol=BWD_ATOL * scale, msg=lambda m: f"{name}: {m}")

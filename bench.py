@@ -357,6 +357,13 @@ def model_leg(world, rank, dev, steps):
         m1, m2 = ddp(MambaUnet(num_classes=4).to(dev).train()), ddp(MambaUnet(num_classes=4).to(dev).train())
         o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
         res["train_semi_dual_bs16"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw), n), 16)
+        # the same step with the second network on a second stream: at 16 images per network most kernels under-fill a B200 (stage-1
+        # scan: 192 CTAs on 296 slots), the two networks are independent until the losses
+        try:
+            side = torch.cuda.Stream(dev)
+            res["train_semi_dual_bs16_2streams"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw, side), n), 16)
+        except Exception as e:  # noqa: BLE001
+            res["train_semi_dual_bs16_2streams"] = {"unavailable": repr(e)[:200]}
         del m1, m2, o1, o2
         torch.cuda.empty_cache()
 
@@ -371,14 +378,18 @@ def model_leg(world, rank, dev, steps):
                 return lambda x, y: wl.supervised_step(w, o, dice, x, y)
             return make
 
-        def semi_factory():
-            a, b = ddp_on_stream(MambaUnet(num_classes=4).to(dev).train()), ddp_on_stream(MambaUnet(num_classes=4).to(dev).train())
-            oa, ob = wl.make_sgd(a), wl.make_sgd(b)
-            return lambda x, y: wl.semi_step(a, b, oa, ob, dice, x, y, 8, cw)
+        def semi_factory(two_streams=False):
+            def make():
+                a, b = ddp_on_stream(MambaUnet(num_classes=4).to(dev).train()), ddp_on_stream(MambaUnet(num_classes=4).to(dev).train())
+                oa, ob = wl.make_sgd(a), wl.make_sgd(b)
+                side = torch.cuda.Stream(dev) if two_streams else None
+                return lambda x, y: wl.semi_step(a, b, oa, ob, dice, x, y, 8, cw, side)
+            return make
 
         for key, make, inputs, imgs, tc in (("train_supervised_bs24_cudagraph", sup_factory(False), (x24, y24), 24, tc_default),
                                             ("train_supervised_bs24_tc3xtf32_cudagraph", sup_factory(True), (x24, y24), 24, True),
-                                            ("train_semi_dual_bs16_cudagraph", semi_factory, (x16, y16), 16, tc_default)):
+                                            ("train_semi_dual_bs16_cudagraph", semi_factory(), (x16, y16), 16, tc_default),
+                                            ("train_semi_dual_bs16_2streams_cudagraph", semi_factory(True), (x16, y16), 16, tc_default)):
             ss2d.TC_PROJ = tc
             try:
                 fn = make()

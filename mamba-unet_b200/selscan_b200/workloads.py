@@ -36,8 +36,21 @@ def supervised_step(model, opt, dice, x, y):
     return loss
 
 
-def semi_step(model1, model2, opt1, opt2, dice, x, y, labeled_bs, cw):
-    o1, o2 = model1(x), model2(x)
+def semi_step(model1, model2, opt1, opt2, dice, x, y, labeled_bs, cw, side=None):
+    """side: a second CUDA stream.  The two networks are independent until the losses, and at 16 images per network most of their
+    kernels leave a B200 under-filled (the scan at stage 1: 192 CTAs on 296 slots); with `side` the second network's forward runs
+    there, concurrently with the first one's, and autograd runs each network's backward on the stream of its forward -- the
+    arithmetic is unchanged.  Also capturable (GraphedStep): the capture forks and joins the two streams."""
+    if side is None:
+        o1, o2 = model1(x), model2(x)
+    else:
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)                 # x, y and both networks' parameters (previous optimizer step) are ready
+        with torch.cuda.stream(side):
+            o2 = model2(x)
+        o1 = model1(x)
+        cur.wait_stream(side)                 # join before the losses
+        o2.record_stream(cur)
     s1, s2 = torch.softmax(o1, dim=1), torch.softmax(o2, dim=1)
     lb = labeled_bs
     loss1 = 0.5 * (F.cross_entropy(o1[:lb], y[:lb].long()) + dice(s1[:lb], y[:lb].unsqueeze(1)))

@@ -81,6 +81,41 @@ def test_training_step_captured_as_cuda_graph_matches_eager():
         assert abs(lg - le) <= 1e-5 * max(1.0, abs(le)), (lg, le)
 
 
+def test_semi_step_on_two_streams_matches_one_stream():
+    """workloads.semi_step(side=stream): the second network's forward (and, through autograd, its backward) runs on a second stream,
+    concurrently with the first one's.  Same losses and parameters as the single-stream step (drop path off: its random masks
+    are drawn in issue order, which differs), eager and captured as a CUDA graph."""
+    import copy
+
+    from selscan_b200 import workloads as wl
+    from selscan_b200.vssm import DiceLoss, MambaUnet
+
+    torch.manual_seed(3)
+    kw = dict(num_classes=4, depths=(1, 1, 1, 1), dims=(32, 64, 128, 256), drop_path_rate=0.0)
+    a0, b0 = MambaUnet(**kw).cuda().train(), MambaUnet(**kw).cuda().train()
+    dice, cw = DiceLoss(4), wl.consistency_weight(3000)
+    x = torch.rand(4, 1, 64, 64, device="cuda")
+    y = torch.randint(0, 4, (4, 64, 64), device="cuda")
+    runs = {}
+    for mode in ("one", "two", "two_graph"):
+        a, b = copy.deepcopy(a0), copy.deepcopy(b0)
+        oa, ob = wl.make_sgd(a), wl.make_sgd(b)
+        side = None if mode == "one" else torch.cuda.Stream()
+        step = lambda xx, yy: wl.semi_step(a, b, oa, ob, dice, xx, yy, 2, cw, side)   # noqa: E731
+        if mode == "two_graph":
+            step = wl.GraphedStep(step, x, y, warmup=2)      # two eager steps first (lazy optimizer state), then the capture
+            losses = [None, None] + [float(step(x, y).detach()) for _ in range(3)]
+        else:
+            losses = [float(step(x, y).detach()) for _ in range(5)]
+        torch.cuda.synchronize()
+        runs[mode] = (losses, [p.detach().clone() for p in list(a.parameters()) + list(b.parameters())])
+    for mode in ("two", "two_graph"):
+        for l1, l2 in zip(runs["one"][0], runs[mode][0]):
+            assert l2 is None or abs(l1 - l2) <= 2e-5 * max(1.0, abs(l1)), (mode, runs["one"][0], runs[mode][0])
+        for p1, p2 in zip(runs["one"][1], runs[mode][1]):
+            torch.testing.assert_close(p2, p1, rtol=1e-3, atol=2e-5)
+
+
 @pytest.mark.parametrize("B,D,H,W", [(2, 5, 7, 7), (1, 3, 4, 9), (2, 8, 56, 56), (3, 4, 14, 14)])
 def test_cross_scan_merge_kernels(B, D, H, W):
     """The plane kernels against the plain-torch statement of CrossScan / CrossMerge, forward and backward (bit-exact:

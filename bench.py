@@ -314,13 +314,16 @@ def model_leg(world, rank, dev, steps):
     # that a failed capture cannot disturb an eager number.
     cap_stream = torch.cuda.Stream(dev) if world > 1 else None
 
-    def ddp_on_stream(m):
+    def ddp_on_stream(m, stream=None):
+        """DDP wrapper constructed on `stream` (default: the capture stream): its reducer and AccumulateGrad nodes belong to the
+        stream the model's forwards will run on."""
         if world == 1:
             return m
-        cap_stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(cap_stream):
+        st = cap_stream if stream is None else stream
+        st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
             w = ddp(m)
-        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        torch.cuda.current_stream(dev).wait_stream(st)
         return w
 
     try:
@@ -359,12 +362,18 @@ def model_leg(world, rank, dev, steps):
         res["train_semi_dual_bs16"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw), n), 16)
         # the same step with the second network on a second stream: at 16 images per network most kernels under-fill a B200 (stage-1
         # scan: 192 CTAs on 296 slots), the two networks are independent until the losses
+        del m1, m2, o1, o2
+        torch.cuda.empty_cache()
         try:
             side = torch.cuda.Stream(dev)
-            res["train_semi_dual_bs16_2streams"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw, side), n), 16)
+            m1 = ddp(MambaUnet(num_classes=4).to(dev).train())
+            m2 = ddp_on_stream(MambaUnet(num_classes=4).to(dev).train(), side)      # (the second network lives on the second stream)
+            o1, o2 = wl.make_sgd(m1), wl.make_sgd(m2)
+            res["train_semi_dual_bs16_2streams"] = entry(timed(lambda: wl.semi_step(m1, m2, o1, o2, dice, x16, y16, 8, cw, side), n,
+                                                               warm=8 if world > 1 else 3), 16)    # (DDP's static graph settles in its first iterations)
+            del m1, m2, o1, o2
         except Exception as e:  # noqa: BLE001
             res["train_semi_dual_bs16_2streams"] = {"unavailable": repr(e)[:200]}
-        del m1, m2, o1, o2
         torch.cuda.empty_cache()
 
         # ---- the same steps replayed as ONE CUDA graph each (fresh models: under DDP the wrapper must be built on the capture stream) ----
@@ -380,9 +389,9 @@ def model_leg(world, rank, dev, steps):
 
         def semi_factory(two_streams=False):
             def make():
-                a, b = ddp_on_stream(MambaUnet(num_classes=4).to(dev).train()), ddp_on_stream(MambaUnet(num_classes=4).to(dev).train())
-                oa, ob = wl.make_sgd(a), wl.make_sgd(b)
                 side = torch.cuda.Stream(dev) if two_streams else None
+                a, b = ddp_on_stream(MambaUnet(num_classes=4).to(dev).train()), ddp_on_stream(MambaUnet(num_classes=4).to(dev).train(), side)
+                oa, ob = wl.make_sgd(a), wl.make_sgd(b)
                 return lambda x, y: wl.semi_step(a, b, oa, ob, dice, x, y, 8, cw, side)
             return make
 

@@ -153,6 +153,7 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
   if (warp == kConsWarps) {
     // ================================ producer ================================
     const bool lanes_along_l = (a.B_l_stride == 1 && a.C_l_stride == 1);
+    const bool small_n_strides = a.B_n_stride >= 0 && a.B_n_stride < (1 << 26) && a.C_n_stride >= 0 && a.C_n_stride < (1 << 26);   // 16 * stride fits an int
     uint32_t it = 0;   // tiles issued by this CTA: ring position
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item w = decode_item<kMode>(p, item);
@@ -182,7 +183,22 @@ selscan_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_c
         }
         const uint32_t bc = sm0 + LY::oBC + (uint32_t)s * (kTL * kBCPitch * 4);
         float v[32];
-        if (lanes_along_l) {  // (.., N, L) layout: a warp reads 128 contiguous bytes of one state row
+        if (lanes_along_l && N == kStatePad && l0 + kTL <= L && !rev && small_n_strides) {
+          // the common case (all 16 states, a full tile, forward direction): no bounds or direction arithmetic, one 32-bit
+          // multiply-add per address -- this warp's gather cost the forward ~6 % (what-if build), most of it instructions on the
+          // consumers' scheduler
+          const float* pb = Bg + l0 + lane;
+          const float* pc = Cg + l0 + lane;
+          const int sb = (int)a.B_n_stride, sc = (int)a.C_n_stride;
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            v[n] = __ldg(pb + n * sb);
+            v[16 + n] = __ldg(pc + n * sc);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            sts_f4(bc + (uint32_t)(lane * kBCPitch + i) * 4, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        } else if (lanes_along_l) {  // (.., N, L) layout: a warp reads 128 contiguous bytes of one state row
           const int l = l0 + lane;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {

@@ -418,7 +418,8 @@ def model_leg(world, rank, dev, steps):
         ss2d.TC_PROJ = tc_default
     res["note"] = ("img/s is the whole-job aggregate over %d GPU(s); per-GPU batch fixed (weak scaling); DDP (static_graph, "
                    "gradient_as_bucket_view, bucket_cap_mb=%g) gradient all-reduce over NCCL when n_gpus > 1 (19.1 M fp32 gradients per "
-                   "model); default arm: ss2d.TC_PROJ=%s" % (world, bucket_mb, tc_default))
+                   "model); default arm: ss2d.TC_PROJ=%s; *_2streams: the second network of the dual-network step runs on a second CUDA "
+                   "stream (workloads.semi_step(side=...)), same arithmetic" % (world, bucket_mb, tc_default))
     return res
 
 
